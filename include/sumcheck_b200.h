@@ -1,0 +1,210 @@
+/*
+ * sumcheck_b200.h -- C ABI of libsumcheck_b200.so, the B200-native drop-in for the sum-check
+ * prover hot path of montekki/thaler-study.
+ *
+ * The reference has no FFI; its one extension point is the Rust trait
+ *   sum_check_protocol::SumCheckPolynomial<F>      (sum-check-protocol/src/lib.rs:121-156)
+ * which Prover/Verifier (:73-117, :227-331), fiat-shamir (fiat-shamir/src/lib.rs:44-98) and the GKR
+ * prover (gkr-protocol/src/lib.rs:335,426,446,453) are generic over.  The entry points below are
+ * what a Rust `impl SumCheckPolynomial<F> for GpuPoly<F>` binds (see INTEGRATION.md and
+ * rust/sumcheck-b200/src/lib.rs); each one cites the reference interface it replaces.
+ *
+ * Data format across the boundary: ark-ff's in-memory Fp -- n_limbs little-endian uint64_t limbs
+ * per element, MONTGOMERY form with R = 2^(64 n_limbs), value < p -- so a Rust `&[F]` crosses as
+ * `(const uint64_t*, len)` with no conversion.  Host buffers unless a name says `_device`.
+ *
+ * Conventions: every function returns SCB_OK (0) or a negative scb_status; the message is kept in a
+ * thread-local string (scb_last_error).  Nothing throws or aborts across the boundary.  A handle is
+ * not thread-safe; distinct handles may be used from distinct threads.  Calls are synchronous with
+ * respect to their host outputs; device work is ordered on the library's current stream
+ * (scb_set_stream; default = the legacy default stream, which is also torch's default stream).
+ * There is no CPU fallback: without a CUDA device every compute call returns SCB_ECUDA.
+ */
+#ifndef SUMCHECK_B200_H
+#define SUMCHECK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum scb_status {
+    SCB_OK = 0,
+    SCB_EINVAL = -1,   /* bad argument / dimension mismatch (Rust shim maps it to `None`, :126) */
+    SCB_ENOMEM = -2,
+    SCB_ECUDA = -3,    /* CUDA runtime error or no device */
+    SCB_ENCCL = -4,    /* reserved for the multi-GPU exchange */
+    SCB_EVERIFY = -5,  /* sum_check_protocol::Error::ProverClaimMismatch (:26-27) */
+    SCB_ENOPOLY = -6   /* sum_check_protocol::Error::NoPolySet (:29-30) */
+} scb_status;
+
+typedef struct scb_field scb_field;       /* a prime field (MontConfig of the reference, e.g. :349-354) */
+typedef struct scb_mle scb_mle;           /* [ARK] DenseMultilinearExtension<F>, table resident in HBM */
+typedef struct scb_poly scb_poly;         /* an implementor of SumCheckPolynomial<F> */
+typedef struct scb_prover scb_prover;     /* sum_check_protocol::Prover<F,P>   (:73-117) */
+typedef struct scb_verifier scb_verifier; /* sum_check_protocol::Verifier<F,P> (:227-331) */
+
+/* ------------------------------------------------------------------ library / device */
+const char* scb_last_error(void);
+const char* scb_version(void);
+int scb_device_count(int* out);
+int scb_set_stream(void* cuda_stream);    /* cudaStream_t; NULL = legacy default stream */
+int scb_synchronize(void);
+/* number of kernels this library launched since load / last reset (bench.py's gpu_launches) */
+int scb_launch_count(uint64_t* out, int reset);
+
+/* ------------------------------------------------------------------ field (a11) */
+/* replaces #[derive(MontConfig)] #[modulus = ..] + Fp64<MontBackend<_,1>> (sum-check-protocol/src/lib.rs:349-354);
+ * n_limbs in {1, 4}; derives -p^-1 mod 2^64, R, R^2 */
+int scb_field_create(uint32_t n_limbs, const uint64_t* modulus_le, scb_field** out);
+void scb_field_free(scb_field* f);
+int scb_field_n_limbs(const scb_field* f, uint32_t* out);
+int scb_field_modulus_bits(const scb_field* f, uint32_t* out);
+/* 0 = small-prime 32-bit path (p < 2^28), 1 = generic 1 limb, 4 = 4 limbs */
+int scb_field_policy(const scb_field* f, uint32_t* out);
+/* host helpers: canonical integer limbs <-> Montgomery limbs (F::from_bigint / into_bigint) */
+int scb_field_to_mont(const scb_field* f, const uint64_t* canonical, uint64_t* mont, size_t count);
+int scb_field_from_mont(const scb_field* f, const uint64_t* mont, uint64_t* canonical, size_t count);
+
+/* ------------------------------------------------------------------ dense MLE (a4, a10) */
+/* DenseMultilinearExtension::from_evaluations_vec / _slice (matrix-multiplication/src/lib.rs:81,85) */
+int scb_mle_from_host(const scb_field* f, uint32_t num_vars, const uint64_t* evals, scb_mle** out);
+/* table already in HBM: copy != 0 copies it, copy == 0 borrows the pointer (caller keeps it alive,
+ * 32-byte aligned) */
+int scb_mle_from_device(const scb_field* f, uint32_t num_vars, const uint64_t* d_evals, int copy, scb_mle** out);
+/* synthetic uniform table generated on the device: entry i = stream(seed, start + i) */
+int scb_mle_synthetic(const scb_field* f, uint32_t num_vars, uint64_t seed, uint64_t start, scb_mle** out);
+int scb_mle_clone(const scb_mle* m, scb_mle** out);          /* #[derive(Clone)]; O(1), shares the table */
+void scb_mle_free(scb_mle* m);
+int scb_mle_num_vars(const scb_mle* m, uint32_t* out);
+int scb_mle_device_ptr(const scb_mle* m, const uint64_t** out);
+/* [ARK] fix_variables(partial_point): t[b] = t[2b] + r (t[2b+1] - t[2b]) per coordinate, variable 0 =
+ * index LSB (called at matrix-multiplication/src/lib.rs:83,86,104-105) */
+int scb_mle_fix_variables(const scb_mle* m, const uint64_t* partial_point, uint32_t n_point, scb_mle** out);
+/* [ARK] Polynomial::evaluate(point) = fix_variables(point)[0], LSB-first (matrix-multiplication/src/lib.rs:97-98) */
+int scb_mle_evaluate(const scb_mle* m, const uint64_t* point, uint32_t n_point, uint64_t* out_elem);
+/* same value with the point in the big-endian order of multilinear-extensions (r[0] <-> index MSB) */
+int scb_mle_evaluate_be(const scb_mle* m, const uint64_t* r, uint32_t n_r, uint64_t* out_elem);
+/* [ARK] relabel(a, b, k) (matrix-multiplication/src/lib.rs:82) */
+int scb_mle_relabel(const scb_mle* m, uint32_t a, uint32_t b, uint32_t k, scb_mle** out);
+/* [ARK] to_evaluations(): device -> host copy of the 2^num_vars entries */
+int scb_mle_to_evaluations(const scb_mle* m, uint64_t* out, size_t cap_elems);
+/* device -> device copy of the table (stream-ordered; used to hand slabs to the multi-GPU exchange) */
+int scb_mle_copy_to_device(const scb_mle* m, uint64_t* d_out);
+
+/* ------------------------------------------------------------------ multilinear-extensions (a8, a9) */
+/* vsbw_multilinear_from_evaluations(evals, r)  multilinear-extensions/src/lib.rs:6-24 */
+int scb_vsbw_multilinear_from_evaluations(const scb_field* f, const uint64_t* evals, size_t n_evals, const uint64_t* r,
+                                          uint32_t n_r, uint64_t* out_elem);
+/* cti_multilinear_from_evaluations(evals, r)   multilinear-extensions/src/lib.rs:29-48 (same element) */
+int scb_cti_multilinear_from_evaluations(const scb_field* f, const uint64_t* evals, size_t n_evals, const uint64_t* r,
+                                         uint32_t n_r, uint64_t* out_elem);
+
+/* ------------------------------------------------------------------ SumCheckPolynomial implementors */
+typedef enum scb_poly_kind {
+    SCB_POLY_PRODUCT = 0,    /* ProductMLE<K>: K dense MLEs over the same variables (new impl) */
+    SCB_POLY_MATMUL_G = 1,   /* matrix_multiplication::G {f_a, f_b}   matrix-multiplication/src/lib.rs:12-15 */
+    SCB_POLY_TRIANGLE_G = 2, /* triangle_counting::G                  triangle-counting/src/lib.rs:22-27 */
+    SCB_POLY_GKR_W = 3       /* gkr_protocol::round_polynomial::W     gkr-protocol/src/round_polynomial.rs:23-28 */
+} scb_poly_kind;
+
+int scb_poly_product(const scb_mle* const* tables, uint32_t k, scb_poly** out);
+int scb_poly_matmul_g(const scb_mle* f_a, const scb_mle* f_b, scb_poly** out);
+/* G::new(n, a, b, point)  matrix-multiplication/src/lib.rs:77-92: a, b = row-major n x n matrices
+ * (2^(2n) elements each), point = 2n elements */
+int scb_poly_matmul_g_new(const scb_field* f, uint32_t n, const uint64_t* a, const uint64_t* b, const uint64_t* point,
+                          scb_poly** out);
+/* G::new_adj_matrix(num_vars, matrix)  triangle-counting/src/lib.rs:32-51: adj = 2^num_vars bytes (0/1) */
+int scb_poly_triangle_g_new(const scb_field* f, uint32_t num_vars, const uint8_t* adj, scb_poly** out);
+/* W::new(add_i, mul_i, w_b, w_c)  gkr-protocol/src/round_polynomial.rs:32-44 */
+int scb_poly_gkr_w(const scb_mle* add_i, const scb_mle* mul_i, const scb_mle* w_b, const scb_mle* w_c, scb_poly** out);
+int scb_poly_clone(const scb_poly* p, scb_poly** out);
+void scb_poly_free(scb_poly* p);
+int scb_poly_kind_of(const scb_poly* p, uint32_t* out);
+int scb_poly_n_tables(const scb_poly* p, uint32_t* out);
+int scb_poly_table(const scb_poly* p, uint32_t idx, scb_mle** out); /* clone of table idx */
+/* number of points of a round message (degree bound + 1) */
+int scb_poly_n_points(const scb_poly* p, uint32_t* out);
+
+/* trait methods, sum-check-protocol/src/lib.rs:121-156 */
+int scb_poly_evaluate(const scb_poly* p, const uint64_t* point, uint32_t n_point, uint64_t* out_elem);  /* :126 */
+int scb_poly_fix_variables(const scb_poly* p, const uint64_t* partial_point, uint32_t n_point, scb_poly** out); /* :130 */
+int scb_poly_num_vars(const scb_poly* p, uint32_t* out);                                                /* :151 */
+int scb_poly_to_evaluations(const scb_poly* p, uint64_t* out, size_t cap_elems);                        /* :155 */
+/* to_univariate (:148) as (degree, coefficient) terms of the univariate::SparsePolynomial */
+int scb_poly_to_univariate(const scb_poly* p, uint64_t* degrees, uint64_t* coeffs, uint32_t cap_terms, uint32_t* n_terms);
+/* the device half of to_univariate: sums over the hypercube of the remaining variables at
+ * X = 0 .. n_points-1 (matrix-multiplication/src/lib.rs:110-122) */
+int scb_poly_round_evals(const scb_poly* p, uint32_t n_points, uint64_t* out_elems);
+/* c_1 = to_evaluations().into_iter().sum() without the 2^v-entry host Vec (Prover::new, :89) */
+int scb_poly_sum(const scb_poly* p, uint64_t* out_elem);
+/* fused `g = g.fix_variables(&[r]); g.to_univariate()` of Prover::round (:105-112): one pass */
+int scb_poly_fix_and_round_evals(const scb_poly* p, const uint64_t* r, uint32_t n_points, scb_poly** out,
+                                 uint64_t* out_elems);
+/* sharded / device-resident variant: the partial sums stay on the device (n_points elements at
+ * d_out) so that the per-round exchange of the multi-GPU prover never touches the host */
+int scb_poly_round_evals_device(const scb_poly* p, uint32_t n_points, uint64_t* d_out);
+int scb_poly_fix_and_round_evals_device(const scb_poly* p, const uint64_t* r, uint32_t n_points, scb_poly** out,
+                                        uint64_t* d_out);
+
+/* ------------------------------------------------------------------ round-message algebra (host) */
+/* (d+1) sums at X = 0..d  ->  the SparsePolynomial the reference would send, per implementor:
+ * MATMUL_G: interpolate_quadratic_poly (matrix-multiplication/src/lib.rs:17-60, explicit zero terms kept);
+ * others: unique interpolant, Dense -> Sparse (triangle-counting/src/lib.rs:128-131) */
+int scb_evals_to_univariate(const scb_field* f, uint32_t kind, const uint64_t* evals, uint32_t n_points, uint64_t* degrees,
+                            uint64_t* coeffs, uint32_t cap_terms, uint32_t* n_terms);
+/* SparsePolynomial::serialize_uncompressed (fiat-shamir/src/lib.rs:58) */
+int scb_unipoly_serialize(const scb_field* f, const uint64_t* degrees, const uint64_t* coeffs, uint32_t n_terms, uint8_t* out,
+                          size_t cap, size_t* out_len);
+int scb_unipoly_evaluate(const scb_field* f, const uint64_t* degrees, const uint64_t* coeffs, uint32_t n_terms,
+                         const uint64_t* x, uint64_t* out_elem);
+/* DefaultFieldHasher<Sha256>::new(&[]).hash_to_field::<1>(msg)[0] (fiat-shamir/src/lib.rs:78,88) */
+int scb_hash_to_field(const scb_field* f, const uint8_t* msg, size_t len, uint64_t* out_elem);
+
+/* ------------------------------------------------------------------ Prover / Verifier */
+int scb_prover_new(const scb_poly* g, scb_prover** out);                   /* Prover::new  :88-97 */
+void scb_prover_free(scb_prover* p);
+int scb_prover_c_1(const scb_prover* p, uint64_t* out_elem);               /* :100-102 */
+int scb_prover_num_vars(const scb_prover* p, uint32_t* out);               /* :114-116 */
+/* Prover::round(r_prev, j) :105-112 (r_prev ignored when j == 0) */
+int scb_prover_round(scb_prover* p, const uint64_t* r_prev, uint32_t j, uint64_t* degrees, uint64_t* coeffs,
+                     uint32_t cap_terms, uint32_t* n_terms);
+
+/* Verifier::new(n, g) :261-269; g may be NULL (no oracle access) */
+int scb_verifier_new(const scb_field* f, uint32_t n, const scb_poly* g, scb_verifier** out);
+void scb_verifier_free(scb_verifier* v);
+int scb_verifier_set_c_1(scb_verifier* v, const uint64_t* c_1);            /* :271-273 */
+/* Verifier::round(g_j, rng) :278-330 with rng.draw() == r_j.  *final_round = 1 and *accepted set on the
+ * last round (VerifierRoundResult::FinalRound), else *final_round = 0 (JthRound(r_j)).
+ * SCB_EVERIFY = ProverClaimMismatch, SCB_ENOPOLY = NoPolySet. */
+int scb_verifier_round(scb_verifier* v, const uint64_t* degrees, const uint64_t* coeffs, uint32_t n_terms, const uint64_t* r_j,
+                       int* final_round, int* accepted);
+
+/* ------------------------------------------------------------------ fiat-shamir */
+/* generate_transcript::<F, Prover<F,P>, DefaultFieldHasher<Sha256>>(prover)  fiat-shamir/src/lib.rs:75-98.
+ * Consumes the prover's rounds.  out = g_1 || g_2 || ...; offsets[i]..offsets[i+1] delimits message i
+ * (offsets has num_vars + 1 entries). */
+int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t cap, size_t* out_len, uint64_t* offsets);
+/* verify_transcript(transcript, verifier)  fiat-shamir/src/lib.rs:123-143 */
+int scb_fs_verify_transcript(scb_verifier* v, const uint8_t* transcript, const uint64_t* offsets, uint32_t n_msgs,
+                             int* accepted);
+
+/* The same hash chain as an explicit state machine, for provers whose round sums arrive in pieces (the sharded
+ * multi-GPU prover: one row of (d+1) partial sums per rank).  absorb_round adds the n_parts rows mod p, turns the
+ * sums into the implementor's SparsePolynomial, appends its serialization (the first message is prefixed with
+ * c_1 = g_1(0) + g_1(1), fiat-shamir/src/lib.rs:48-50) and returns r = hash_to_field(all bytes so far) (:88). */
+typedef struct scb_transcript scb_transcript;
+int scb_transcript_new(const scb_field* f, uint32_t kind, scb_transcript** out);
+void scb_transcript_free(scb_transcript* t);
+int scb_transcript_absorb_round(scb_transcript* t, const uint64_t* parts, uint32_t n_parts, uint32_t n_points, uint64_t* out_r);
+int scb_transcript_c_1(const scb_transcript* t, uint64_t* out_elem);
+/* out == NULL: size query (out_len, n_msgs) */
+int scb_transcript_bytes(const scb_transcript* t, uint8_t* out, size_t cap, size_t* out_len, uint64_t* offsets, uint32_t cap_msgs,
+                         uint32_t* n_msgs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUMCHECK_B200_H */

@@ -1,0 +1,107 @@
+"""CPU-only checks of the C ABI: the library loads, exports every symbol the header declares, and its HOST
+protocol layer (field conversion, interpolation to SparsePolynomial, serialization, hash-to-field) agrees with
+the Python oracle.  No device compute is called here."""
+import os
+import random
+import re
+
+import pytest
+
+from oracle import pyoracle as O
+
+import thaler_study_b200 as T
+from thaler_study_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIELDS = [O.FP5, O.FP389, O.FP1572869, O.Field((1 << 61) - 1), O.Field(0xFFFFFFFF00000001), O.BLS12_381_FR]
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "sumcheck_b200.h")).read()
+    declared = set(re.findall(r"\b(scb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(_lib.lib, name), name
+    assert b"sm_100a" in _lib.lib.scb_version()
+
+
+def test_no_cpu_fallback_without_device():
+    if T.device_count() > 0:
+        pytest.skip("a device is present")
+    F = T.Field(1572869)
+    with pytest.raises(T.ScbError) as ei:
+        T.DenseMultilinearExtension.from_evaluations_vec(F, 2, [1, 2, 3, 4])
+    assert ei.value.code == _lib.SCB_ECUDA
+
+
+def test_field_create_rejects_bad_moduli():
+    for bad in (4, 0, 1):
+        with pytest.raises(T.ScbError):
+            T.Field(bad)
+
+
+@pytest.mark.parametrize("OF", FIELDS, ids=lambda F: f"p{F.bits}")
+def test_montgomery_representation_is_arks(OF):
+    F = T.Field(OF.p)
+    rnd = random.Random(3)
+    vals = [0, 1, OF.p - 1] + [rnd.randrange(OF.p) for _ in range(50)]
+    m = F.to_mont(vals)
+    assert F.unpack_raw(m) == [OF.to_mont(v) for v in vals]
+    assert F.from_mont(m) == vals
+    assert F.policy == (4 if OF.n_limbs == 4 else (0 if OF.bits <= 28 else 1))
+
+
+@pytest.mark.parametrize("OF", FIELDS, ids=lambda F: f"p{F.bits}")
+def test_hash_to_field_matches_oracle(OF):
+    F = T.Field(OF.p)
+    rnd = random.Random(5)
+    for ln in (0, 1, 17, 31, 32, 33, 55, 56, 63, 64, 65, 200, 1000):
+        msg = bytes(rnd.randrange(256) for _ in range(ln))
+        assert F.hash_to_field(msg) == O.hash_to_field(OF, msg), ln
+
+
+@pytest.mark.parametrize("OF", FIELDS, ids=lambda F: f"p{F.bits}")
+def test_evals_to_univariate_and_serialization(OF):
+    F = T.Field(OF.p)
+    rnd = random.Random(7)
+    cases3 = [[0, 0, 0], [0, 3 % OF.p, 0], [0, 0, 1], [1, 0, 0], [2 % OF.p, 2 % OF.p, 2 % OF.p], [0, 1, 2 % OF.p]]
+    cases3 += [[rnd.randrange(OF.p) for _ in range(3)] for _ in range(40)]
+    if OF.p == 5:
+        cases3 = [[a, b, c] for a in range(5) for b in range(5) for c in range(5)]
+    for ev in cases3:
+        # matrix_multiplication::G -- interpolate_quadratic_poly incl. explicit zero terms
+        want = O.interpolate_quadratic_poly(OF, list(zip([0, 1, 2 % OF.p], ev)))
+        got = T.evals_to_univariate(F, T.KIND_MATMUL_G, ev)
+        assert got.coeffs == want.coeffs, ev
+        assert got.serialize_uncompressed() == want.serialize()
+        # triangle / GKR / ProductMLE<2>: Dense -> Sparse
+        want2 = O.SparsePoly.from_dense(OF, O.lagrange_to_coeffs(OF, ev))
+        for kind in (T.KIND_PRODUCT, T.KIND_TRIANGLE_G, T.KIND_GKR_W):
+            got2 = T.evals_to_univariate(F, kind, ev)
+            assert got2.coeffs == want2.coeffs, ev
+            assert got2.serialize_uncompressed() == want2.serialize()
+        x = rnd.randrange(OF.p)
+        assert got.evaluate(x) == want.evaluate(x)
+    for npts in (2, 4, 5):
+        if npts > OF.p:
+            continue
+        for _ in range(20):
+            ev = [rnd.randrange(OF.p) for _ in range(npts)]
+            want = O.SparsePoly.from_dense(OF, O.lagrange_to_coeffs(OF, ev))
+            got = T.evals_to_univariate(F, T.KIND_PRODUCT, ev)
+            assert got.coeffs == want.coeffs
+            assert [got.evaluate(i) for i in range(npts)] == ev
+
+
+def test_domain4_interpolation_equals_lagrange_on_0_1_2():
+    # the engine samples X = 0,1,2 where the reference samples the 4th roots of unity
+    # (triangle-counting/src/lib.rs:121-131): same polynomial, same coefficients.
+    rnd = random.Random(9)
+    for OF in (O.FP5, O.FP389, O.FP1572869):
+        for _ in range(30):
+            coeffs = [rnd.randrange(OF.p) for _ in range(3)]
+            f = lambda x: sum(c * pow(x, i, OF.p) for i, c in enumerate(coeffs)) % OF.p
+            dom = O.interpolate_domain4(OF, [f(e) for e in O.domain4_elements(OF)])
+            lag = O.lagrange_to_coeffs(OF, [f(0), f(1), f(2)])
+            assert dom == lag

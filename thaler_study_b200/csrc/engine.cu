@@ -1,0 +1,931 @@
+// engine.cu -- level 1 of the C ABI (include/sumcheck_b200.h): fields, HBM-resident dense MLEs and
+// the SumCheckPolynomial implementors, on top of the kernels in kernels.cuh.
+//
+// There is NO CPU fallback in this file: every compute entry point needs a CUDA device and returns
+// SCB_ECUDA without one.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "internal.hpp"
+#include "kernels.cuh"
+#include "sumcheck_b200.h"
+
+using namespace scb;
+
+// ------------------------------------------------------------------------------------------ errors
+namespace scb {
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+}  // namespace scb
+
+#define CU_TRY(expr)                                                                          \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return SCB_ECUDA;                                                                 \
+        }                                                                                     \
+    } while (0)
+#define ARG_TRY(cond, msg)        \
+    do {                          \
+        if (!(cond)) {            \
+            set_error("%s", msg); \
+            return SCB_EINVAL;    \
+        }                         \
+    } while (0)
+#define RC_TRY(expr)                 \
+    do {                             \
+        int rc__ = (expr);           \
+        if (rc__ != SCB_OK) return rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ context
+static thread_local cudaStream_t g_stream = 0;
+static std::atomic<uint64_t> g_launches{0};
+
+struct Ctx {
+    int dev = -1;
+    int sms = 0;
+    uint64_t* partials = nullptr;  // per-block partial sums
+    unsigned int* ticket = nullptr;
+    uint64_t* h_res = nullptr;     // mapped pinned host memory: kernels write round sums here directly
+    uint64_t* d_scratch = nullptr; // small device scratch (points, results)
+};
+static constexpr int kMaxGrid = 148 * 16;
+static constexpr int kMaxDev = 16;
+static Ctx g_ctx[kMaxDev];
+static std::mutex g_ctx_mu;
+
+static int get_ctx(Ctx** out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        set_error("no CUDA device available: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+        return SCB_ECUDA;
+    }
+    ARG_TRY(dev >= 0 && dev < kMaxDev, "device index out of range");
+    Ctx& c = g_ctx[dev];
+    if (c.dev < 0) {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        if (c.dev < 0) {
+            int sms = 0;
+            CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            cudaMemPool_t pool;
+            CU_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+            uint64_t thr = UINT64_MAX;  // keep freed table buffers cached in the pool (ping-pong folds)
+            CU_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+            CU_TRY(cudaMalloc(&c.partials, (size_t)kMaxGrid * kMaxPts * kMaxLimbs * 8));
+            CU_TRY(cudaMalloc(&c.ticket, 64));
+            CU_TRY(cudaMemset(c.ticket, 0, 64));
+            CU_TRY(cudaHostAlloc(&c.h_res, 4096, cudaHostAllocMapped | cudaHostAllocPortable));
+            CU_TRY(cudaMalloc(&c.d_scratch, 64 * 1024));
+            c.sms = sms;
+            c.dev = dev;
+        }
+    }
+    *out = &c;
+    return SCB_OK;
+}
+
+static inline int grid_for(const Ctx* c, uint64_t items, int blocks_per_sm = 8) {
+    uint64_t want = (items + kThreads - 1) / kThreads;
+    uint64_t cap = (uint64_t)c->sms * blocks_per_sm;
+    if (cap > (uint64_t)kMaxGrid) cap = kMaxGrid;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+#define LAUNCH_CHECK()                                                                      \
+    do {                                                                                    \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                 \
+        cudaError_t e__ = cudaGetLastError();                                               \
+        if (e__ != cudaSuccess) {                                                           \
+            set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return SCB_ECUDA;                                                               \
+        }                                                                                   \
+    } while (0)
+
+// policy dispatch: binds `A` to the arithmetic policy of the field
+#define DISPATCH_POLICY(pol, ...)                              \
+    switch (pol) {                                             \
+        case POL_SP: { using A = PolSP; __VA_ARGS__; } break;   \
+        case POL_G1: { using A = PolG1; __VA_ARGS__; } break;   \
+        case POL_G4: { using A = PolGN<4>; __VA_ARGS__; } break; \
+        default: set_error("unsupported field policy"); return SCB_EINVAL; \
+    }
+#define DISPATCH_K(kk, ...)                                   \
+    switch (kk) {                                             \
+        case 1: { constexpr int K = 1; __VA_ARGS__; } break;  \
+        case 2: { constexpr int K = 2; __VA_ARGS__; } break;  \
+        case 3: { constexpr int K = 3; __VA_ARGS__; } break;  \
+        case 4: { constexpr int K = 4; __VA_ARGS__; } break;  \
+        default: set_error("number of tables must be 1..4"); return SCB_EINVAL; \
+    }
+
+// ------------------------------------------------------------------------------------------ buffers
+struct DevBuf {
+    uint64_t* ptr = nullptr;
+    size_t bytes = 0;
+    bool owned = false;
+    cudaStream_t stream = 0;
+    ~DevBuf() {
+        if (owned && ptr) cudaFreeAsync(ptr, stream);
+    }
+};
+typedef std::shared_ptr<DevBuf> BufRef;
+
+static int alloc_buf(size_t bytes, BufRef* out) {
+    auto b = std::make_shared<DevBuf>();
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, bytes < 32 ? 32 : bytes, g_stream);
+    if (e != cudaSuccess) {
+        set_error("cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? SCB_ENOMEM : SCB_ECUDA;
+    }
+    b->ptr = (uint64_t*)p;
+    b->bytes = bytes;
+    b->owned = true;
+    b->stream = g_stream;
+    *out = b;
+    return SCB_OK;
+}
+
+struct Table {
+    uint32_t nv = 0;
+    BufRef buf;
+    uint64_t len() const { return 1ull << nv; }
+};
+
+struct scb_mle {
+    std::shared_ptr<FieldImpl> f;
+    Table t;
+};
+
+struct scb_poly {
+    uint32_t kind = 0;
+    std::shared_ptr<FieldImpl> f;
+    std::vector<Table> t;
+    uint32_t var_len = 0;  // triangle_counting::G::var_len
+};
+
+static ElemArg elem_arg(const FieldImpl& f, const uint64_t* w) {
+    ElemArg a;
+    for (int i = 0; i < kMaxLimbs; ++i) a.w[i] = i < (int)f.d.n ? w[i] : 0;
+    return a;
+}
+static bool elem_canonical(const FieldImpl& f, const uint64_t* w) {
+    Fe e;
+    f.h.load(w, e);
+    return f.h.is_canonical(e);
+}
+
+// ------------------------------------------------------------------------------------------ library
+extern "C" const char* scb_last_error(void) { return g_err.c_str(); }
+extern "C" const char* scb_version(void) { return "sumcheck_b200 0.1 (sm_100a)"; }
+extern "C" int scb_device_count(int* out) {
+    ARG_TRY(out, "null out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *out = n;
+    return SCB_OK;
+}
+extern "C" int scb_set_stream(void* s) {
+    g_stream = (cudaStream_t)s;
+    return SCB_OK;
+}
+extern "C" int scb_synchronize(void) {
+    CU_TRY(cudaStreamSynchronize(g_stream));
+    return SCB_OK;
+}
+extern "C" int scb_launch_count(uint64_t* out, int reset) {
+    ARG_TRY(out, "null out");
+    *out = reset ? g_launches.exchange(0) : g_launches.load();
+    return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ field
+extern "C" int scb_field_create(uint32_t n_limbs, const uint64_t* modulus, scb_field** out) {
+    ARG_TRY(modulus && out, "null argument");
+    ARG_TRY(n_limbs == 1 || n_limbs == 4, "n_limbs must be 1 or 4");
+    auto impl = std::make_shared<FieldImpl>();
+    try {
+        impl->h = HostField(n_limbs, modulus);
+    } catch (const std::exception& ex) {
+        set_error("scb_field_create: %s", ex.what());
+        return SCB_EINVAL;
+    }
+    std::memset(&impl->d, 0, sizeof impl->d);
+    for (uint32_t i = 0; i < n_limbs; ++i) {
+        impl->d.p[i] = impl->h.p[i];
+        impl->d.one[i] = impl->h.one_.l[i];
+        impl->d.r2[i] = impl->h.r2_.l[i];
+    }
+    impl->d.inv = impl->h.inv;
+    impl->d.n = n_limbs;
+    impl->d.bits = impl->h.bits;
+    impl->policy = n_limbs == 4 ? POL_G4 : (impl->h.bits <= 28 ? POL_SP : POL_G1);
+    *out = new scb_field{impl};
+    return SCB_OK;
+}
+extern "C" void scb_field_free(scb_field* f) { delete f; }
+extern "C" int scb_field_n_limbs(const scb_field* f, uint32_t* out) {
+    ARG_TRY(f && out, "null argument");
+    *out = f->impl->d.n;
+    return SCB_OK;
+}
+extern "C" int scb_field_modulus_bits(const scb_field* f, uint32_t* out) {
+    ARG_TRY(f && out, "null argument");
+    *out = f->impl->d.bits;
+    return SCB_OK;
+}
+extern "C" int scb_field_policy(const scb_field* f, uint32_t* out) {
+    ARG_TRY(f && out, "null argument");
+    *out = f->impl->policy;
+    return SCB_OK;
+}
+extern "C" int scb_field_to_mont(const scb_field* f, const uint64_t* canonical, uint64_t* mont, size_t count) {
+    ARG_TRY(f && canonical && mont, "null argument");
+    const HostField& h = f->impl->h;
+    for (size_t i = 0; i < count; ++i) {
+        Fe e;
+        h.load(canonical + i * h.n, e);
+        ARG_TRY(h.is_canonical(e), "scb_field_to_mont: value >= modulus");
+        h.store(h.to_mont(e), mont + i * h.n);
+    }
+    return SCB_OK;
+}
+extern "C" int scb_field_from_mont(const scb_field* f, const uint64_t* mont, uint64_t* canonical, size_t count) {
+    ARG_TRY(f && canonical && mont, "null argument");
+    const HostField& h = f->impl->h;
+    for (size_t i = 0; i < count; ++i) {
+        Fe e;
+        h.load(mont + i * h.n, e);
+        h.store(h.from_mont(e), canonical + i * h.n);
+    }
+    return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ MLE
+static int mle_new(const std::shared_ptr<FieldImpl>& f, uint32_t nv, scb_mle** out, bool alloc) {
+    ARG_TRY(nv <= 40, "num_vars too large");
+    auto m = std::make_unique<scb_mle>();
+    m->f = f;
+    m->t.nv = nv;
+    if (alloc) RC_TRY(alloc_buf((size_t)8 * f->d.n << nv, &m->t.buf));
+    *out = m.release();
+    return SCB_OK;
+}
+
+extern "C" int scb_mle_from_host(const scb_field* f, uint32_t num_vars, const uint64_t* evals, scb_mle** out) {
+    ARG_TRY(f && evals && out, "null argument");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    scb_mle* m = nullptr;
+    RC_TRY(mle_new(f->impl, num_vars, &m, true));
+    cudaError_t e = cudaMemcpyAsync(m->t.buf->ptr, evals, m->t.buf->bytes, cudaMemcpyHostToDevice, g_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);  // the caller may reuse `evals` on return
+    if (e != cudaSuccess) {
+        delete m;
+        set_error("H2D copy failed: %s", cudaGetErrorString(e));
+        return SCB_ECUDA;
+    }
+    *out = m;
+    return SCB_OK;
+}
+extern "C" int scb_mle_from_device(const scb_field* f, uint32_t num_vars, const uint64_t* d_evals, int copy, scb_mle** out) {
+    ARG_TRY(f && d_evals && out, "null argument");
+    ARG_TRY(((uintptr_t)d_evals & 31) == 0, "device table must be 32-byte aligned");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    scb_mle* m = nullptr;
+    RC_TRY(mle_new(f->impl, num_vars, &m, copy != 0));
+    if (copy) {
+        cudaError_t e = cudaMemcpyAsync(m->t.buf->ptr, d_evals, m->t.buf->bytes, cudaMemcpyDeviceToDevice, g_stream);
+        if (e != cudaSuccess) {
+            delete m;
+            set_error("D2D copy failed: %s", cudaGetErrorString(e));
+            return SCB_ECUDA;
+        }
+    } else {
+        m->t.buf = std::make_shared<DevBuf>();
+        m->t.buf->ptr = const_cast<uint64_t*>(d_evals);
+        m->t.buf->bytes = (size_t)8 * f->impl->d.n << num_vars;
+        m->t.buf->owned = false;
+    }
+    *out = m;
+    return SCB_OK;
+}
+extern "C" int scb_mle_synthetic(const scb_field* f, uint32_t num_vars, uint64_t seed, uint64_t start, scb_mle** out) {
+    ARG_TRY(f && out, "null argument");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    scb_mle* m = nullptr;
+    RC_TRY(mle_new(f->impl, num_vars, &m, true));
+    const uint64_t n = 1ull << num_vars;
+    if (f->impl->d.n == 1)
+        k_synth_fill<1><<<grid_for(c, n), kThreads, 0, g_stream>>>(f->impl->d, seed, start, n, m->t.buf->ptr);
+    else
+        k_synth_fill<4><<<grid_for(c, n), kThreads, 0, g_stream>>>(f->impl->d, seed, start, n, m->t.buf->ptr);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        delete m;
+        set_error("k_synth_fill launch failed: %s", cudaGetErrorString(e));
+        return SCB_ECUDA;
+    }
+    *out = m;
+    return SCB_OK;
+}
+extern "C" int scb_mle_clone(const scb_mle* m, scb_mle** out) {
+    ARG_TRY(m && out, "null argument");
+    *out = new scb_mle(*m);
+    return SCB_OK;
+}
+extern "C" void scb_mle_free(scb_mle* m) { delete m; }
+extern "C" int scb_mle_num_vars(const scb_mle* m, uint32_t* out) {
+    ARG_TRY(m && out, "null argument");
+    *out = m->t.nv;
+    return SCB_OK;
+}
+extern "C" int scb_mle_device_ptr(const scb_mle* m, const uint64_t** out) {
+    ARG_TRY(m && out, "null argument");
+    *out = m->t.buf->ptr;
+    return SCB_OK;
+}
+
+// one fold pass of one table (a4)
+static int fold_table(Ctx* c, const FieldImpl& f, const Table& in, const uint64_t* r, Table* out) {
+    ARG_TRY(in.nv >= 1, "cannot fix a variable of a 0-variable table");
+    ARG_TRY(elem_canonical(f, r), "challenge is not a canonical field element");
+    Table o;
+    o.nv = in.nv - 1;
+    RC_TRY(alloc_buf((size_t)8 * f.d.n << o.nv, &o.buf));
+    const uint64_t n_out = o.len();
+    const ElemArg ra = elem_arg(f, r);
+    DISPATCH_POLICY(f.policy, {
+        if (A::N == 1 && n_out >= 2) {
+            k_fold<A, (A::N == 1 ? 2 : 1)><<<grid_for(c, n_out / 2), kThreads, 0, g_stream>>>(f.d, in.buf->ptr, o.buf->ptr, ra, n_out / 2);
+        } else {
+            k_fold<A, 1><<<grid_for(c, n_out), kThreads, 0, g_stream>>>(f.d, in.buf->ptr, o.buf->ptr, ra, n_out);
+        }
+    });
+    LAUNCH_CHECK();
+    *out = o;
+    return SCB_OK;
+}
+static int fix_table(Ctx* c, const FieldImpl& f, const Table& in, const uint64_t* point, uint32_t n, Table* out) {
+    ARG_TRY(n <= in.nv, "invalid size of partial point");  // [ARK] assert in fix_variables
+    Table cur = in;
+    for (uint32_t i = 0; i < n; ++i) {
+        Table nxt;
+        RC_TRY(fold_table(c, f, cur, point + (size_t)i * f.d.n, &nxt));
+        cur = nxt;
+    }
+    *out = cur;
+    return SCB_OK;
+}
+
+extern "C" int scb_mle_fix_variables(const scb_mle* m, const uint64_t* partial_point, uint32_t n_point, scb_mle** out) {
+    ARG_TRY(m && out && (partial_point || n_point == 0), "null argument");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    Table t;
+    RC_TRY(fix_table(c, *m->f, m->t, partial_point, n_point, &t));
+    auto r = new scb_mle{m->f, t};
+    *out = r;
+    return SCB_OK;
+}
+
+// MLE evaluation through eq tables (K4).  bitpt[j] = coordinate bound to index bit j (host memory).
+// Result goes to host (h_out) or, if d_out != nullptr, stays on the device.
+static int eval_table(Ctx* c, const FieldImpl& f, const Table& t, const uint64_t* bitpt, uint64_t* h_out, uint64_t* d_out) {
+    const uint32_t v = t.nv, N = f.d.n;
+    ARG_TRY(v <= 34, "table too large for MLE evaluation");
+    for (uint32_t j = 0; j < v; ++j) ARG_TRY(elem_canonical(f, bitpt + (size_t)j * N), "point coordinate is not canonical");
+    const uint32_t lb_max = N == 1 ? 12 : 10;
+    const uint32_t lb = v < lb_max ? v : lb_max;
+    BufRef pt, lo, hi;
+    RC_TRY(alloc_buf((size_t)8 * N * (v ? v : 1), &pt));
+    RC_TRY(alloc_buf((size_t)8 * N << lb, &lo));
+    RC_TRY(alloc_buf((size_t)8 * N << (v - lb), &hi));
+    if (v) CU_TRY(cudaMemcpyAsync(pt->ptr, bitpt, (size_t)8 * N * v, cudaMemcpyHostToDevice, g_stream));
+    uint64_t* res = d_out ? d_out : c->h_res;
+    DISPATCH_POLICY(f.policy, {
+        k_eq_build<A><<<2, 1024, 0, g_stream>>>(f.d, pt->ptr, lb, v, lo->ptr, hi->ptr);
+        LAUNCH_CHECK();
+        const size_t smem = (size_t)8 * N << lb;
+        const uint64_t n = t.len();
+        if (A::N == 1 && lb >= 2) {
+            k_mle_dot<A, (A::N == 1 ? 4 : 1)><<<grid_for(c, n / 4), kThreads, smem, g_stream>>>(f.d, t.buf->ptr, lo->ptr, hi->ptr, lb, n / 4, c->partials, c->ticket, res);
+        } else {
+            k_mle_dot<A, 1><<<grid_for(c, n), kThreads, smem, g_stream>>>(f.d, t.buf->ptr, lo->ptr, hi->ptr, lb, n, c->partials, c->ticket, res);
+        }
+    });
+    LAUNCH_CHECK();
+    if (!d_out) {
+        CU_TRY(cudaStreamSynchronize(g_stream));
+        std::memcpy(h_out, c->h_res, 8 * N);
+    }
+    return SCB_OK;
+}
+
+extern "C" int scb_mle_evaluate(const scb_mle* m, const uint64_t* point, uint32_t n_point, uint64_t* out_elem) {
+    ARG_TRY(m && out_elem && (point || n_point == 0), "null argument");
+    ARG_TRY(n_point == m->t.nv, "point dimension does not match num_vars");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    return eval_table(c, *m->f, m->t, point, out_elem, nullptr);  // LSB-first: bit j <-> point[j]
+}
+static int eval_table_be(Ctx* c, const FieldImpl& f, const Table& t, const uint64_t* r, uint64_t* out) {
+    const uint32_t v = t.nv, N = f.d.n;
+    std::vector<uint64_t> bitpt((size_t)N * (v ? v : 1));
+    for (uint32_t j = 0; j < v; ++j) std::memcpy(&bitpt[(size_t)j * N], r + (size_t)(v - 1 - j) * N, 8 * N);  // r[0] <-> MSB
+    return eval_table(c, f, t, bitpt.data(), out, nullptr);
+}
+extern "C" int scb_mle_evaluate_be(const scb_mle* m, const uint64_t* r, uint32_t n_r, uint64_t* out_elem) {
+    ARG_TRY(m && out_elem && (r || n_r == 0), "null argument");
+    ARG_TRY(n_r == m->t.nv, "point dimension does not match num_vars");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    return eval_table_be(c, *m->f, m->t, r, out_elem);
+}
+extern "C" int scb_mle_relabel(const scb_mle* m, uint32_t a, uint32_t b, uint32_t k, scb_mle** out) {
+    ARG_TRY(m && out, "null argument");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    if (a > b) std::swap(a, b);
+    if (a == b || k == 0) return scb_mle_clone(m, out);
+    ARG_TRY(b + k <= m->t.nv, "invalid relabel argument");
+    ARG_TRY(a + k <= b, "overlapped swap window is not allowed");
+    scb_mle* r = nullptr;
+    RC_TRY(mle_new(m->f, m->t.nv, &r, true));
+    const uint64_t n = m->t.len();
+    if (m->f->d.n == 1)
+        k_relabel<1><<<grid_for(c, n), kThreads, 0, g_stream>>>(m->t.buf->ptr, r->t.buf->ptr, n, a, b, k);
+    else
+        k_relabel<4><<<grid_for(c, n), kThreads, 0, g_stream>>>(m->t.buf->ptr, r->t.buf->ptr, n, a, b, k);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        delete r;
+        set_error("k_relabel launch failed: %s", cudaGetErrorString(e));
+        return SCB_ECUDA;
+    }
+    *out = r;
+    return SCB_OK;
+}
+static int table_to_host(const FieldImpl& f, const Table& t, uint64_t* out, size_t cap_elems) {
+    ARG_TRY(cap_elems >= t.len(), "output buffer too small");
+    CU_TRY(cudaMemcpyAsync(out, t.buf->ptr, (size_t)8 * f.d.n << t.nv, cudaMemcpyDeviceToHost, g_stream));
+    CU_TRY(cudaStreamSynchronize(g_stream));
+    return SCB_OK;
+}
+extern "C" int scb_mle_copy_to_device(const scb_mle* m, uint64_t* d_out) {
+    ARG_TRY(m && d_out, "null argument");
+    CU_TRY(cudaMemcpyAsync(d_out, m->t.buf->ptr, (size_t)8 * m->f->d.n << m->t.nv, cudaMemcpyDeviceToDevice, g_stream));
+    return SCB_OK;
+}
+extern "C" int scb_mle_to_evaluations(const scb_mle* m, uint64_t* out, size_t cap_elems) {
+    ARG_TRY(m && out, "null argument");
+    return table_to_host(*m->f, m->t, out, cap_elems);
+}
+
+// multilinear-extensions free functions: evals in host memory, r[0] <-> index MSB
+static int mle_eval_host_be(const scb_field* f, const uint64_t* evals, size_t n_evals, const uint64_t* r, uint32_t n_r, uint64_t* out) {
+    ARG_TRY(f && evals && out && (r || n_r == 0), "null argument");
+    ARG_TRY(n_r <= 34 && n_evals == ((size_t)1 << n_r), "evals.len() must be 2^r.len()");
+    scb_mle* m = nullptr;
+    RC_TRY(scb_mle_from_host(f, n_r, evals, &m));
+    int rc = scb_mle_evaluate_be(m, r, n_r, out);
+    scb_mle_free(m);
+    return rc;
+}
+extern "C" int scb_vsbw_multilinear_from_evaluations(const scb_field* f, const uint64_t* evals, size_t n_evals, const uint64_t* r,
+                                                     uint32_t n_r, uint64_t* out_elem) {
+    return mle_eval_host_be(f, evals, n_evals, r, n_r, out_elem);
+}
+extern "C" int scb_cti_multilinear_from_evaluations(const scb_field* f, const uint64_t* evals, size_t n_evals, const uint64_t* r,
+                                                    uint32_t n_r, uint64_t* out_elem) {
+    // same field element as the vsbw form (exact arithmetic); one kernel serves both
+    return mle_eval_host_be(f, evals, n_evals, r, n_r, out_elem);
+}
+
+// ------------------------------------------------------------------------------------------ polys
+static uint32_t tri_xn(const scb_poly* p) { return p->t[0].nv > p->var_len ? p->t[0].nv - p->var_len : 0; }   // :53-55
+static uint32_t tri_yn(const scb_poly* p) { return p->t[1].nv > p->var_len ? p->t[1].nv - p->var_len : 0; }   // :57-59
+static uint32_t tri_zn(const scb_poly* p) { return p->t[2].nv < p->var_len ? p->t[2].nv : p->var_len; }       // :61-67
+
+static uint32_t poly_num_vars(const scb_poly* p) {
+    switch (p->kind) {
+        case SCB_POLY_TRIANGLE_G: return tri_xn(p) + tri_yn(p) + tri_zn(p);  // triangle-counting/src/lib.rs:134-136
+        case SCB_POLY_GKR_W: return p->t[0].nv;                              // round_polynomial.rs:92-94
+        default: return p->t[0].nv;                                          // matrix-multiplication/src/lib.rs:133-135
+    }
+}
+static uint32_t poly_n_points(const scb_poly* p) {
+    switch (p->kind) {
+        case SCB_POLY_PRODUCT: return (uint32_t)p->t.size() + 1;
+        default: return 3;  // round degree 2
+    }
+}
+
+extern "C" int scb_poly_product(const scb_mle* const* tables, uint32_t k, scb_poly** out) {
+    ARG_TRY(tables && out, "null argument");
+    ARG_TRY(k >= 1 && k <= (uint32_t)kMaxTables, "number of tables must be 1..4");
+    auto p = std::make_unique<scb_poly>();
+    p->kind = SCB_POLY_PRODUCT;
+    for (uint32_t i = 0; i < k; ++i) {
+        ARG_TRY(tables[i], "null table");
+        ARG_TRY(tables[i]->f.get() == tables[0]->f.get() || std::memcmp(&tables[i]->f->d, &tables[0]->f->d, sizeof(FieldDesc)) == 0,
+                "tables are over different fields");
+        ARG_TRY(tables[i]->t.nv == tables[0]->t.nv, "tables must have the same number of variables");
+        p->t.push_back(tables[i]->t);
+    }
+    p->f = tables[0]->f;
+    ARG_TRY((uint64_t)k < p->f->h.p[0] || p->f->d.n > 1, "field characteristic too small to interpolate degree-K messages");
+    *out = p.release();
+    return SCB_OK;
+}
+extern "C" int scb_poly_matmul_g(const scb_mle* f_a, const scb_mle* f_b, scb_poly** out) {
+    ARG_TRY(f_a && f_b && out, "null argument");
+    const scb_mle* tabs[2] = {f_a, f_b};
+    RC_TRY(scb_poly_product(tabs, 2, out));
+    (*out)->kind = SCB_POLY_MATMUL_G;
+    return SCB_OK;
+}
+extern "C" int scb_poly_matmul_g_new(const scb_field* f, uint32_t n, const uint64_t* a, const uint64_t* b, const uint64_t* point,
+                                     scb_poly** out) {
+    // matrix-multiplication/src/lib.rs:77-92
+    ARG_TRY(f && a && b && point && out, "null argument");
+    ARG_TRY(n >= 1 && n <= 15, "n out of range");
+    const uint32_t N = f->impl->d.n;
+    scb_mle *ma = nullptr, *mar = nullptr, *maf = nullptr, *mb = nullptr, *mbf = nullptr;
+    int rc = scb_mle_from_host(f, 2 * n, a, &ma);                              // :81
+    if (rc == SCB_OK) rc = scb_mle_relabel(ma, 0, n, n, &mar);                 // :82
+    if (rc == SCB_OK) rc = scb_mle_fix_variables(mar, point, n, &maf);         // :83
+    if (rc == SCB_OK) rc = scb_mle_from_host(f, 2 * n, b, &mb);                // :85
+    if (rc == SCB_OK) rc = scb_mle_fix_variables(mb, point + (size_t)n * N, n, &mbf);  // :86
+    if (rc == SCB_OK) rc = scb_poly_matmul_g(maf, mbf, out);
+    scb_mle_free(ma);
+    scb_mle_free(mar);
+    scb_mle_free(maf);
+    scb_mle_free(mb);
+    scb_mle_free(mbf);
+    return rc;
+}
+extern "C" int scb_poly_triangle_g_new(const scb_field* f, uint32_t num_vars, const uint8_t* adj, scb_poly** out) {
+    // triangle-counting/src/lib.rs:32-51
+    ARG_TRY(f && adj && out, "null argument");
+    ARG_TRY(num_vars <= 30, "num_vars out of range");
+    const uint32_t N = f->impl->d.n;
+    const size_t len = (size_t)1 << num_vars;
+    std::vector<uint64_t> host(len * N, 0);
+    for (size_t i = 0; i < len; ++i)
+        if (adj[i]) std::memcpy(&host[i * N], f->impl->d.one, 8 * N);  // F::one() / F::zero()
+    scb_mle* g = nullptr;
+    RC_TRY(scb_mle_from_host(f, num_vars, host.data(), &g));
+    auto p = std::make_unique<scb_poly>();
+    p->kind = SCB_POLY_TRIANGLE_G;
+    p->f = f->impl;
+    p->t = {g->t, g->t, g->t};  // f_a_1, f_a_2, f_a_3 are clones of one table (:46-48)
+    p->var_len = num_vars / 2;  // :44
+    scb_mle_free(g);
+    *out = p.release();
+    return SCB_OK;
+}
+extern "C" int scb_poly_gkr_w(const scb_mle* add_i, const scb_mle* mul_i, const scb_mle* w_b, const scb_mle* w_c, scb_poly** out) {
+    ARG_TRY(add_i && mul_i && w_b && w_c && out, "null argument");
+    ARG_TRY(add_i->t.nv == mul_i->t.nv, "add_i and mul_i must have the same number of variables");
+    ARG_TRY(add_i->t.nv == w_b->t.nv + w_c->t.nv, "add_i must range over (b, c)");
+    ARG_TRY(std::memcmp(&add_i->f->d, &mul_i->f->d, sizeof(FieldDesc)) == 0 && std::memcmp(&add_i->f->d, &w_b->f->d, sizeof(FieldDesc)) == 0 &&
+                std::memcmp(&add_i->f->d, &w_c->f->d, sizeof(FieldDesc)) == 0,
+            "tables are over different fields");
+    auto p = std::make_unique<scb_poly>();
+    p->kind = SCB_POLY_GKR_W;
+    p->f = add_i->f;
+    p->t = {add_i->t, mul_i->t, w_b->t, w_c->t};
+    *out = p.release();
+    return SCB_OK;
+}
+extern "C" int scb_poly_clone(const scb_poly* p, scb_poly** out) {
+    ARG_TRY(p && out, "null argument");
+    *out = new scb_poly(*p);
+    return SCB_OK;
+}
+extern "C" void scb_poly_free(scb_poly* p) { delete p; }
+extern "C" int scb_poly_kind_of(const scb_poly* p, uint32_t* out) {
+    ARG_TRY(p && out, "null argument");
+    *out = p->kind;
+    return SCB_OK;
+}
+extern "C" int scb_poly_n_tables(const scb_poly* p, uint32_t* out) {
+    ARG_TRY(p && out, "null argument");
+    *out = (uint32_t)p->t.size();
+    return SCB_OK;
+}
+extern "C" int scb_poly_table(const scb_poly* p, uint32_t idx, scb_mle** out) {
+    ARG_TRY(p && out, "null argument");
+    ARG_TRY(idx < p->t.size(), "table index out of range");
+    *out = new scb_mle{p->f, p->t[idx]};
+    return SCB_OK;
+}
+extern "C" int scb_poly_n_points(const scb_poly* p, uint32_t* out) {
+    ARG_TRY(p && out, "null argument");
+    *out = poly_n_points(p);
+    return SCB_OK;
+}
+extern "C" int scb_poly_num_vars(const scb_poly* p, uint32_t* out) {
+    ARG_TRY(p && out, "null argument");
+    *out = poly_num_vars(p);
+    return SCB_OK;
+}
+
+// SumCheckPolynomial::evaluate
+extern "C" int scb_poly_evaluate(const scb_poly* p, const uint64_t* point, uint32_t n_point, uint64_t* out_elem) {
+    ARG_TRY(p && out_elem && (point || n_point == 0), "null argument");
+    ARG_TRY(n_point == poly_num_vars(p), "point dimension does not match num_vars");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    const FieldImpl& f = *p->f;
+    const HostField& h = f.h;
+    const uint32_t N = f.d.n;
+    auto ev = [&](const Table& t, const uint64_t* pt, Fe* out) -> int {
+        uint64_t w[kMaxLimbs];
+        RC_TRY(eval_table(c, f, t, pt, w, nullptr));
+        h.load(w, *out);
+        return SCB_OK;
+    };
+    Fe res;
+    if (p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) {
+        // matrix-multiplication/src/lib.rs:96-101
+        res = h.one();
+        for (size_t k = 0; k < p->t.size(); ++k) {
+            Fe e;
+            RC_TRY(ev(p->t[k], point, &e));
+            res = k == 0 ? e : h.mul(res, e);
+        }
+    } else if (p->kind == SCB_POLY_TRIANGLE_G) {
+        // triangle-counting/src/lib.rs:71-87
+        const uint32_t xn = tri_xn(p), yn = tri_yn(p), zn = tri_zn(p);
+        std::vector<uint64_t> xz((size_t)(xn + zn + 1) * N);
+        std::memcpy(xz.data(), point, (size_t)8 * N * xn);
+        std::memcpy(xz.data() + (size_t)xn * N, point + (size_t)(xn + yn) * N, (size_t)8 * N * zn);
+        Fe e1, e2, e3;
+        RC_TRY(ev(p->t[0], point, &e1));                      // x_y_point = point[..xn+yn]
+        RC_TRY(ev(p->t[1], point + (size_t)xn * N, &e2));      // y_z_point = point[xn..]
+        RC_TRY(ev(p->t[2], xz.data(), &e3));
+        res = h.mul(h.mul(e1, e3), e2);
+    } else {
+        // gkr-protocol/src/round_polynomial.rs:48-57
+        const uint32_t bn = p->t[2].nv;
+        Fe ea, em, eb, ec;
+        RC_TRY(ev(p->t[0], point, &ea));
+        RC_TRY(ev(p->t[1], point, &em));
+        RC_TRY(ev(p->t[2], point, &eb));
+        RC_TRY(ev(p->t[3], point + (size_t)bn * N, &ec));
+        res = h.add(h.mul(ea, h.add(eb, ec)), h.mul(em, h.mul(eb, ec)));
+    }
+    h.store(res, out_elem);
+    return SCB_OK;
+}
+
+// SumCheckPolynomial::fix_variables
+extern "C" int scb_poly_fix_variables(const scb_poly* p, const uint64_t* pp, uint32_t n, scb_poly** out) {
+    ARG_TRY(p && out && (pp || n == 0), "null argument");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    const FieldImpl& f = *p->f;
+    const uint32_t N = f.d.n;
+    auto q = std::make_unique<scb_poly>(*p);
+    if (p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) {
+        // matrix-multiplication/src/lib.rs:103-108
+        for (size_t k = 0; k < p->t.size(); ++k) RC_TRY(fix_table(c, f, p->t[k], pp, n, &q->t[k]));
+    } else if (p->kind == SCB_POLY_TRIANGLE_G) {
+        // triangle-counting/src/lib.rs:89-118
+        const uint32_t xn = tri_xn(p), yn = tri_yn(p);
+        const uint32_t n_xy = n < xn + yn ? n : xn + yn;
+        const uint32_t n_yz = xn <= n ? n - xn : 0;
+        const uint32_t n_x = n < xn ? n : xn;
+        const uint32_t n_z = xn + yn <= n ? n - (xn + yn) : 0;
+        std::vector<uint64_t> xz((size_t)(n_x + n_z + 1) * N);
+        std::memcpy(xz.data(), pp, (size_t)8 * N * n_x);
+        if (n_z) std::memcpy(xz.data() + (size_t)n_x * N, pp + (size_t)(xn + yn) * N, (size_t)8 * N * n_z);
+        RC_TRY(fix_table(c, f, p->t[0], pp, n_xy, &q->t[0]));
+        RC_TRY(fix_table(c, f, p->t[1], pp + (size_t)(n_yz ? xn : 0) * N, n_yz, &q->t[1]));
+        RC_TRY(fix_table(c, f, p->t[2], xz.data(), n_x + n_z, &q->t[2]));
+    } else {
+        // gkr-protocol/src/round_polynomial.rs:59-76
+        const uint32_t bn = p->t[2].nv;
+        const uint32_t n_b = n < bn ? n : bn;
+        const uint32_t n_c = bn <= n ? n - bn : 0;
+        RC_TRY(fix_table(c, f, p->t[0], pp, n, &q->t[0]));
+        RC_TRY(fix_table(c, f, p->t[1], pp, n, &q->t[1]));
+        RC_TRY(fix_table(c, f, p->t[2], pp, n_b, &q->t[2]));
+        RC_TRY(fix_table(c, f, p->t[3], pp + (size_t)(n_c ? bn : 0) * N, n_c, &q->t[3]));
+    }
+    *out = q.release();
+    return SCB_OK;
+}
+
+// launch the message kernel of `p`; result (np elements) to `res` (mapped host or device memory)
+static int launch_round_evals(Ctx* c, const scb_poly* p, uint64_t* res) {
+    const FieldImpl& f = *p->f;
+    ARG_TRY(poly_num_vars(p) >= 1, "polynomial has no variables left");
+    if (p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) {
+        const uint64_t n_pairs = p->t[0].len() / 2;
+        ARG_TRY(f.policy != POL_SP || p->t[0].nv <= 32, "table too large for the small-prime path");
+        DISPATCH_POLICY(f.policy, DISPATCH_K(p->t.size(), {
+            TabsIn<K> in;
+            for (int k = 0; k < K; ++k) in.p[k] = p->t[k].buf->ptr;
+            k_round_evals<A, K><<<grid_for(c, n_pairs), kThreads, 0, g_stream>>>(f.d, in, n_pairs, c->partials, c->ticket, res);
+        }));
+    } else if (p->kind == SCB_POLY_TRIANGLE_G) {
+        const uint32_t xn = tri_xn(p), yn = tri_yn(p), zn = tri_zn(p);
+        const uint64_t n_t = xn > 0 ? 1ull << (xn - 1 + zn) : (yn > 0 ? 1ull << (yn - 1 + zn) : 1ull << (zn - 1));
+        DISPATCH_POLICY(f.policy, {
+            k_triangle_round<A><<<grid_for(c, n_t), kThreads, 0, g_stream>>>(f.d, p->t[0].buf->ptr, p->t[1].buf->ptr, p->t[2].buf->ptr, xn, yn, zn,
+                                                                            c->partials, c->ticket, res);
+        });
+    } else {
+        const uint32_t bn = p->t[2].nv, cn = p->t[3].nv;
+        const uint64_t n_t = 1ull << (bn + cn - 1);
+        DISPATCH_POLICY(f.policy, {
+            k_gkrw_round<A><<<grid_for(c, n_t), kThreads, 0, g_stream>>>(f.d, p->t[0].buf->ptr, p->t[1].buf->ptr, p->t[2].buf->ptr, p->t[3].buf->ptr,
+                                                                        bn, cn, c->partials, c->ticket, res);
+        });
+    }
+    LAUNCH_CHECK();
+    return SCB_OK;
+}
+
+static int round_evals_impl(const scb_poly* p, uint32_t n_points, uint64_t* h_out, uint64_t* d_out) {
+    ARG_TRY(p && (h_out || d_out), "null argument");
+    ARG_TRY(n_points >= 1 && n_points <= poly_n_points(p), "n_points out of range for this polynomial");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    const uint32_t N = p->f->d.n;
+    if (d_out) {
+        if (n_points == poly_n_points(p)) return launch_round_evals(c, p, d_out);
+        RC_TRY(launch_round_evals(c, p, c->d_scratch));
+        CU_TRY(cudaMemcpyAsync(d_out, c->d_scratch, (size_t)8 * N * n_points, cudaMemcpyDeviceToDevice, g_stream));
+        return SCB_OK;
+    }
+    RC_TRY(launch_round_evals(c, p, c->h_res));
+    CU_TRY(cudaStreamSynchronize(g_stream));
+    std::memcpy(h_out, c->h_res, (size_t)8 * N * n_points);
+    return SCB_OK;
+}
+extern "C" int scb_poly_round_evals(const scb_poly* p, uint32_t n_points, uint64_t* out_elems) {
+    return round_evals_impl(p, n_points, out_elems, nullptr);
+}
+extern "C" int scb_poly_round_evals_device(const scb_poly* p, uint32_t n_points, uint64_t* d_out) {
+    return round_evals_impl(p, n_points, nullptr, d_out);
+}
+
+// fused fold + message (product kinds: one kernel; mixed-arity kinds: fold kernels then message kernel)
+static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_points, scb_poly** out, uint64_t* h_out, uint64_t* d_out) {
+    ARG_TRY(p && r && out && (h_out || d_out), "null argument");
+    ARG_TRY(n_points >= 1 && n_points <= poly_n_points(p), "n_points out of range for this polynomial");
+    ARG_TRY(poly_num_vars(p) >= 2, "need at least two variables to fix one and send a message");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    const FieldImpl& f = *p->f;
+    const uint32_t N = f.d.n;
+    ARG_TRY(elem_canonical(f, r), "challenge is not a canonical field element");
+    uint64_t* res = d_out ? (n_points == poly_n_points(p) ? d_out : c->d_scratch) : c->h_res;
+    std::unique_ptr<scb_poly> q;
+    if (p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) {
+        ARG_TRY(f.policy != POL_SP || p->t[0].nv <= 32, "table too large for the small-prime path");
+        q = std::make_unique<scb_poly>(*p);
+        const uint64_t n_quads = p->t[0].len() / 4;
+        for (size_t k = 0; k < p->t.size(); ++k) {
+            q->t[k].nv = p->t[k].nv - 1;
+            q->t[k].buf.reset();
+            RC_TRY(alloc_buf((size_t)8 * N << q->t[k].nv, &q->t[k].buf));
+        }
+        const ElemArg ra = elem_arg(f, r);
+        DISPATCH_POLICY(f.policy, DISPATCH_K(p->t.size(), {
+            TabsIn<K> in;
+            TabsOut<K> o;
+            for (int k = 0; k < K; ++k) {
+                in.p[k] = p->t[k].buf->ptr;
+                o.p[k] = q->t[k].buf->ptr;
+            }
+            k_fold_round<A, K><<<grid_for(c, n_quads), kThreads, 0, g_stream>>>(f.d, in, o, ra, n_quads, c->partials, c->ticket, res);
+        }));
+        LAUNCH_CHECK();
+    } else {
+        scb_poly* qq = nullptr;
+        RC_TRY(scb_poly_fix_variables(p, r, 1, &qq));
+        q.reset(qq);
+        RC_TRY(launch_round_evals(c, q.get(), res));
+    }
+    if (d_out) {
+        if (res != d_out) CU_TRY(cudaMemcpyAsync(d_out, res, (size_t)8 * N * n_points, cudaMemcpyDeviceToDevice, g_stream));
+    } else {
+        CU_TRY(cudaStreamSynchronize(g_stream));
+        std::memcpy(h_out, c->h_res, (size_t)8 * N * n_points);
+    }
+    *out = q.release();
+    return SCB_OK;
+}
+extern "C" int scb_poly_fix_and_round_evals(const scb_poly* p, const uint64_t* r, uint32_t n_points, scb_poly** out, uint64_t* out_elems) {
+    return fix_and_round_impl(p, r, n_points, out, out_elems, nullptr);
+}
+extern "C" int scb_poly_fix_and_round_evals_device(const scb_poly* p, const uint64_t* r, uint32_t n_points, scb_poly** out, uint64_t* d_out) {
+    return fix_and_round_impl(p, r, n_points, out, nullptr, d_out);
+}
+
+// c_1 (Prover::new)
+extern "C" int scb_poly_sum(const scb_poly* p, uint64_t* out_elem) {
+    ARG_TRY(p && out_elem, "null argument");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    const FieldImpl& f = *p->f;
+    if (p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) {
+        const uint64_t n = p->t[0].len();
+        ARG_TRY(f.policy != POL_SP || p->t[0].nv <= 32, "table too large for the small-prime path");
+        DISPATCH_POLICY(f.policy, DISPATCH_K(p->t.size(), {
+            TabsIn<K> in;
+            for (int k = 0; k < K; ++k) in.p[k] = p->t[k].buf->ptr;
+            if (A::N == 1 && n >= 4)
+                k_product_sum<A, K, (A::N == 1 ? 4 : 1)><<<grid_for(c, n / 4), kThreads, 0, g_stream>>>(f.d, in, n / 4, c->partials, c->ticket, c->h_res);
+            else
+                k_product_sum<A, K, 1><<<grid_for(c, n), kThreads, 0, g_stream>>>(f.d, in, n, c->partials, c->ticket, c->h_res);
+        }));
+    } else if (p->kind == SCB_POLY_TRIANGLE_G) {
+        const uint32_t xn = tri_xn(p), yn = tri_yn(p), zn = tri_zn(p);
+        DISPATCH_POLICY(f.policy, {
+            k_triangle_sum<A><<<grid_for(c, 1ull << (xn + zn)), kThreads, 0, g_stream>>>(f.d, p->t[0].buf->ptr, p->t[1].buf->ptr, p->t[2].buf->ptr, xn, yn,
+                                                                                        zn, c->partials, c->ticket, c->h_res);
+        });
+    } else {
+        const uint32_t bn = p->t[2].nv, cn = p->t[3].nv;
+        DISPATCH_POLICY(f.policy, {
+            k_gkrw_sum<A><<<grid_for(c, 1ull << (bn + cn)), kThreads, 0, g_stream>>>(f.d, p->t[0].buf->ptr, p->t[1].buf->ptr, p->t[2].buf->ptr,
+                                                                                    p->t[3].buf->ptr, bn, cn, c->partials, c->ticket, c->h_res);
+        });
+    }
+    LAUNCH_CHECK();
+    CU_TRY(cudaStreamSynchronize(g_stream));
+    std::memcpy(out_elem, c->h_res, 8 * f.d.n);
+    return SCB_OK;
+}
+
+// SumCheckPolynomial::to_evaluations
+extern "C" int scb_poly_to_evaluations(const scb_poly* p, uint64_t* out, size_t cap_elems) {
+    ARG_TRY(p && out, "null argument");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    const FieldImpl& f = *p->f;
+    const uint32_t nv = poly_num_vars(p);
+    ARG_TRY(nv <= 34 && cap_elems >= ((size_t)1 << nv), "output buffer too small");
+    const uint64_t n = 1ull << nv;
+    BufRef tmp;
+    RC_TRY(alloc_buf((size_t)8 * f.d.n << nv, &tmp));
+    if (p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) {
+        DISPATCH_POLICY(f.policy, DISPATCH_K(p->t.size(), {
+            TabsIn<K> in;
+            for (int k = 0; k < K; ++k) in.p[k] = p->t[k].buf->ptr;
+            k_product_table<A, K><<<grid_for(c, n), kThreads, 0, g_stream>>>(f.d, in, tmp->ptr, n);
+        }));
+    } else if (p->kind == SCB_POLY_TRIANGLE_G) {
+        DISPATCH_POLICY(f.policy, {
+            k_triangle_table<A><<<grid_for(c, n), kThreads, 0, g_stream>>>(f.d, p->t[0].buf->ptr, p->t[1].buf->ptr, p->t[2].buf->ptr, tri_xn(p), tri_yn(p),
+                                                                          tri_zn(p), tmp->ptr);
+        });
+    } else {
+        DISPATCH_POLICY(f.policy, {
+            k_gkrw_table<A><<<grid_for(c, n), kThreads, 0, g_stream>>>(f.d, p->t[0].buf->ptr, p->t[1].buf->ptr, p->t[2].buf->ptr, p->t[3].buf->ptr,
+                                                                      p->t[2].nv, p->t[3].nv, tmp->ptr);
+        });
+    }
+    LAUNCH_CHECK();
+    CU_TRY(cudaMemcpyAsync(out, tmp->ptr, (size_t)8 * f.d.n << nv, cudaMemcpyDeviceToHost, g_stream));
+    CU_TRY(cudaStreamSynchronize(g_stream));
+    return SCB_OK;
+}
+
+// accessor used by protocol.cpp
+extern "C" int scb_poly_field_impl(const scb_poly* p, const FieldImpl** out) {
+    ARG_TRY(p && out, "null argument");
+    *out = p->f.get();
+    return SCB_OK;
+}

@@ -1,0 +1,145 @@
+// fiat_shamir.hpp -- host mirror of the challenge derivation used by
+// /root/reference/fiat-shamir/src/lib.rs:75-98,123-143:
+//   hasher = DefaultFieldHasher<Sha256>::new(&[])      (empty DST, :78)
+//   r_j    = hasher.hash_to_field::<1>(g_1 || ... || g_j)[0]   (cumulative byte string, :87-88)
+// [ARK] DefaultFieldHasher<Sha256, 128>: L = ceil((bits(p) + 128) / 8); uniform bytes =
+// expand_message_xmd(msg, DST, L) per RFC 9380 with SHA-256, EXCEPT that Z_pad has L zero bytes
+// (ark's `block_size: len_per_base_elem`) instead of the hash's 64-byte block; DST' = DST || len(DST);
+// the L bytes are read big-endian and reduced mod p (from_be_bytes_mod_order).
+// The reference holds no vector for these bytes ("parity unpinned"); the Python
+// oracle restates the same published algorithm on top of hashlib and must agree byte for byte.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "hostfield.hpp"
+
+namespace scb {
+
+class Sha256 {
+   public:
+    Sha256() { reset(); }
+    void reset() {
+        static const uint32_t iv[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a,
+                                       0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+        std::memcpy(h_, iv, sizeof iv);
+        len_ = 0;
+        fill_ = 0;
+    }
+    void update(const uint8_t* data, size_t n) {
+        len_ += n;
+        while (n) {
+            size_t take = 64 - fill_ < n ? 64 - fill_ : n;
+            std::memcpy(buf_ + fill_, data, take);
+            fill_ += take;
+            data += take;
+            n -= take;
+            if (fill_ == 64) {
+                compress(buf_);
+                fill_ = 0;
+            }
+        }
+    }
+    void finalize(uint8_t out[32]) {
+        uint64_t bitlen = len_ * 8;
+        uint8_t pad = 0x80;
+        update(&pad, 1);
+        uint8_t z = 0;
+        while (fill_ != 56) update(&z, 1);
+        uint8_t lb[8];
+        for (int i = 0; i < 8; ++i) lb[i] = (uint8_t)(bitlen >> (56 - 8 * i));
+        update(lb, 8);
+        for (int i = 0; i < 8; ++i) {
+            out[4 * i] = (uint8_t)(h_[i] >> 24);
+            out[4 * i + 1] = (uint8_t)(h_[i] >> 16);
+            out[4 * i + 2] = (uint8_t)(h_[i] >> 8);
+            out[4 * i + 3] = (uint8_t)h_[i];
+        }
+    }
+
+   private:
+    static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+    void compress(const uint8_t* blk) {
+        static const uint32_t k[64] = {
+            0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
+            0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
+            0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147,
+            0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+            0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08,
+            0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
+            0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+        uint32_t w[64];
+        for (int i = 0; i < 16; ++i)
+            w[i] = ((uint32_t)blk[4 * i] << 24) | ((uint32_t)blk[4 * i + 1] << 16) | ((uint32_t)blk[4 * i + 2] << 8) | blk[4 * i + 3];
+        for (int i = 16; i < 64; ++i) {
+            uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+            uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+            w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+        }
+        uint32_t a = h_[0], b = h_[1], c = h_[2], d = h_[3], e = h_[4], f = h_[5], g = h_[6], h = h_[7];
+        for (int i = 0; i < 64; ++i) {
+            uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+            uint32_t ch = (e & f) ^ (~e & g);
+            uint32_t t1 = h + S1 + ch + k[i] + w[i];
+            uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+            uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+            uint32_t t2 = S0 + mj;
+            h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        h_[0] += a; h_[1] += b; h_[2] += c; h_[3] += d; h_[4] += e; h_[5] += f; h_[6] += g; h_[7] += h;
+    }
+    uint32_t h_[8];
+    uint64_t len_;
+    uint8_t buf_[64];
+    size_t fill_;
+};
+
+// [ARK] ExpanderXmd::expand (block_size = Z_pad length)
+inline std::vector<uint8_t> expand_message_xmd(const uint8_t* msg, size_t msg_len, const std::vector<uint8_t>& dst, size_t n,
+                                               size_t block_size) {
+    const size_t b_len = 32;
+    const size_t ell = (n + b_len - 1) / b_len;
+    std::vector<uint8_t> dst_prime(dst);
+    dst_prime.push_back((uint8_t)dst.size());
+    std::vector<uint8_t> z_pad(block_size, 0);
+    uint8_t lib_str[2] = {(uint8_t)(n >> 8), (uint8_t)n};
+    uint8_t b0[32], bi[32];
+    Sha256 h;
+    h.update(z_pad.data(), z_pad.size());
+    h.update(msg, msg_len);
+    h.update(lib_str, 2);
+    uint8_t zero = 0;
+    h.update(&zero, 1);
+    h.update(dst_prime.data(), dst_prime.size());
+    h.finalize(b0);
+    h.reset();
+    h.update(b0, 32);
+    uint8_t one = 1;
+    h.update(&one, 1);
+    h.update(dst_prime.data(), dst_prime.size());
+    h.finalize(bi);
+    std::vector<uint8_t> out(bi, bi + 32);
+    for (size_t i = 2; i <= ell; ++i) {
+        uint8_t x[32];
+        for (int k = 0; k < 32; ++k) x[k] = b0[k] ^ bi[k];
+        h.reset();
+        h.update(x, 32);
+        uint8_t ib = (uint8_t)i;
+        h.update(&ib, 1);
+        h.update(dst_prime.data(), dst_prime.size());
+        h.finalize(bi);
+        out.insert(out.end(), bi, bi + 32);
+    }
+    out.resize(n);
+    return out;
+}
+
+// hasher.hash_to_field::<1>(msg)[0] with H::new(&[])
+inline Fe hash_to_field(const HostField& F, const uint8_t* msg, size_t len) {
+    const size_t L = (F.bits + 128 + 7) / 8;
+    std::vector<uint8_t> uniform = expand_message_xmd(msg, len, std::vector<uint8_t>(), L, L);
+    return F.from_be_bytes_mod_order(uniform.data(), uniform.size());
+}
+
+}  // namespace scb

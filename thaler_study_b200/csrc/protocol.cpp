@@ -1,0 +1,414 @@
+// protocol.cpp -- level 2 of the C ABI: the host half of the drop-in.  C++ mirror of
+//   sum_check_protocol::{Prover, Verifier}      /root/reference/sum-check-protocol/src/lib.rs:73-117,227-331
+//   SumCheckPolynomial::to_univariate           per implementor (interpolation + SparsePolynomial conventions)
+//   fiat_shamir::{generate_transcript, verify_transcript}   /root/reference/fiat-shamir/src/lib.rs:44-98,123-171
+// built ONLY on level 1 (engine.cu): the device produces the (d+1) round sums, everything that decides
+// transcript bytes (interpolation, zero-term handling, serialization, SHA-256 hash-to-field) is host code
+// here, exactly where the reference keeps it.  In a Rust build this file is replaced by the reference's own
+// crates; it exists so that the path is complete and testable without a Rust toolchain.
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "host/fiat_shamir.hpp"
+#include "host/unipoly.hpp"
+#include "internal.hpp"
+#include "sumcheck_b200.h"
+
+using namespace scb;
+
+extern "C" int scb_poly_field_impl(const scb_poly* p, const FieldImpl** out);
+
+#define ARG_TRY(cond, msg)        \
+    do {                          \
+        if (!(cond)) {            \
+            set_error("%s", msg); \
+            return SCB_EINVAL;    \
+        }                         \
+    } while (0)
+#define RC_TRY(expr)                     \
+    do {                                 \
+        int rc__ = (expr);               \
+        if (rc__ != SCB_OK) return rc__; \
+    } while (0)
+
+static constexpr uint32_t kMaxTerms = 8;
+
+// (d+1) sums -> the univariate::SparsePolynomial each implementor's to_univariate returns
+static SparsePoly evals_to_poly(const HostField& F, uint32_t kind, const std::vector<Fe>& ev) {
+    if (kind == SCB_POLY_MATMUL_G && ev.size() == 3) {
+        // matrix-multiplication/src/lib.rs:124-130
+        const Fe x[3] = {F.zero(), F.one(), F.add(F.one(), F.one())};
+        const Fe y[3] = {ev[0], ev[1], ev[2]};
+        return interpolate_quadratic_poly(F, x, y);
+    }
+    // triangle-counting/src/lib.rs:128-131, gkr-protocol/src/round_polynomial.rs:86-89 (`p.into()`),
+    // and ProductMLE<K>: unique interpolant, Dense -> Sparse
+    return SparsePoly::from_dense(F, lagrange_to_coeffs(F, ev));
+}
+
+static int poly_out(const HostField& F, const SparsePoly& sp, uint64_t* degrees, uint64_t* coeffs, uint32_t cap, uint32_t* n_terms) {
+    ARG_TRY(degrees && coeffs && n_terms, "null argument");
+    ARG_TRY(sp.coeffs.size() <= cap, "term buffer too small");
+    for (size_t i = 0; i < sp.coeffs.size(); ++i) {
+        degrees[i] = sp.coeffs[i].first;
+        F.store(sp.coeffs[i].second, coeffs + i * F.n);
+    }
+    *n_terms = (uint32_t)sp.coeffs.size();
+    return SCB_OK;
+}
+static SparsePoly poly_in(const HostField& F, const uint64_t* degrees, const uint64_t* coeffs, uint32_t n_terms) {
+    SparsePoly sp;
+    for (uint32_t i = 0; i < n_terms; ++i) {
+        Fe c;
+        F.load(coeffs + (size_t)i * F.n, c);
+        sp.coeffs.emplace_back(degrees[i], c);
+    }
+    return sp;
+}
+
+static int device_round_poly(const scb_poly* g, SparsePoly* out) {
+    const FieldImpl* fi;
+    RC_TRY(scb_poly_field_impl(g, &fi));
+    uint32_t np = 0, kind = 0;
+    RC_TRY(scb_poly_n_points(g, &np));
+    RC_TRY(scb_poly_kind_of(g, &kind));
+    uint64_t w[8 * kHostMaxLimbs];
+    RC_TRY(scb_poly_round_evals(g, np, w));
+    std::vector<Fe> ev(np);
+    for (uint32_t i = 0; i < np; ++i) fi->h.load(w + (size_t)i * fi->h.n, ev[i]);
+    *out = evals_to_poly(fi->h, kind, ev);
+    return SCB_OK;
+}
+
+extern "C" int scb_poly_to_univariate(const scb_poly* p, uint64_t* degrees, uint64_t* coeffs, uint32_t cap_terms, uint32_t* n_terms) {
+    ARG_TRY(p, "null argument");
+    const FieldImpl* fi;
+    RC_TRY(scb_poly_field_impl(p, &fi));
+    SparsePoly sp;
+    RC_TRY(device_round_poly(p, &sp));
+    return poly_out(fi->h, sp, degrees, coeffs, cap_terms, n_terms);
+}
+
+extern "C" int scb_evals_to_univariate(const scb_field* f, uint32_t kind, const uint64_t* evals, uint32_t n_points, uint64_t* degrees,
+                                       uint64_t* coeffs, uint32_t cap_terms, uint32_t* n_terms) {
+    ARG_TRY(f && evals, "null argument");
+    ARG_TRY(n_points >= 1 && n_points <= kMaxTerms, "n_points out of range");
+    const HostField& F = f->impl->h;
+    std::vector<Fe> ev(n_points);
+    for (uint32_t i = 0; i < n_points; ++i) {
+        F.load(evals + (size_t)i * F.n, ev[i]);
+        ARG_TRY(F.is_canonical(ev[i]), "evaluation is not a canonical field element");
+    }
+    return poly_out(F, evals_to_poly(F, kind, ev), degrees, coeffs, cap_terms, n_terms);
+}
+extern "C" int scb_unipoly_serialize(const scb_field* f, const uint64_t* degrees, const uint64_t* coeffs, uint32_t n_terms, uint8_t* out,
+                                     size_t cap, size_t* out_len) {
+    ARG_TRY(f && out && out_len && ((degrees && coeffs) || n_terms == 0), "null argument");
+    const HostField& F = f->impl->h;
+    std::vector<uint8_t> bytes;
+    poly_in(F, degrees, coeffs, n_terms).serialize(F, bytes);
+    ARG_TRY(bytes.size() <= cap, "output buffer too small");
+    std::memcpy(out, bytes.data(), bytes.size());
+    *out_len = bytes.size();
+    return SCB_OK;
+}
+extern "C" int scb_unipoly_evaluate(const scb_field* f, const uint64_t* degrees, const uint64_t* coeffs, uint32_t n_terms,
+                                    const uint64_t* x, uint64_t* out_elem) {
+    ARG_TRY(f && x && out_elem && ((degrees && coeffs) || n_terms == 0), "null argument");
+    const HostField& F = f->impl->h;
+    Fe xe;
+    F.load(x, xe);
+    F.store(poly_in(F, degrees, coeffs, n_terms).evaluate(F, xe), out_elem);
+    return SCB_OK;
+}
+extern "C" int scb_hash_to_field(const scb_field* f, const uint8_t* msg, size_t len, uint64_t* out_elem) {
+    ARG_TRY(f && out_elem && (msg || len == 0), "null argument");
+    const HostField& F = f->impl->h;
+    F.store(hash_to_field(F, msg, len), out_elem);
+    return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ Prover
+struct scb_prover {
+    scb_poly* g = nullptr;      // g: P
+    Fe c_1;                     // c_1: F
+    std::vector<Fe> r;          // r: Vec<F>
+    uint32_t num_vars = 0;
+    const FieldImpl* fi = nullptr;
+    uint32_t kind = 0, np = 0;
+    bool have_round0 = false;   // round-0 sums computed by Prover::new (they also yield c_1)
+    std::vector<Fe> round0;
+    ~scb_prover() { scb_poly_free(g); }
+};
+
+extern "C" int scb_prover_new(const scb_poly* g, scb_prover** out) {
+    // Prover::new :88-97 -- c_1 = g.to_evaluations().into_iter().sum(), computed on the device
+    ARG_TRY(g && out, "null argument");
+    auto p = std::make_unique<scb_prover>();
+    RC_TRY(scb_poly_clone(g, &p->g));
+    RC_TRY(scb_poly_field_impl(g, &p->fi));
+    RC_TRY(scb_poly_kind_of(g, &p->kind));
+    RC_TRY(scb_poly_n_points(g, &p->np));
+    RC_TRY(scb_poly_num_vars(g, &p->num_vars));
+    const HostField& F = p->fi->h;
+    if (p->num_vars >= 1) {
+        // sum over the hypercube = g_1(0) + g_1(1): the round-0 message pass also yields c_1, so the
+        // tables are streamed once here and not again by round(_, 0)  (same field elements either way)
+        uint64_t w[8 * kHostMaxLimbs];
+        RC_TRY(scb_poly_round_evals(g, p->np, w));
+        p->round0.resize(p->np);
+        for (uint32_t i = 0; i < p->np; ++i) F.load(w + (size_t)i * F.n, p->round0[i]);
+        p->have_round0 = true;
+        p->c_1 = F.add(p->round0[0], p->round0[1]);
+    } else {
+        uint64_t w[kHostMaxLimbs];
+        RC_TRY(scb_poly_sum(g, w));
+        F.load(w, p->c_1);
+    }
+    p->r.reserve(p->num_vars);
+    *out = p.release();
+    return SCB_OK;
+}
+extern "C" void scb_prover_free(scb_prover* p) { delete p; }
+extern "C" int scb_prover_c_1(const scb_prover* p, uint64_t* out_elem) {
+    ARG_TRY(p && out_elem, "null argument");
+    p->fi->h.store(p->c_1, out_elem);
+    return SCB_OK;
+}
+extern "C" int scb_prover_num_vars(const scb_prover* p, uint32_t* out) {
+    ARG_TRY(p && out, "null argument");
+    *out = p->num_vars;
+    return SCB_OK;
+}
+
+// Prover::round :105-112.  For j != 0 the fold and the message are ONE fused kernel.
+static int prover_round(scb_prover* p, const Fe* r_prev, uint32_t j, SparsePoly* out) {
+    const HostField& F = p->fi->h;
+    uint64_t w[8 * kHostMaxLimbs];
+    if (j != 0) {
+        uint64_t rw[kHostMaxLimbs];
+        F.store(*r_prev, rw);
+        p->r.push_back(*r_prev);
+        scb_poly* next = nullptr;
+        RC_TRY(scb_poly_fix_and_round_evals(p->g, rw, p->np, &next, w));
+        scb_poly_free(p->g);
+        p->g = next;
+    } else if (p->have_round0) {
+        *out = evals_to_poly(F, p->kind, p->round0);
+        return SCB_OK;
+    } else {
+        RC_TRY(scb_poly_round_evals(p->g, p->np, w));
+    }
+    std::vector<Fe> ev(p->np);
+    for (uint32_t i = 0; i < p->np; ++i) F.load(w + (size_t)i * F.n, ev[i]);
+    *out = evals_to_poly(F, p->kind, ev);
+    return SCB_OK;
+}
+extern "C" int scb_prover_round(scb_prover* p, const uint64_t* r_prev, uint32_t j, uint64_t* degrees, uint64_t* coeffs,
+                                uint32_t cap_terms, uint32_t* n_terms) {
+    ARG_TRY(p && (r_prev || j == 0), "null argument");
+    Fe r;
+    if (j != 0) p->fi->h.load(r_prev, r);
+    SparsePoly sp;
+    RC_TRY(prover_round(p, &r, j, &sp));
+    return poly_out(p->fi->h, sp, degrees, coeffs, cap_terms, n_terms);
+}
+
+// ------------------------------------------------------------------------------------------ Verifier
+struct scb_verifier {
+    std::shared_ptr<FieldImpl> f;
+    uint32_t n = 0;                    // n: usize
+    Fe c_1;                            // c_1: F
+    std::vector<SparsePoly> g_part;    // g_part
+    std::vector<Fe> r;                 // r
+    scb_poly* g = nullptr;             // g: Option<P>
+    ~scb_verifier() { scb_poly_free(g); }
+};
+
+extern "C" int scb_verifier_new(const scb_field* f, uint32_t n, const scb_poly* g, scb_verifier** out) {
+    ARG_TRY(f && out, "null argument");
+    auto v = std::make_unique<scb_verifier>();
+    v->f = f->impl;
+    v->n = n;
+    if (g) RC_TRY(scb_poly_clone(g, &v->g));
+    *out = v.release();
+    return SCB_OK;
+}
+extern "C" void scb_verifier_free(scb_verifier* v) { delete v; }
+extern "C" int scb_verifier_set_c_1(scb_verifier* v, const uint64_t* c_1) {
+    ARG_TRY(v && c_1, "null argument");
+    v->f->h.load(c_1, v->c_1);
+    return SCB_OK;
+}
+
+// Verifier::round :278-330
+static int verifier_round(scb_verifier* v, const SparsePoly& g_j, const Fe& r_j, int* final_round, int* accepted) {
+    const HostField& F = v->f->h;
+    *final_round = 0;
+    *accepted = 0;
+    if (v->r.empty()) {  // first round :284-297
+        Fe evaluation = F.add(g_j.evaluate(F, F.zero()), g_j.evaluate(F, F.one()));
+        if (v->c_1 != evaluation) {
+            set_error("prover claim mismatches evaluation (start)");
+            return SCB_EVERIFY;
+        }
+        v->g_part.push_back(g_j);
+        v->r.push_back(r_j);
+        return SCB_OK;
+    } else if (v->r.size() == (size_t)v->n - 1) {  // last round :298-310
+        v->r.push_back(r_j);
+        if (!v->g) {
+            set_error("verifier has no oracle access to the polynomial");
+            return SCB_ENOPOLY;
+        }
+        std::vector<uint64_t> pt((size_t)v->n * F.n);
+        for (uint32_t i = 0; i < v->n; ++i) F.store(v->r[i], &pt[(size_t)i * F.n]);
+        uint64_t w[kHostMaxLimbs];
+        RC_TRY(scb_poly_evaluate(v->g, pt.data(), v->n, w));  // g.evaluate(&self.r) on the device (K4, LSB-first)
+        Fe oracle;
+        F.load(w, oracle);
+        *final_round = 1;
+        *accepted = g_j.evaluate(F, r_j) == oracle ? 1 : 0;
+        return SCB_OK;
+    } else {  // j-th round :311-329
+        Fe prev = v->g_part.back().evaluate(F, v->r.back());
+        Fe evaluation = F.add(g_j.evaluate(F, F.zero()), g_j.evaluate(F, F.one()));
+        if (prev != evaluation) {
+            set_error("prover claim mismatches evaluation (round %zu)", v->r.size());
+            return SCB_EVERIFY;
+        }
+        v->g_part.push_back(g_j);
+        v->r.push_back(r_j);
+        return SCB_OK;
+    }
+}
+extern "C" int scb_verifier_round(scb_verifier* v, const uint64_t* degrees, const uint64_t* coeffs, uint32_t n_terms, const uint64_t* r_j,
+                                  int* final_round, int* accepted) {
+    ARG_TRY(v && r_j && final_round && accepted && ((degrees && coeffs) || n_terms == 0), "null argument");
+    const HostField& F = v->f->h;
+    Fe r;
+    F.load(r_j, r);
+    return verifier_round(v, poly_in(F, degrees, coeffs, n_terms), r, final_round, accepted);
+}
+
+// ------------------------------------------------------------------------------------------ fiat-shamir
+extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t cap, size_t* out_len, uint64_t* offsets) {
+    // fiat-shamir/src/lib.rs:75-98 with InteractiveProver for Prover (:44-66)
+    ARG_TRY(p && out && out_len && offsets, "null argument");
+    const HostField& F = p->fi->h;
+    std::vector<uint8_t> hash_input;  // == concatenation of all messages so far
+    SparsePoly sp;
+    Fe dummy;
+    // g_1 = (c_1, round(F::one(), 0)).serialize_uncompressed()
+    RC_TRY(prover_round(p, &dummy, 0, &sp));
+    F.serialize(p->c_1, hash_input);
+    sp.serialize(F, hash_input);
+    offsets[0] = 0;
+    offsets[1] = hash_input.size();
+    for (uint32_t j = 1; j < p->num_vars; ++j) {
+        Fe r_j = hash_to_field(F, hash_input.data(), hash_input.size());
+        RC_TRY(prover_round(p, &r_j, j, &sp));
+        sp.serialize(F, hash_input);
+        offsets[j + 1] = hash_input.size();
+    }
+    ARG_TRY(hash_input.size() <= cap, "transcript buffer too small");
+    std::memcpy(out, hash_input.data(), hash_input.size());
+    *out_len = hash_input.size();
+    return SCB_OK;
+}
+
+extern "C" int scb_fs_verify_transcript(scb_verifier* v, const uint8_t* transcript, const uint64_t* offsets, uint32_t n_msgs, int* accepted) {
+    // fiat-shamir/src/lib.rs:123-143 with InteractiveVerifier for Verifier (:151-171)
+    ARG_TRY(v && transcript && offsets && accepted, "null argument");
+    const HostField& F = v->f->h;
+    *accepted = 0;
+    for (uint32_t j = 0; j < n_msgs; ++j) {
+        const uint8_t* msg = transcript + offsets[j];
+        const size_t len = offsets[j + 1] - offsets[j];
+        Fe r_j = hash_to_field(F, transcript, offsets[j + 1]);  // hash of g_1 || ... || g_j
+        size_t off = 0;
+        if (j == 0) {
+            if (len < F.ser_bytes()) {
+                set_error("Codec error");
+                return SCB_EINVAL;
+            }
+            Fe c_1;
+            if (!F.deserialize(msg, c_1)) {
+                set_error("Codec error");
+                return SCB_EINVAL;
+            }
+            v->c_1 = c_1;
+            off = F.ser_bytes();
+        }
+        SparsePoly g_j;
+        size_t used = SparsePoly::deserialize(F, msg + off, len - off, g_j);
+        if (used == 0) {
+            set_error("Codec error");
+            return SCB_EINVAL;
+        }
+        int fin = 0, acc = 0;
+        RC_TRY(verifier_round(v, g_j, r_j, &fin, &acc));
+        if (j == 0) continue;       // :155-161 returns Ok(true) for the first message
+        if (fin && !acc) return SCB_OK;  // *accepted stays 0
+    }
+    *accepted = 1;
+    return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ transcript object
+// The Fiat-Shamir chain of fiat-shamir/src/lib.rs:75-98 as an explicit state machine, for provers whose
+// round sums arrive in pieces (the sharded multi-GPU prover: one row of partial sums per rank).
+struct scb_transcript {
+    std::shared_ptr<FieldImpl> f;
+    uint32_t kind = 0;
+    std::vector<uint8_t> bytes;      // g_1 || g_2 || ...  (== hash_input)
+    std::vector<uint64_t> offsets{0};
+    Fe c_1;
+};
+extern "C" int scb_transcript_new(const scb_field* f, uint32_t kind, scb_transcript** out) {
+    ARG_TRY(f && out, "null argument");
+    auto t = std::make_unique<scb_transcript>();
+    t->f = f->impl;
+    t->kind = kind;
+    *out = t.release();
+    return SCB_OK;
+}
+extern "C" void scb_transcript_free(scb_transcript* t) { delete t; }
+extern "C" int scb_transcript_absorb_round(scb_transcript* t, const uint64_t* parts, uint32_t n_parts, uint32_t n_points, uint64_t* out_r) {
+    ARG_TRY(t && parts && out_r, "null argument");
+    ARG_TRY(n_parts >= 1 && n_points >= 2 && n_points <= kMaxTerms, "bad shape");
+    const HostField& F = t->f->h;
+    std::vector<Fe> ev(n_points, F.zero());
+    for (uint32_t g = 0; g < n_parts; ++g)
+        for (uint32_t x = 0; x < n_points; ++x) {
+            Fe e;
+            F.load(parts + ((size_t)g * n_points + x) * F.n, e);
+            ARG_TRY(F.is_canonical(e), "partial sum is not a canonical field element");
+            ev[x] = F.add(ev[x], e);
+        }
+    if (t->offsets.size() == 1) {  // g_1 = (c_1, poly): c_1 = sum over the hypercube = g_1(0) + g_1(1)
+        t->c_1 = F.add(ev[0], ev[1]);
+        F.serialize(t->c_1, t->bytes);
+    }
+    evals_to_poly(F, t->kind, ev).serialize(F, t->bytes);
+    t->offsets.push_back(t->bytes.size());
+    F.store(hash_to_field(F, t->bytes.data(), t->bytes.size()), out_r);
+    return SCB_OK;
+}
+extern "C" int scb_transcript_c_1(const scb_transcript* t, uint64_t* out_elem) {
+    ARG_TRY(t && out_elem, "null argument");
+    t->f->h.store(t->c_1, out_elem);
+    return SCB_OK;
+}
+extern "C" int scb_transcript_bytes(const scb_transcript* t, uint8_t* out, size_t cap, size_t* out_len, uint64_t* offsets, uint32_t cap_msgs,
+                                    uint32_t* n_msgs) {
+    ARG_TRY(t && out_len && n_msgs, "null argument");
+    *out_len = t->bytes.size();
+    *n_msgs = (uint32_t)t->offsets.size() - 1;
+    if (!out) return SCB_OK;  // size query
+    ARG_TRY(offsets && cap >= t->bytes.size() && cap_msgs + 1 >= t->offsets.size(), "output buffer too small");
+    std::memcpy(out, t->bytes.data(), t->bytes.size());
+    std::memcpy(offsets, t->offsets.data(), 8 * t->offsets.size());
+    return SCB_OK;
+}

@@ -1,0 +1,152 @@
+"""Sharded multi-GPU sum-check prover: one process per GPU, torch.distributed for the plumbing.
+
+Every table is split by its TOP log2(G) index bits: rank g owns the contiguous slab [g*2^lv, (g+1)*2^lv).  ark folds
+variable 0 = index LSB first, so adjacent pairs never straddle ranks and no table data moves while a slab has more
+than ``consolidate_at`` variables.  Per round each rank reduces its slab to (d+1) partial field sums on the device;
+the only exchange is one all-gather of those (d+1)*E bytes per rank; every rank then adds the G rows mod p, derives
+the message polynomial and the Fiat-Shamir challenge (identical on all ranks, so nothing is broadcast) and launches
+the next fused fold+message kernel.  When the slabs are down to 2^consolidate_at entries they are all-gathered once
+and the remaining rounds run replicated on every rank with no further communication.
+
+The transcript is bit-identical to the single-GPU proof of the concatenated tables (tests/test_distributed_gloo.py
+checks this over gloo with an oracle-backed engine; tests/test_gpu_parity.py on NCCL when >1 GPU is present).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import api
+from ._lib import check, lib
+
+
+class LocalEngine:
+    """What the sharded driver needs from the per-rank compute engine.  All tensors are torch.int64 views of
+    Montgomery limbs with shape [..., n_limbs] on the engine's device."""
+
+    F: api.Field
+    kind: int
+    n_points: int
+
+    def num_vars(self) -> int:  # local variables left in this rank's slab
+        raise NotImplementedError
+
+    def round_evals(self, out) -> None:  # out: int64[n_points, n_limbs]
+        raise NotImplementedError
+
+    def fix_and_round_evals(self, r_mont: np.ndarray, out) -> None:
+        raise NotImplementedError
+
+    def slabs(self) -> list:  # current tables as int64[2^num_vars, n_limbs] tensors
+        raise NotImplementedError
+
+    def from_slabs(self, tables: list) -> "LocalEngine":  # engine over (gathered) tables
+        raise NotImplementedError
+
+    def new_buffer(self, shape: Sequence[int]):
+        raise NotImplementedError
+
+
+class CudaProductEngine(LocalEngine):
+    """ProductMLE<K> / matrix_multiplication::G slab on this rank's GPU (libsumcheck_b200.so kernels)."""
+
+    def __init__(self, poly: api.SumCheckPolynomial, keepalive=None):
+        import torch
+
+        self._torch = torch
+        self.poly = poly
+        self.F = poly.F
+        self.kind = poly.kind
+        self.n_points = poly.n_points
+        self._keep = keepalive
+        o = C.c_uint32()
+        check(lib.scb_poly_n_tables(poly._h, C.byref(o)))
+        self.n_tables = o.value
+
+    def num_vars(self) -> int:
+        return self.poly.num_vars()
+
+    def new_buffer(self, shape):
+        return self._torch.empty(list(shape), dtype=self._torch.int64, device="cuda")
+
+    def round_evals(self, out) -> None:
+        check(lib.scb_poly_round_evals_device(self.poly._h, self.n_points, C.c_void_p(out.data_ptr())))
+
+    def fix_and_round_evals(self, r_mont: np.ndarray, out) -> None:
+        h = C.c_void_p()
+        check(lib.scb_poly_fix_and_round_evals_device(self.poly._h, api._p64(r_mont), self.n_points, C.byref(h), C.c_void_p(out.data_ptr())))
+        self.poly = type(self.poly)(self.F, h)
+
+    def slabs(self) -> list:
+        out = []
+        for k in range(self.n_tables):
+            m = self.poly.table(k)
+            t = self.new_buffer([1 << m.num_vars, self.F.n])
+            check(lib.scb_mle_copy_to_device(m._h, C.c_void_p(t.data_ptr())))
+            out.append(t)
+        return out
+
+    def from_slabs(self, tables: list) -> "CudaProductEngine":
+        nv = int(tables[0].shape[0]).bit_length() - 1
+        mles = [api.DenseMultilinearExtension.from_device(self.F, nv, t.data_ptr(), copy=False) for t in tables]
+        if self.kind == api.KIND_MATMUL_G:
+            poly = api.MatMulG.from_tables(mles[0], mles[1])
+        else:
+            poly = api.ProductMLE.new(mles)
+        return CudaProductEngine(poly, keepalive=tables)  # the borrowed tensors must outlive the handles
+
+
+def _all_gather(dist, group, out, inp):
+    if hasattr(dist, "all_gather_into_tensor"):
+        dist.all_gather_into_tensor(out.view(-1), inp.view(-1), group=group)  # rank-order concatenation
+    else:  # pragma: no cover
+        chunks = list(out.chunk(dist.get_world_size(group)))
+        dist.all_gather(chunks, inp, group=group)
+
+
+def prove_sharded(engine: LocalEngine, group=None, consolidate_at: int = 16) -> Tuple[int, List[bytes]]:
+    """Fiat-Shamir sum-check proof of the polynomial whose tables are the rank-order concatenation of every rank's
+    slabs.  Returns (c_1, [g_1 bytes, g_2 bytes, ...]) -- fiat_shamir::generate_transcript's output
+    (fiat-shamir/src/lib.rs:75-98) -- identically on every rank."""
+    import torch.distributed as dist
+
+    G = dist.get_world_size(group) if dist.is_initialized() else 1
+    assert G & (G - 1) == 0, "the number of ranks must be a power of two (tables shard by their top variables)"
+    lg = G.bit_length() - 1
+    consolidate_at = max(1, consolidate_at)
+    F, npts = engine.F, engine.n_points
+    v = engine.num_vars() + lg
+    transcript = api.Transcript(F, engine.kind)
+
+    def gather_tables(eng: LocalEngine) -> LocalEngine:
+        gathered = []
+        for t in eng.slabs():
+            full = eng.new_buffer([G * t.shape[0], t.shape[1]])
+            _all_gather(dist, group, full, t.contiguous())
+            gathered.append(full)
+        return eng.from_slabs(gathered)
+
+    sharded = G > 1
+    if sharded and engine.num_vars() <= consolidate_at:
+        engine, sharded = gather_tables(engine), False
+    mine = engine.new_buffer([npts, F.n])
+    parts = engine.new_buffer([G, npts, F.n]) if sharded else None
+
+    def exchange_and_absorb() -> np.ndarray:
+        if sharded:
+            _all_gather(dist, group, parts, mine)
+            host = parts.cpu().numpy().view(np.uint64)
+        else:
+            host = mine.cpu().numpy().view(np.uint64)[None]
+        return transcript.absorb_round_mont(host).copy()
+
+    engine.round_evals(mine)
+    r = exchange_and_absorb()
+    for _ in range(1, v):
+        if sharded and engine.num_vars() <= consolidate_at:
+            engine, sharded = gather_tables(engine), False
+        engine.fix_and_round_evals(r, mine)
+        r = exchange_and_absorb()
+    return transcript.c_1(), transcript.messages()
