@@ -132,7 +132,9 @@ def test_fiat_shamir_transcript_bytes(OF, kind):
         assert got == want, (kind, v)
         assert T.verify_transcript(got, T.Verifier(v, dg))
         assert O.verify_transcript(OF, got, O.Verifier(v, og))
-        if v >= 2:
+        if v >= 2 and OF.bits > 20:
+            # (the reference's last-round branch checks only g_v(r_v) == g(r), :298-310, so over a tiny field a
+            # tampered coefficient is accepted whenever r_v^deg vanishes; only test where that cannot happen)
             bad = list(got)
             last = bytearray(bad[-1])
             last[-1] ^= 1
