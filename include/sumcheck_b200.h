@@ -149,6 +149,13 @@ int scb_poly_round_evals_device(const scb_poly* p, uint32_t n_points, uint64_t* 
 int scb_poly_fix_and_round_evals_device(const scb_poly* p, const uint64_t* r, uint32_t n_points, scb_poly** out,
                                         uint64_t* d_out);
 
+/* All remaining rounds of a product polynomial (num_vars = m >= 2 -> m-1 rounds of Prover::round, :105-112) in ONE
+ * resident kernel: per round the callback gets the n_points sums and returns the next challenge through a mailbox
+ * in mapped pinned memory -- no launches or stream synchronisation between rounds (latency-bound tail).
+ * The callback returns SCB_OK or an error, which aborts the kernel.  `p` itself is not modified. */
+typedef int (*scb_round_cb)(void* user, uint32_t round, const uint64_t* evals, uint64_t* next_challenge_out);
+int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, uint32_t n_points, scb_round_cb cb, void* user);
+
 /* ------------------------------------------------------------------ round-message algebra (host) */
 /* (d+1) sums at X = 0..d  ->  the SparsePolynomial the reference would send, per implementor:
  * MATMUL_G: interpolate_quadratic_poly (matrix-multiplication/src/lib.rs:17-60, explicit zero terms kept);

@@ -383,3 +383,37 @@ def test_large_prover_verifier_invariants(OF, v, K):
     if OF.n_limbs == 1:
         ev = g.to_evaluations()
         assert T.Prover(g).c_1() == sum(ev) % OF.p
+
+
+# ----------------------------------------------------------------------------- persistent tail kernel
+def test_tail_kernel_matches_per_round_launches():
+    """The resident tail kernel (mailbox in mapped memory) must give the same transcript bytes as one launch per
+    round, for every threshold; SCB_TAIL_VARS is read once per process, hence the subprocesses."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import thaler_study_b200 as T\n"
+        "for p, v, K in ((1572869, 13, 3), (5, 9, 2), (0xFFFFFFFF00000001, 11, 4), (%d, 10, 3)):\n"
+        "    F = T.Field(p)\n"
+        "    g = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, 50 + k) for k in range(K)])\n"
+        "    print(b''.join(T.generate_transcript(T.Prover(g))).hex())\n"
+        "    a = T.DenseMultilinearExtension.synthetic(F, v, 7); b = T.DenseMultilinearExtension.synthetic(F, v, 8)\n"
+        "    print(b''.join(T.generate_transcript(T.Prover(T.MatMulG.from_tables(a, b)))).hex())\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), O.BLS12_381_FR.p)
+    outs = []
+    for tv in ("0", "2", "5", "14", "24"):
+        env = dict(os.environ, SCB_TAIL_VARS=tv)
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300))
+    for o in outs:
+        assert o.returncode == 0, o.stderr[-2000:]
+    assert len(set(o.stdout for o in outs)) == 1
+    assert len(outs[0].stdout.split()) == 8
+    # and the SCB_TAIL_VARS=0 output is the oracle's transcript
+    OF = O.FP1572869
+    cf = CField(OF.p)
+    tabs = [cf.from_mont(cf.synth(50 + k, 0, 1 << 13)) for k in range(3)]
+    want = O.generate_transcript(OF, O.Prover(O.ProductMLE(OF, [O.DenseMLE(OF, 13, t) for t in tabs])))
+    assert outs[0].stdout.split()[0] == b"".join(want).hex()

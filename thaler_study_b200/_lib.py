@@ -18,6 +18,8 @@ u32p = C.POINTER(C.c_uint32)
 u8p = C.POINTER(C.c_uint8)
 vp = C.c_void_p
 vpp = C.POINTER(C.c_void_p)
+# scb_round_cb: int (*)(void* user, uint32_t round, const uint64_t* evals, uint64_t* next_challenge_out)
+ROUND_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, u64p, u64p)
 
 # name -> (restype, argtypes); every symbol include/sumcheck_b200.h declares
 SIGNATURES = {
@@ -70,6 +72,7 @@ SIGNATURES = {
     "scb_poly_fix_and_round_evals": (C.c_int, [vp, u64p, C.c_uint32, vpp, u64p]),
     "scb_poly_round_evals_device": (C.c_int, [vp, C.c_uint32, vp]),
     "scb_poly_fix_and_round_evals_device": (C.c_int, [vp, u64p, C.c_uint32, vpp, vp]),
+    "scb_poly_tail_rounds": (C.c_int, [vp, u64p, C.c_uint32, ROUND_CB, vp]),
     "scb_evals_to_univariate": (C.c_int, [vp, C.c_uint32, u64p, C.c_uint32, u64p, u64p, C.c_uint32, u32p]),
     "scb_unipoly_serialize": (C.c_int, [vp, u64p, u64p, C.c_uint32, u8p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "scb_unipoly_evaluate": (C.c_int, [vp, u64p, u64p, C.c_uint32, u64p, u64p]),

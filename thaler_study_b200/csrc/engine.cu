@@ -14,6 +14,7 @@
 
 #include "internal.hpp"
 #include "kernels.cuh"
+#include "tail.cuh"
 #include "sumcheck_b200.h"
 
 using namespace scb;
@@ -63,6 +64,7 @@ struct Ctx {
     unsigned int* ticket = nullptr;
     uint64_t* h_res = nullptr;     // mapped pinned host memory: kernels write round sums here directly
     uint64_t* d_scratch = nullptr; // small device scratch (points, results)
+    TailMailbox* mailbox = nullptr; // mapped pinned host memory shared with the persistent tail kernel
 };
 static constexpr int kMaxGrid = 148 * 16;
 static constexpr int kMaxDev = 16;
@@ -92,6 +94,8 @@ static int get_ctx(Ctx** out) {
             CU_TRY(cudaMemset(c.ticket, 0, 64));
             CU_TRY(cudaHostAlloc(&c.h_res, 4096, cudaHostAllocMapped | cudaHostAllocPortable));
             CU_TRY(cudaMalloc(&c.d_scratch, 64 * 1024));
+            CU_TRY(cudaHostAlloc(&c.mailbox, sizeof(TailMailbox), cudaHostAllocMapped | cudaHostAllocPortable));
+            std::memset((void*)c.mailbox, 0, sizeof(TailMailbox));
             c.sms = sms;
             c.dev = dev;
         }
@@ -106,6 +110,41 @@ static inline int grid_for(const Ctx* c, uint64_t items, int blocks_per_sm = 8) 
     if (cap > (uint64_t)kMaxGrid) cap = kMaxGrid;
     if (want < 1) want = 1;
     return (int)(want < cap ? want : cap);
+}
+
+// Grid for a grid-stride kernel: exactly one resident wave (SMs x active blocks per SM, from the occupancy
+// calculator, cached per kernel) so that no partial second wave runs at reduced occupancy.
+#include <unordered_map>
+static std::unordered_map<const void*, int> g_occ;
+static std::mutex g_occ_mu;
+// pref_bps > 0 overrides the blocks-per-SM count (measured sweet spots, profiles/r01_kernel_sweep.md):
+// the fused fold+message kernel streams 2 reads : 1 write and peaks at 5 CTAs/SM, the read-only message
+// kernel keeps improving up to two full waves.
+template <class KernelT>
+static int occ_grid(const Ctx* c, KernelT kernel, uint64_t items, size_t dyn_smem = 0, int pref_bps = 0) {
+    int nb = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_occ_mu);
+        auto it = g_occ.find((const void*)kernel);
+        if (it == g_occ.end()) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kThreads, dyn_smem) != cudaSuccess || nb < 1) nb = 1;
+            g_occ[(const void*)kernel] = nb;
+        } else {
+            nb = it->second;
+        }
+    }
+    if (pref_bps > 0) nb = pref_bps;
+    static const int bps_env = getenv("SCB_BPS") ? atoi(getenv("SCB_BPS")) : 0;
+    if (bps_env > 0) nb = bps_env;
+    uint64_t want = (items + kThreads - 1) / kThreads;
+    uint64_t cap = (uint64_t)c->sms * nb;
+    if (cap > (uint64_t)kMaxGrid) cap = kMaxGrid;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+static int tune_unroll() {
+    static const int u = getenv("SCB_UNROLL") ? atoi(getenv("SCB_UNROLL")) : 1;
+    return u;
 }
 
 #define LAUNCH_CHECK()                                                                      \
@@ -754,7 +793,14 @@ static int launch_round_evals(Ctx* c, const scb_poly* p, uint64_t* res) {
         DISPATCH_POLICY(f.policy, DISPATCH_K(p->t.size(), {
             TabsIn<K> in;
             for (int k = 0; k < K; ++k) in.p[k] = p->t[k].buf->ptr;
-            k_round_evals<A, K><<<grid_for(c, n_pairs), kThreads, 0, g_stream>>>(f.d, in, n_pairs, c->partials, c->ticket, res);
+            if (A::N == 1 && n_pairs >= 2) {
+                constexpr int PV = A::N == 1 ? 2 : 1;
+                auto kern = k_round_evals<A, K, PV>;
+                kern<<<occ_grid(c, kern, n_pairs / PV, 0, A::kLight ? 16 : 0), kThreads, 0, g_stream>>>(f.d, in, n_pairs / PV, c->partials, c->ticket, res);
+            } else {
+                auto kern = k_round_evals<A, K, 1>;
+                kern<<<occ_grid(c, kern, n_pairs), kThreads, 0, g_stream>>>(f.d, in, n_pairs, c->partials, c->ticket, res);
+            }
         }));
     } else if (p->kind == SCB_POLY_TRIANGLE_G) {
         const uint32_t xn = tri_xn(p), yn = tri_yn(p), zn = tri_zn(p);
@@ -828,7 +874,14 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
                 in.p[k] = p->t[k].buf->ptr;
                 o.p[k] = q->t[k].buf->ptr;
             }
-            k_fold_round<A, K><<<grid_for(c, n_quads), kThreads, 0, g_stream>>>(f.d, in, o, ra, n_quads, c->partials, c->ticket, res);
+            if (A::N == 1 && tune_unroll() == 2) {
+                constexpr int U = A::N == 1 ? 2 : 1;
+                auto kern = k_fold_round<A, K, U>;
+                kern<<<occ_grid(c, kern, (n_quads + U - 1) / U), kThreads, 0, g_stream>>>(f.d, in, o, ra, n_quads, c->partials, c->ticket, res);
+            } else {
+                auto kern = k_fold_round<A, K, 1>;
+                kern<<<occ_grid(c, kern, n_quads, 0, A::kLight ? 5 : 0), kThreads, 0, g_stream>>>(f.d, in, o, ra, n_quads, c->partials, c->ticket, res);
+            }
         }));
         LAUNCH_CHECK();
     } else {
@@ -921,6 +974,88 @@ extern "C" int scb_poly_to_evaluations(const scb_poly* p, uint64_t* out, size_t 
     CU_TRY(cudaMemcpyAsync(out, tmp->ptr, (size_t)8 * f.d.n << nv, cudaMemcpyDeviceToHost, g_stream));
     CU_TRY(cudaStreamSynchronize(g_stream));
     return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ persistent tail
+// Runs ALL remaining rounds of a product polynomial (m = num_vars >= 2 -> m-1 rounds) in one resident kernel
+// (tail.cuh).  For round t the callback receives the n_points sums and returns the next challenge.
+extern "C" int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, uint32_t n_points, scb_round_cb cb, void* user) {
+    ARG_TRY(p && r_first && cb, "null argument");
+    ARG_TRY(p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G, "the persistent tail handles product polynomials only");
+    ARG_TRY(n_points == poly_n_points(p), "n_points must be the full message size");
+    const uint32_t m = p->t[0].nv;
+    ARG_TRY(m >= 2 && m <= 24, "tail needs 2..24 variables");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    const FieldImpl& f = *p->f;
+    const uint32_t N = f.d.n, n_rounds = m - 1;
+    ARG_TRY(elem_canonical(f, r_first), "challenge is not a canonical field element");
+    std::vector<BufRef> ba(p->t.size()), bb(p->t.size());
+    for (size_t k = 0; k < p->t.size(); ++k) {
+        RC_TRY(alloc_buf((size_t)8 * N << (m - 1), &ba[k]));
+        RC_TRY(alloc_buf((size_t)8 * N << (m - 1), &bb[k]));
+    }
+    TailMailbox* mb = c->mailbox;
+    std::memset((void*)mb, 0, sizeof(TailMailbox));
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    const ElemArg ra = elem_arg(f, r_first);
+    const uint64_t timeout_ns = 5ull * 1000 * 1000 * 1000;
+    DISPATCH_POLICY(f.policy, DISPATCH_K(p->t.size(), {
+        TabsIn<K> in;
+        TabsOut<K> oa, ob;
+        for (int k = 0; k < K; ++k) {
+            in.p[k] = p->t[k].buf->ptr;
+            oa.p[k] = ba[k]->ptr;
+            ob.p[k] = bb[k]->ptr;
+        }
+        k_tail_rounds<A, K><<<1, tail_threads<A>(), 0, g_stream>>>(f.d, in, oa, ob, ra, m, n_rounds, mb, timeout_ns);
+    }));
+    LAUNCH_CHECK();
+    int rc = SCB_OK;
+    uint64_t evals[kMaxPts * kMaxLimbs], next_r[kMaxLimbs];
+    for (uint32_t t = 0; t < n_rounds && rc == SCB_OK; ++t) {
+        uint64_t spins = 0;
+        while (mb->seq_dev < (uint64_t)t + 1) {
+            if (mb->dev_status == 2) {
+                set_error("tail kernel timed out waiting for a challenge");
+                rc = SCB_ECUDA;
+                break;
+            }
+            if ((++spins & 0xFFFFF) == 0) {  // every ~1M polls make sure the kernel is still alive
+                cudaError_t q = cudaStreamQuery(g_stream);
+                if (q != cudaErrorNotReady && mb->seq_dev < (uint64_t)t + 1) {
+                    set_error("tail kernel ended early: %s", cudaGetErrorString(q));
+                    rc = SCB_ECUDA;
+                    break;
+                }
+            }
+        }
+        if (rc != SCB_OK) break;
+        std::atomic_thread_fence(std::memory_order_acquire);
+        for (uint32_t i = 0; i < n_points * N; ++i) evals[i] = mb->evals[i];
+        rc = cb(user, t, evals, next_r);
+        if (rc != SCB_OK) break;
+        if (t + 1 < n_rounds) {
+            if (!elem_canonical(f, next_r)) {
+                set_error("challenge is not a canonical field element");
+                rc = SCB_EINVAL;
+                break;
+            }
+            for (uint32_t i = 0; i < N; ++i) mb->challenge[i] = next_r[i];
+            std::atomic_thread_fence(std::memory_order_release);
+            mb->seq_host = (uint64_t)t + 1;
+        }
+    }
+    if (rc != SCB_OK) {
+        mb->abort_flag = 1;
+        std::atomic_thread_fence(std::memory_order_seq_cst);
+    }
+    cudaError_t e = cudaStreamSynchronize(g_stream);
+    if (e != cudaSuccess && rc == SCB_OK) {
+        set_error("tail kernel failed: %s", cudaGetErrorString(e));
+        rc = SCB_ECUDA;
+    }
+    return rc;
 }
 
 // accessor used by protocol.cpp

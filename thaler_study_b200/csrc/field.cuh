@@ -25,6 +25,7 @@ namespace scb {
 // "lazy" value < 2^32.  mul() accepts one operand < 2^32 and one < 2^31 and returns a value <= p.
 // ------------------------------------------------------------------------------------------
 struct PolSP {
+    static constexpr bool kLight = true;  // few registers per element (launch-bounds class)
     static constexpr int N = 1;   // u64 words per element in memory
     static constexpr int AW = 1;  // u64 words per accumulator
     using El = uint32_t;
@@ -70,6 +71,7 @@ struct PolSP {
 // PolG1: one 64-bit limb, any odd modulus.
 // ------------------------------------------------------------------------------------------
 struct PolG1 {
+    static constexpr bool kLight = false;
     static constexpr int N = 1;
     static constexpr int AW = 1;
     using El = uint64_t;
@@ -141,6 +143,7 @@ __device__ __forceinline__ void mac64(uint64_t& t, uint64_t a, uint64_t b, uint6
 
 template <int NL>
 struct PolGN {
+    static constexpr bool kLight = false;
     static constexpr int N = NL;
     static constexpr int AW = NL;
     using El = ElN<NL>;

@@ -135,6 +135,54 @@ inline std::vector<uint8_t> expand_message_xmd(const uint8_t* msg, size_t msg_le
     return out;
 }
 
+// Incremental form of the same chain: the hash input of round j is the concatenation g_1 || ... || g_j
+// (fiat-shamir/src/lib.rs:82-92), so the SHA-256 state after Z_pad || g_1 || ... || g_j is kept and only the
+// new message bytes are compressed each round (identical digest, O(new bytes) instead of O(all bytes)).
+class FsChain {
+   public:
+    explicit FsChain(const HostField& F) : F_(F), L_((F.bits + 128 + 7) / 8) {
+        std::vector<uint8_t> z_pad(L_, 0);
+        prefix_.update(z_pad.data(), z_pad.size());
+    }
+    void absorb(const uint8_t* data, size_t n) { prefix_.update(data, n); }
+    // hash_to_field::<1>(everything absorbed so far)[0]
+    Fe challenge() const {
+        const size_t ell = (L_ + 31) / 32;
+        const uint8_t dst_prime[1] = {0};  // DST = "" => DST' = I2OSP(0, 1)
+        uint8_t lib_str[2] = {(uint8_t)(L_ >> 8), (uint8_t)L_};
+        uint8_t b0[32], bi[32], zero = 0, one = 1;
+        Sha256 h = prefix_;
+        h.update(lib_str, 2);
+        h.update(&zero, 1);
+        h.update(dst_prime, 1);
+        h.finalize(b0);
+        h.reset();
+        h.update(b0, 32);
+        h.update(&one, 1);
+        h.update(dst_prime, 1);
+        h.finalize(bi);
+        uint8_t uniform[96];
+        std::memcpy(uniform, bi, 32);
+        for (size_t i = 2; i <= ell && i <= 3; ++i) {
+            uint8_t x[32];
+            for (int k = 0; k < 32; ++k) x[k] = b0[k] ^ bi[k];
+            h.reset();
+            h.update(x, 32);
+            uint8_t ib = (uint8_t)i;
+            h.update(&ib, 1);
+            h.update(dst_prime, 1);
+            h.finalize(bi);
+            std::memcpy(uniform + 32 * (i - 1), bi, 32);
+        }
+        return F_.from_be_bytes_mod_order(uniform, L_);
+    }
+
+   private:
+    const HostField& F_;
+    size_t L_;
+    Sha256 prefix_;
+};
+
 // hasher.hash_to_field::<1>(msg)[0] with H::new(&[])
 inline Fe hash_to_field(const HostField& F, const uint8_t* msg, size_t len) {
     const size_t L = (F.bits + 128 + 7) / 8;

@@ -7,7 +7,11 @@
 // non-zero coefficients.
 #pragma once
 #include <algorithm>
+#include <array>
 #include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -130,6 +134,82 @@ inline SparsePoly interpolate_quadratic_poly(const HostField& F, const Fe (&x)[3
     };
     SparsePoly p1 = basis(0, 1, 2), p2 = basis(1, 0, 2), p3 = basis(2, 0, 1);
     return p1.add(F, p2).add(F, p3);
+}
+
+// Per-field constants of the two interpolations, computed once (the field inversions are the expensive part:
+// a Fermat inversion is ~380 multiplications in a 255-bit field).
+struct InterpConsts {
+    Fe x[3];           // 0, 1, 2
+    Fe den_inv[3];     // 1/((x_a-x_b)(x_a-x_c)) for the three Lagrange basis polynomials on {0,1,2}
+    std::vector<std::vector<Fe>> basis[10];  // basis[n][i][k] = coefficient k of the i-th Lagrange basis on {0..n-1}
+};
+inline const InterpConsts& interp_consts(const HostField& F) {
+    static std::mutex mu;
+    static std::map<std::array<uint64_t, kHostMaxLimbs>, std::unique_ptr<InterpConsts>> cache;
+    std::array<uint64_t, kHostMaxLimbs> key{{F.p[0], F.p[1], F.p[2], F.p[3]}};
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return *it->second;
+    auto c = std::make_unique<InterpConsts>();
+    c->x[0] = F.zero();
+    c->x[1] = F.one();
+    c->x[2] = F.add(F.one(), F.one());
+    const int perm[3][3] = {{0, 1, 2}, {1, 0, 2}, {2, 0, 1}};
+    for (int a = 0; a < 3; ++a) {
+        Fe den = F.mul(F.sub(c->x[perm[a][0]], c->x[perm[a][1]]), F.sub(c->x[perm[a][0]], c->x[perm[a][2]]));
+        c->den_inv[a] = F.inverse(den);
+    }
+    for (size_t n = 1; n < 10; ++n) {
+        if (F.n == 1 && (uint64_t)n > F.p[0]) break;  // points 0..n-1 must be distinct mod p
+        c->basis[n].assign(n, std::vector<Fe>());
+        for (size_t i = 0; i < n; ++i) {
+            std::vector<Fe> num(1, F.one());
+            Fe den = F.one();
+            for (size_t j = 0; j < n; ++j) {
+                if (j == i) continue;
+                Fe fj = F.from_u64(j);
+                std::vector<Fe> nn(num.size() + 1, F.zero());
+                for (size_t k = 0; k < num.size(); ++k) {
+                    nn[k + 1] = F.add(nn[k + 1], num[k]);
+                    nn[k] = F.sub(nn[k], F.mul(fj, num[k]));
+                }
+                num.swap(nn);
+                den = F.mul(den, F.sub(F.from_u64(i), fj));
+            }
+            Fe dinv = F.inverse(den);
+            for (auto& v : num) v = F.mul(v, dinv);
+            c->basis[n][i] = num;
+        }
+    }
+    auto* raw = c.get();
+    cache[key] = std::move(c);
+    return *raw;
+}
+
+// interpolate_quadratic_poly on the fixed points X = 0, 1, 2 with the three denominators' inverses cached:
+// same terms, same explicit zeros, same merge order as the literal function above.
+inline SparsePoly interpolate_quadratic_012(const HostField& F, const InterpConsts& c, const Fe (&y)[3]) {
+    auto basis = [&](int a, int b, int cc) {
+        std::vector<std::pair<uint64_t, Fe>> co;
+        co.emplace_back(0, F.mul(c.x[b], c.x[cc]));
+        co.emplace_back(1, F.sub(F.neg(c.x[b]), c.x[cc]));
+        co.emplace_back(2, F.one());
+        for (auto& t : co) t.second = F.mul(F.mul(t.second, y[a]), c.den_inv[a]);
+        return SparsePoly::from_coefficients_vec(F, std::move(co));
+    };
+    SparsePoly p1 = basis(0, 1, 2), p2 = basis(1, 0, 2), p3 = basis(2, 0, 1);
+    return p1.add(F, p2).add(F, p3);
+}
+
+// Same coefficients as lagrange_to_coeffs below, from the cached basis (sum_i y_i * basis_i).
+inline std::vector<Fe> lagrange_to_coeffs_cached(const HostField& F, const InterpConsts& c, const std::vector<Fe>& ys) {
+    const size_t n = ys.size();
+    std::vector<Fe> coeffs(n, F.zero());
+    const auto& B = c.basis[n];
+    for (size_t i = 0; i < n; ++i)
+        for (size_t k = 0; k < n; ++k) coeffs[k] = F.add(coeffs[k], F.mul(ys[i], B[i][k]));
+    while (!coeffs.empty() && F.is_zero(coeffs.back())) coeffs.pop_back();
+    return coeffs;
 }
 
 // Coefficients of the unique polynomial of degree <= d through (0,y0)..(d,yd), trailing zeros

@@ -158,36 +158,56 @@ __device__ __forceinline__ void pair_into_prod(const A& ar, bool first, const ty
 // ------------------------------------------------------------------------------------------
 // K2a  round message of a product of K dense MLEs over the same variables.
 // Replaces G::to_univariate's pass over adjacent pairs (matrix-multiplication/src/lib.rs:110-122)
-// generalised to K tables / X = 0..K.  One hypercube pair per thread-iteration.
+// generalised to K tables / X = 0..K.  PV adjacent hypercube pairs per thread-iteration
+// (PV = 2 for one-limb fields: one 256-bit load per table per iteration).
 // ------------------------------------------------------------------------------------------
-template <class A, int K>
-__global__ void __launch_bounds__(kThreads) k_round_evals(FieldDesc f, TabsIn<K> in, uint64_t n_pairs,
-                                                          uint64_t* partials, unsigned int* ticket, uint64_t* out) {
+template <class A, int K, int PV>
+constexpr int round_min_blocks() {  // resident CTAs per SM the register budget is tuned for
+    if (A::N > 1) return 1;
+    if (A::kLight) return (PV == 1 || K <= 2) ? 8 : 6;
+    return K <= 2 ? 6 : 4;
+}
+template <class A, int K, int U>
+constexpr int fold_min_blocks() {
+    if (A::N > 1) return 1;
+    if (A::kLight) return U == 1 ? (K <= 3 ? 8 : 6) : 5;
+    return K <= 2 ? 6 : (U == 1 ? 4 : 3);
+}
+
+template <class A, int K, int PV>
+__global__ void __launch_bounds__(kThreads, (round_min_blocks<A, K, PV>())) k_round_evals(FieldDesc f, TabsIn<K> in, uint64_t n_groups,
+                                                                            uint64_t* partials, unsigned int* ticket, uint64_t* out) {
     constexpr int NP = K + 1, N = A::N;
     const A ar(f);
     typename A::Acc acc[NP];
 #pragma unroll
     for (int x = 0; x < NP; ++x) ar.acc_zero(acc[x]);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += stride) {
-        typename A::Lz prod[NP];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_groups; i += stride) {
         if constexpr (N == 1) {
-            uint64_t w[K][2];
+            uint64_t w[K][2 * PV];
 #pragma unroll
-            for (int k = 0; k < K; ++k) ld_words<2>(in.p[k] + i * 2, w[k]);
+            for (int k = 0; k < K; ++k) ld_words<2 * PV>(in.p[k] + i * 2 * PV, w[k]);
 #pragma unroll
-            for (int k = 0; k < K; ++k)
-                pair_into_prod<A, NP>(ar, k == 0, ar.from_words(&w[k][0]), ar.from_words(&w[k][1]), prod);
+            for (int e = 0; e < PV; ++e) {
+                typename A::Lz prod[NP];
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    pair_into_prod<A, NP>(ar, k == 0, ar.from_words(&w[k][2 * e]), ar.from_words(&w[k][2 * e + 1]), prod);
+#pragma unroll
+                for (int x = 0; x < NP; ++x) ar.acc_add(acc[x], prod[x]);
+            }
         } else {
+            typename A::Lz prod[NP];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 uint64_t w[2 * N];
                 ld_words<2 * N>(in.p[k] + i * 2 * N, w);
                 pair_into_prod<A, NP>(ar, k == 0, ar.from_words(w), ar.from_words(w + N), prod);
             }
-        }
 #pragma unroll
-        for (int x = 0; x < NP; ++x) ar.acc_add(acc[x], prod[x]);
+            for (int x = 0; x < NP; ++x) ar.acc_add(acc[x], prod[x]);
+        }
     }
     grid_reduce_finish<A, NP>(ar, acc, partials, ticket, out);
 }
@@ -196,38 +216,56 @@ __global__ void __launch_bounds__(kThreads) k_round_evals(FieldDesc f, TabsIn<K>
 // K3+K2  fused fold(r) + next round message.  Replaces, for round j >= 1,
 //   self.g = self.g.fix_variables(&[r_prev]); self.g.to_univariate()
 // (sum-check-protocol/src/lib.rs:105-112) with ONE pass: each thread-iteration loads 4 adjacent
-// entries of every table, folds them to 2 ([ARK] fix_variables: t[b] = t[2b] + r (t[2b+1]-t[2b])),
-// stores the 2 folded entries (canonical) and accumulates the message of that folded pair.
+// entries of every table (one 256-bit load for one-limb fields), folds them to 2 ([ARK] fix_variables:
+// t[b] = t[2b] + r (t[2b+1]-t[2b])), stores the 2 folded entries (canonical, one 128-bit store) and
+// accumulates the message of that folded pair.  U independent quads per iteration (more loads in flight).
 // Traffic: read M, write M/2 per table -- the 4*K*2^v*E total of SURVEY 8d.
 // ------------------------------------------------------------------------------------------
-template <class A, int K>
-__global__ void __launch_bounds__(kThreads) k_fold_round(FieldDesc f, TabsIn<K> in, TabsOut<K> outp, ElemArg rarg,
-                                                         uint64_t n_quads, uint64_t* partials, unsigned int* ticket,
-                                                         uint64_t* out) {
+template <class A, int K, int U>
+__global__ void __launch_bounds__(kThreads, (fold_min_blocks<A, K, U>()))
+    k_fold_round(FieldDesc f, TabsIn<K> in, TabsOut<K> outp, ElemArg rarg, uint64_t n_quads, uint64_t* partials, unsigned int* ticket,
+                 uint64_t* out) {
     constexpr int NP = K + 1, N = A::N;
+    static_assert(N == 1 || U == 1, "unrolling is only implemented for one-limb fields");
     const A ar(f);
     const typename A::El r = ar.from_words(rarg.w);
     typename A::Acc acc[NP];
 #pragma unroll
     for (int x = 0; x < NP; ++x) ar.acc_zero(acc[x]);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_quads; i += stride) {
-        typename A::Lz prod[NP];
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_quads; i0 += stride * U) {
         if constexpr (N == 1) {
-            uint64_t w[K][4];
+            uint64_t w[U][K][4];
 #pragma unroll
-            for (int k = 0; k < K; ++k) ld_words<4>(in.p[k] + i * 4, w[k]);
+            for (int u = 0; u < U; ++u) {
+                const uint64_t i = i0 + (uint64_t)u * stride;
+                if (u == 0 || i < n_quads) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                typename A::El u0 = ar.fold(ar.from_words(&w[k][0]), ar.from_words(&w[k][1]), r);
-                typename A::El u1 = ar.fold(ar.from_words(&w[k][2]), ar.from_words(&w[k][3]), r);
-                uint64_t o[2];
-                ar.to_words(u0, &o[0]);
-                ar.to_words(u1, &o[1]);
-                st_words<2>(outp.p[k] + i * 2, o);
-                pair_into_prod<A, NP>(ar, k == 0, u0, u1, prod);
+                    for (int k = 0; k < K; ++k) ld_words<4>(in.p[k] + i * 4, w[u][k]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint64_t i = i0 + (uint64_t)u * stride;
+                if (u == 0 || i < n_quads) {
+                    typename A::Lz prod[NP];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        typename A::El u0 = ar.fold(ar.from_words(&w[u][k][0]), ar.from_words(&w[u][k][1]), r);
+                        typename A::El u1 = ar.fold(ar.from_words(&w[u][k][2]), ar.from_words(&w[u][k][3]), r);
+                        uint64_t o[2];
+                        ar.to_words(u0, &o[0]);
+                        ar.to_words(u1, &o[1]);
+                        st_words<2>(outp.p[k] + i * 2, o);
+                        pair_into_prod<A, NP>(ar, k == 0, u0, u1, prod);
+                    }
+#pragma unroll
+                    for (int x = 0; x < NP; ++x) ar.acc_add(acc[x], prod[x]);
+                }
             }
         } else {
+            const uint64_t i = i0;
+            typename A::Lz prod[NP];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 uint64_t w[4 * N];
@@ -240,9 +278,9 @@ __global__ void __launch_bounds__(kThreads) k_fold_round(FieldDesc f, TabsIn<K> 
                 st_words<2 * N>(outp.p[k] + i * 2 * N, o);
                 pair_into_prod<A, NP>(ar, k == 0, u0, u1, prod);
             }
-        }
 #pragma unroll
-        for (int x = 0; x < NP; ++x) ar.acc_add(acc[x], prod[x]);
+            for (int x = 0; x < NP; ++x) ar.acc_add(acc[x], prod[x]);
+        }
     }
     grid_reduce_finish<A, NP>(ar, acc, partials, ticket, out);
 }

@@ -36,14 +36,15 @@ static constexpr uint32_t kMaxTerms = 8;
 
 // (d+1) sums -> the univariate::SparsePolynomial each implementor's to_univariate returns
 static SparsePoly evals_to_poly(const HostField& F, uint32_t kind, const std::vector<Fe>& ev) {
+    const InterpConsts& c = interp_consts(F);
     if (kind == SCB_POLY_MATMUL_G && ev.size() == 3) {
         // matrix-multiplication/src/lib.rs:124-130
-        const Fe x[3] = {F.zero(), F.one(), F.add(F.one(), F.one())};
         const Fe y[3] = {ev[0], ev[1], ev[2]};
-        return interpolate_quadratic_poly(F, x, y);
+        return interpolate_quadratic_012(F, c, y);
     }
     // triangle-counting/src/lib.rs:128-131, gkr-protocol/src/round_polynomial.rs:86-89 (`p.into()`),
     // and ProductMLE<K>: unique interpolant, Dense -> Sparse
+    if (ev.size() < 10 && !c.basis[ev.size()].empty()) return SparsePoly::from_dense(F, lagrange_to_coeffs_cached(F, c, ev));
     return SparsePoly::from_dense(F, lagrange_to_coeffs(F, ev));
 }
 
@@ -293,23 +294,66 @@ extern "C" int scb_verifier_round(scb_verifier* v, const uint64_t* degrees, cons
 }
 
 // ------------------------------------------------------------------------------------------ fiat-shamir
+// Tables of at most 2^tail_max_vars() entries are finished by the persistent tail kernel (0 disables it).
+static uint32_t tail_max_vars() {
+    static const uint32_t v = getenv("SCB_TAIL_VARS") ? (uint32_t)atoi(getenv("SCB_TAIL_VARS")) : 14;
+    return v > 24 ? 24 : v;
+}
+struct TailCtx {
+    const HostField* F;
+    uint32_t kind;
+    std::vector<uint8_t>* hash_input;
+    FsChain* chain;
+    uint64_t* offsets;
+    uint32_t j;   // protocol round of the tail's round 0
+    uint32_t np;  // sums per round
+};
+// one tail round on the host: sums -> message polynomial -> bytes -> hash chain -> next challenge
+static int tail_round_cb(void* user, uint32_t t, const uint64_t* evals, uint64_t* next_r) {
+    TailCtx* tc = (TailCtx*)user;
+    const HostField& F = *tc->F;
+    std::vector<Fe> ev(tc->np);
+    for (size_t i = 0; i < ev.size(); ++i) F.load(evals + i * F.n, ev[i]);
+    const size_t before = tc->hash_input->size();
+    evals_to_poly(F, tc->kind, ev).serialize(F, *tc->hash_input);
+    tc->chain->absorb(tc->hash_input->data() + before, tc->hash_input->size() - before);
+    tc->offsets[tc->j + t + 1] = tc->hash_input->size();
+    F.store(tc->chain->challenge(), next_r);
+    return SCB_OK;
+}
+
 extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t cap, size_t* out_len, uint64_t* offsets) {
     // fiat-shamir/src/lib.rs:75-98 with InteractiveProver for Prover (:44-66)
     ARG_TRY(p && out && out_len && offsets, "null argument");
     const HostField& F = p->fi->h;
     std::vector<uint8_t> hash_input;  // == concatenation of all messages so far
+    FsChain chain(F);                 // SHA-256 state over the same bytes, advanced incrementally
     SparsePoly sp;
     Fe dummy;
     // g_1 = (c_1, round(F::one(), 0)).serialize_uncompressed()
     RC_TRY(prover_round(p, &dummy, 0, &sp));
     F.serialize(p->c_1, hash_input);
     sp.serialize(F, hash_input);
+    chain.absorb(hash_input.data(), hash_input.size());
     offsets[0] = 0;
     offsets[1] = hash_input.size();
+    const bool product = p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G;
+    const uint32_t tail_vars = tail_max_vars();
     for (uint32_t j = 1; j < p->num_vars; ++j) {
-        Fe r_j = hash_to_field(F, hash_input.data(), hash_input.size());
+        Fe r_j = chain.challenge();  // == hash_to_field(hash_input)
+        const uint32_t live = p->num_vars - (j - 1);  // variables of the table about to be folded
+        if (product && tail_vars >= 2 && live <= tail_vars && live >= 2) {
+            // latency-bound tail: all remaining rounds in one resident kernel, challenges through a mailbox
+            TailCtx tc{&F, p->kind, &hash_input, &chain, offsets, j, p->np};
+            uint64_t rw[kHostMaxLimbs];
+            F.store(r_j, rw);
+            RC_TRY(scb_poly_tail_rounds(p->g, rw, p->np, tail_round_cb, &tc));
+            break;
+        }
         RC_TRY(prover_round(p, &r_j, j, &sp));
+        const size_t before = hash_input.size();
         sp.serialize(F, hash_input);
+        chain.absorb(hash_input.data() + before, hash_input.size() - before);
         offsets[j + 1] = hash_input.size();
     }
     ARG_TRY(hash_input.size() <= cap, "transcript buffer too small");
@@ -365,12 +409,14 @@ struct scb_transcript {
     std::vector<uint8_t> bytes;      // g_1 || g_2 || ...  (== hash_input)
     std::vector<uint64_t> offsets{0};
     Fe c_1;
+    std::unique_ptr<FsChain> chain;
 };
 extern "C" int scb_transcript_new(const scb_field* f, uint32_t kind, scb_transcript** out) {
     ARG_TRY(f && out, "null argument");
     auto t = std::make_unique<scb_transcript>();
     t->f = f->impl;
     t->kind = kind;
+    t->chain = std::make_unique<FsChain>(t->f->h);
     *out = t.release();
     return SCB_OK;
 }
@@ -387,13 +433,15 @@ extern "C" int scb_transcript_absorb_round(scb_transcript* t, const uint64_t* pa
             ARG_TRY(F.is_canonical(e), "partial sum is not a canonical field element");
             ev[x] = F.add(ev[x], e);
         }
+    const size_t before = t->bytes.size();
     if (t->offsets.size() == 1) {  // g_1 = (c_1, poly): c_1 = sum over the hypercube = g_1(0) + g_1(1)
         t->c_1 = F.add(ev[0], ev[1]);
         F.serialize(t->c_1, t->bytes);
     }
     evals_to_poly(F, t->kind, ev).serialize(F, t->bytes);
     t->offsets.push_back(t->bytes.size());
-    F.store(hash_to_field(F, t->bytes.data(), t->bytes.size()), out_r);
+    t->chain->absorb(t->bytes.data() + before, t->bytes.size() - before);
+    F.store(t->chain->challenge(), out_r);
     return SCB_OK;
 }
 extern "C" int scb_transcript_c_1(const scb_transcript* t, uint64_t* out_elem) {

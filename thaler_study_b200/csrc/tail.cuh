@@ -1,0 +1,157 @@
+// tail.cuh -- persistent single-CTA kernel for the latency-bound tail of a product sum-check.
+//
+// Once the live tables are small (<= 2^kTailMaxVars entries) a round is a few microseconds of work and
+// the per-round cost is dominated by launch + completion latency (hard part 5).
+// Fiat-Shamir makes round j+1 depend on the hash of round j's message, so rounds cannot be batched;
+// instead ONE kernel stays resident for all remaining rounds and talks to the host through a mailbox in
+// mapped pinned memory: it posts the (d+1) round sums, the host derives the challenge with the unchanged
+// transcript code (interpolation, serialization, SHA-256 -- the part that decides transcript bytes) and
+// posts it back.  No kernel launches, no stream synchronisation, two PCIe posted writes per round.
+//
+// Same arithmetic as k_fold_round (kernels.cuh); buffers written inside this kernel are read back with
+// ld.global.cg (never through the non-coherent path).
+#pragma once
+#include <cstdint>
+
+#include "kernels.cuh"
+
+namespace scb {
+
+constexpr uint32_t kTailMaxRounds = 32;
+
+// Mapped pinned host memory.  seq_dev / seq_host count completed posts (monotone within one kernel).
+struct TailMailbox {
+    volatile uint64_t seq_dev;                    // device -> host: round sums of round `seq_dev` are valid
+    uint64_t evals[kMaxPts * kMaxLimbs];
+    volatile uint64_t seq_host;                   // host -> device: challenge number `seq_host` is valid
+    uint64_t challenge[kMaxLimbs];
+    volatile uint64_t abort_flag;                 // host -> device: give up (error on the host side)
+    volatile uint64_t dev_status;                 // device -> host: 0 running, 1 done, 2 timed out
+};
+
+template <int W>
+__device__ __forceinline__ void ld_words_cg(const uint64_t* ptr, uint64_t* w) {
+    if constexpr (W % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < W; i += 2)
+            asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(w[i]), "=l"(w[i + 1]) : "l"(ptr + i) : "memory");
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(w[i]) : "l"(ptr + i) : "memory");
+    }
+}
+__device__ __forceinline__ uint64_t ld_sys(const volatile uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys(volatile uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <class A>
+constexpr int tail_threads() {
+    return A::kLight ? 1024 : (A::N == 1 ? 512 : 256);
+}
+
+// Runs `n_rounds` fused fold+message rounds on tables of 2^m entries (m >= 2, n_rounds <= m - 1).
+// Round 0 folds by `r0`; round t > 0 folds by challenge number t posted by the host.
+template <class A, int K>
+__global__ void __launch_bounds__(tail_threads<A>(), 1)
+    k_tail_rounds(FieldDesc f, TabsIn<K> in0, TabsOut<K> buf_a, TabsOut<K> buf_b, ElemArg r0, uint32_t m, uint32_t n_rounds,
+                  TailMailbox* mb, uint64_t timeout_ns) {
+    constexpr int NP = K + 1, N = A::N;
+    const A ar(f);
+    __shared__ uint64_t sm[32 * NP * A::AW];
+    __shared__ uint64_t r_sm[kMaxLimbs];
+    __shared__ int abort_sm;
+    const uint64_t* src[K];
+    uint64_t* dst[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        src[k] = in0.p[k];
+        dst[k] = buf_a.p[k];
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) r_sm[i] = r0.w[i];
+        abort_sm = 0;
+    }
+    __syncthreads();
+    for (uint32_t t = 0; t < n_rounds; ++t) {
+        if (t > 0) {
+            if (threadIdx.x == 0) {  // wait for the host's challenge number t
+                const uint64_t t0 = globaltimer_ns();
+                int bad = 0;
+                while (ld_sys(&mb->seq_host) < t) {
+                    if (ld_sys(&mb->abort_flag) != 0 || globaltimer_ns() - t0 > timeout_ns) {
+                        bad = 1;
+                        break;
+                    }
+                }
+                __threadfence_system();
+                if (!bad) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) r_sm[i] = ld_sys(&mb->challenge[i]);
+                }
+                abort_sm = bad;
+            }
+            __syncthreads();
+            if (abort_sm) {
+                if (threadIdx.x == 0) st_sys(&mb->dev_status, 2);
+                return;
+            }
+        }
+        const typename A::El r = ar.from_words(r_sm);
+        typename A::Acc acc[NP];
+#pragma unroll
+        for (int x = 0; x < NP; ++x) ar.acc_zero(acc[x]);
+        const uint64_t n_quads = 1ull << (m - 2);
+        for (uint64_t i = threadIdx.x; i < n_quads; i += blockDim.x) {
+            typename A::Lz prod[NP];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                uint64_t w[4 * N];
+                ld_words_cg<4 * N>(src[k] + i * 4 * N, w);
+                typename A::El u0 = ar.fold(ar.from_words(w), ar.from_words(w + N), r);
+                typename A::El u1 = ar.fold(ar.from_words(w + 2 * N), ar.from_words(w + 3 * N), r);
+                uint64_t o[2 * N];
+                ar.to_words(u0, o);
+                ar.to_words(u1, o + N);
+#pragma unroll
+                for (int q = 0; q < 2 * N; ++q) __stcg(dst[k] + i * 2 * N + q, o[q]);
+                pair_into_prod<A, NP>(ar, k == 0, u0, u1, prod);
+            }
+#pragma unroll
+            for (int x = 0; x < NP; ++x) ar.acc_add(acc[x], prod[x]);
+        }
+        block_reduce<A, NP>(ar, acc, sm);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int x = 0; x < NP; ++x) {
+                uint64_t w[N];
+                ar.to_words(ar.acc_final(acc[x]), w);
+#pragma unroll
+                for (int i = 0; i < N; ++i) st_sys(&mb->evals[x * N + i], w[i]);
+            }
+            __threadfence_system();
+            st_sys(&mb->seq_dev, (uint64_t)t + 1);
+        }
+        __syncthreads();  // folded tables written by all threads are visible to the next round
+        m -= 1;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint64_t* s = dst[k];
+            dst[k] = (t & 1) ? buf_a.p[k] : buf_b.p[k];
+            src[k] = s;
+        }
+    }
+    if (threadIdx.x == 0) st_sys(&mb->dev_status, 1);
+}
+
+}  // namespace scb
