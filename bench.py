@@ -215,27 +215,37 @@ def run_ours(args):
     # ---- roofline of the dominant kernel: k_fold_round<PolSP,3> on the full tables (round 1 of every proof)
     roof = None
     if rank == 0:
+        # Timed alone, on the same kernel variant the proof runs in round 1: with the small-prime policy the prover's
+        # folded tables are packed uint32 (packed.cuh), so the launch reads 2^v ark elements (E bytes) per table and
+        # writes 2^(v-1) 4-byte entries; otherwise it writes 2^(v-1) E-byte elements (SURVEY 8d's 1.5*K*2^v*E).
+        packed = F.policy == 0 and os.environ.get("SCB_PACKED", "1") != "0"
+        gk = g.clone().allow_packed(packed)
         d_out = torch.empty([K + 1, F.n], dtype=torch.int64, device="cuda")
         r = 123456 % p
         times = []
         for i in range(3 + max(args.steps, 5)):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            nxt = g.fix_and_round_evals_device(r, d_out.data_ptr())
+            nxt = gk.fix_and_round_evals_device(r, d_out.data_ptr())
             b.record()
             torch.cuda.synchronize()
             if i >= 3:
                 times.append(a.elapsed_time(b))
             del nxt
         kms = sum(times) / len(times)
-        alg_bytes = 1.5 * K * (1 << v) * E  # read every table once, write the folded half (4K*2^v*E over all rounds)
+        survey_bytes = 1.5 * K * (1 << v) * E
+        alg_bytes = K * (1 << v) * (E + (2 if packed else E / 2))
+        proof_bytes = K * (1 << v) * (3.0 * E if packed else 4.0 * E)  # packed: 8+8+2+3*(1+1/2+..)=24 B per entry-column
         peak, peak_src = hbm_peak()
         achieved = alg_bytes / (kms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_fold_round<PolSP,3> (fused fold + round message), 2^%d-entry tables" % v,
+        kname = "k_fold_round_sp<3,in=u64,out=u32>" if packed else "k_fold_round<%s,3>" % {0: "PolSP", 1: "PolG1", 4: "PolGN<4>"}[F.policy]
+        roof = {"bound": "hbm", "kernel": kname + " (fused fold + round message), 2^%d-entry tables" % v,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "proof_algorithmic_bytes": 4.0 * K * (1 << v) * E,
-                "proof_frac_of_hbm_roofline": (4.0 * K * (1 << v) * E / (ms * 1e-3) / 1e9) / peak}
+                "survey_bytes_per_launch_unpacked": survey_bytes, "frac_vs_survey_bytes": survey_bytes / (kms * 1e-3) / 1e9 / peak,
+                "proof_bytes_moved": proof_bytes, "proof_frac_of_hbm_roofline": (proof_bytes / (ms * 1e-3) / 1e9) / peak,
+                "proof_survey_bytes": 4.0 * K * (1 << v) * E,
+                "proof_frac_vs_survey_bytes": (4.0 * K * (1 << v) * E / (ms * 1e-3) / 1e9) / peak}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: the same proof through the C ABI with HOST tables (pinned), H2D inside the timed region

@@ -149,6 +149,12 @@ int scb_poly_round_evals_device(const scb_poly* p, uint32_t n_points, uint64_t* 
 int scb_poly_fix_and_round_evals_device(const scb_poly* p, const uint64_t* r, uint32_t n_points, scb_poly** out,
                                         uint64_t* d_out);
 
+/* Opt-in layout optimisation for one-limb fields with p < 2^28 (all of the reference's moduli): polynomials
+ * DERIVED from `p` by the fix_and_round calls may keep their (internal, never exposed) folded tables as packed
+ * uint32 -- a quarter less HBM traffic over a proof, same field elements.  Every other entry point converts such a
+ * handle back to ark's 8-byte layout on entry, so behaviour is unchanged.  scb_prover_new enables it on its clone. */
+int scb_poly_allow_packed(scb_poly* p, int enable);
+
 /* All remaining rounds of a product polynomial (num_vars = m >= 2 -> m-1 rounds of Prover::round, :105-112) in ONE
  * resident kernel: per round the callback gets the n_points sums and returns the next challenge through a mailbox
  * in mapped pinned memory -- no launches or stream synchronisation between rounds (latency-bound tail).

@@ -11,4 +11,5 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | 
 echo "== bench"
 timeout 900 python bench.py --steps 10 --warmup 3 2>gpurun_out/bench.err | tee gpurun_out/bench.json
 tail -5 gpurun_out/bench.err
-for tv in 0 10 12 16 18; do echo "== tail_vars=$tv"; SCB_TAIL_VARS=$tv timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline 2>>gpurun_out/bench.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['gpu_launches'])"; done
+echo "== unpacked for comparison"
+SCB_PACKED=0 timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline 2>>gpurun_out/bench.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['gpu_launches'])"

@@ -295,6 +295,11 @@ class SumCheckPolynomial:
         check(lib.scb_poly_n_points(self._h, C.byref(o)))
         return o.value
 
+    def allow_packed(self, enable: bool = True) -> "SumCheckPolynomial":
+        """Let polynomials derived from this handle keep packed uint32 folded tables (scb_poly_allow_packed)."""
+        check(lib.scb_poly_allow_packed(self._h, 1 if enable else 0))
+        return self
+
     def table(self, idx: int) -> DenseMultilinearExtension:
         h = C.c_void_p()
         check(lib.scb_poly_table(self._h, idx, C.byref(h)))

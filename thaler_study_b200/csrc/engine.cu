@@ -14,6 +14,7 @@
 
 #include "internal.hpp"
 #include "kernels.cuh"
+#include "packed.cuh"
 #include "tail.cuh"
 #include "sumcheck_b200.h"
 
@@ -205,6 +206,7 @@ static int alloc_buf(size_t bytes, BufRef* out) {
 struct Table {
     uint32_t nv = 0;
     BufRef buf;
+    bool p32 = false;  // packed uint32 entries (internal intermediate of the small-prime policy, packed.cuh)
     uint64_t len() const { return 1ull << nv; }
 };
 
@@ -218,7 +220,20 @@ struct scb_poly {
     std::shared_ptr<FieldImpl> f;
     std::vector<Table> t;
     uint32_t var_len = 0;  // triangle_counting::G::var_len
+    bool allow_packed = false;  // descendants produced by fix_and_round may keep packed uint32 tables
+    bool any_packed() const {
+        for (const Table& x : t)
+            if (x.p32) return true;
+        return false;
+    }
 };
+
+// packed-table helpers (defined next to the fused kernels below)
+static int unpack_table(Ctx* c, const FieldImpl& f, const Table& in, Table* out);
+static int plain_poly(const scb_poly* p, std::unique_ptr<scb_poly>* holder, const scb_poly** out);
+#define PLAIN_POLY(p)                             \
+    std::unique_ptr<scb_poly> plain_holder__;     \
+    RC_TRY(plain_poly(p, &plain_holder__, &p))
 
 static ElemArg elem_arg(const FieldImpl& f, const uint64_t* w) {
     ElemArg a;
@@ -681,6 +696,7 @@ extern "C" int scb_poly_n_tables(const scb_poly* p, uint32_t* out) {
 }
 extern "C" int scb_poly_table(const scb_poly* p, uint32_t idx, scb_mle** out) {
     ARG_TRY(p && out, "null argument");
+    PLAIN_POLY(p);
     ARG_TRY(idx < p->t.size(), "table index out of range");
     *out = new scb_mle{p->f, p->t[idx]};
     return SCB_OK;
@@ -699,6 +715,7 @@ extern "C" int scb_poly_num_vars(const scb_poly* p, uint32_t* out) {
 // SumCheckPolynomial::evaluate
 extern "C" int scb_poly_evaluate(const scb_poly* p, const uint64_t* point, uint32_t n_point, uint64_t* out_elem) {
     ARG_TRY(p && out_elem && (point || n_point == 0), "null argument");
+    PLAIN_POLY(p);
     ARG_TRY(n_point == poly_num_vars(p), "point dimension does not match num_vars");
     Ctx* c;
     RC_TRY(get_ctx(&c));
@@ -748,6 +765,7 @@ extern "C" int scb_poly_evaluate(const scb_poly* p, const uint64_t* point, uint3
 // SumCheckPolynomial::fix_variables
 extern "C" int scb_poly_fix_variables(const scb_poly* p, const uint64_t* pp, uint32_t n, scb_poly** out) {
     ARG_TRY(p && out && (pp || n == 0), "null argument");
+    PLAIN_POLY(p);
     Ctx* c;
     RC_TRY(get_ctx(&c));
     const FieldImpl& f = *p->f;
@@ -823,6 +841,7 @@ static int launch_round_evals(Ctx* c, const scb_poly* p, uint64_t* res) {
 
 static int round_evals_impl(const scb_poly* p, uint32_t n_points, uint64_t* h_out, uint64_t* d_out) {
     ARG_TRY(p && (h_out || d_out), "null argument");
+    PLAIN_POLY(p);
     ARG_TRY(n_points >= 1 && n_points <= poly_n_points(p), "n_points out of range for this polynomial");
     Ctx* c;
     RC_TRY(get_ctx(&c));
@@ -845,6 +864,47 @@ extern "C" int scb_poly_round_evals_device(const scb_poly* p, uint32_t n_points,
     return round_evals_impl(p, n_points, nullptr, d_out);
 }
 
+// small-prime fused fold+message with packed uint32 tables on either side (packed.cuh)
+template <int K, bool IN32, bool OUT32, int QP>
+static void launch_fold_sp(Ctx* c, const FieldDesc& d, TabsIn<K> in, TabsOut<K> o, ElemArg ra, uint64_t n_quads, uint64_t* res) {
+    auto kern = k_fold_round_sp<K, IN32, OUT32, QP>;
+    kern<<<occ_grid(c, kern, n_quads / QP, 0, 5), kThreads, 0, g_stream>>>(d, in, o, ra, n_quads / QP, c->partials, c->ticket, res);
+}
+
+// Polynomials with packed tables only exist as descendants of a handle marked with scb_poly_allow_packed; every
+// entry point other than the round/tail calls first converts them back to ark's 8-byte layout.
+static int unpack_table(Ctx* c, const FieldImpl& f, const Table& in, Table* out) {
+    if (!in.p32) {
+        *out = in;
+        return SCB_OK;
+    }
+    Table o;
+    o.nv = in.nv;
+    RC_TRY(alloc_buf((size_t)8 * f.d.n << in.nv, &o.buf));
+    k_unpack32<<<grid_for(c, in.len()), kThreads, 0, g_stream>>>((const uint32_t*)in.buf->ptr, o.buf->ptr, in.len());
+    LAUNCH_CHECK();
+    *out = o;
+    return SCB_OK;
+}
+static int plain_poly(const scb_poly* p, std::unique_ptr<scb_poly>* holder, const scb_poly** out) {
+    if (!p->any_packed()) {
+        *out = p;
+        return SCB_OK;
+    }
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    auto q = std::make_unique<scb_poly>(*p);
+    for (size_t k = 0; k < p->t.size(); ++k) RC_TRY(unpack_table(c, *p->f, p->t[k], &q->t[k]));
+    *holder = std::move(q);
+    *out = holder->get();
+    return SCB_OK;
+}
+extern "C" int scb_poly_allow_packed(scb_poly* p, int enable) {
+    ARG_TRY(p, "null argument");
+    p->allow_packed = enable != 0;
+    return SCB_OK;
+}
+
 // fused fold + message (product kinds: one kernel; mixed-arity kinds: fold kernels then message kernel)
 static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_points, scb_poly** out, uint64_t* h_out, uint64_t* d_out) {
     ARG_TRY(p && r && out && (h_out || d_out), "null argument");
@@ -861,12 +921,32 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
         ARG_TRY(f.policy != POL_SP || p->t[0].nv <= 32, "table too large for the small-prime path");
         q = std::make_unique<scb_poly>(*p);
         const uint64_t n_quads = p->t[0].len() / 4;
+        // small-prime policy: the folded tables may be stored as packed uint32 when the handle allows it
+        const bool in32 = p->t[0].p32;
+        const bool out32 = f.policy == POL_SP && p->allow_packed;
         for (size_t k = 0; k < p->t.size(); ++k) {
+            ARG_TRY(p->t[k].p32 == in32, "tables of one polynomial must share a layout");
             q->t[k].nv = p->t[k].nv - 1;
             q->t[k].buf.reset();
-            RC_TRY(alloc_buf((size_t)8 * N << q->t[k].nv, &q->t[k].buf));
+            q->t[k].p32 = out32;
+            RC_TRY(alloc_buf((size_t)(out32 ? 4 : 8 * N) << q->t[k].nv, &q->t[k].buf));
         }
         const ElemArg ra = elem_arg(f, r);
+        if (f.policy == POL_SP && (in32 || out32)) {
+            DISPATCH_K(p->t.size(), {
+                TabsIn<K> in;
+                TabsOut<K> o;
+                for (int k = 0; k < K; ++k) {
+                    in.p[k] = p->t[k].buf->ptr;
+                    o.p[k] = q->t[k].buf->ptr;
+                }
+                if (!in32) launch_fold_sp<K, false, true, 1>(c, f.d, in, o, ra, n_quads, res);
+                else if (n_quads >= 2 && out32) launch_fold_sp<K, true, true, 2>(c, f.d, in, o, ra, n_quads, res);
+                else if (n_quads >= 2) launch_fold_sp<K, true, false, 2>(c, f.d, in, o, ra, n_quads, res);
+                else if (out32) launch_fold_sp<K, true, true, 1>(c, f.d, in, o, ra, n_quads, res);
+                else launch_fold_sp<K, true, false, 1>(c, f.d, in, o, ra, n_quads, res);
+            });
+        } else
         DISPATCH_POLICY(f.policy, DISPATCH_K(p->t.size(), {
             TabsIn<K> in;
             TabsOut<K> o;
@@ -909,6 +989,7 @@ extern "C" int scb_poly_fix_and_round_evals_device(const scb_poly* p, const uint
 // c_1 (Prover::new)
 extern "C" int scb_poly_sum(const scb_poly* p, uint64_t* out_elem) {
     ARG_TRY(p && out_elem, "null argument");
+    PLAIN_POLY(p);
     Ctx* c;
     RC_TRY(get_ctx(&c));
     const FieldImpl& f = *p->f;
@@ -945,6 +1026,7 @@ extern "C" int scb_poly_sum(const scb_poly* p, uint64_t* out_elem) {
 // SumCheckPolynomial::to_evaluations
 extern "C" int scb_poly_to_evaluations(const scb_poly* p, uint64_t* out, size_t cap_elems) {
     ARG_TRY(p && out, "null argument");
+    PLAIN_POLY(p);
     Ctx* c;
     RC_TRY(get_ctx(&c));
     const FieldImpl& f = *p->f;
@@ -1008,7 +1090,7 @@ extern "C" int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, 
             oa.p[k] = ba[k]->ptr;
             ob.p[k] = bb[k]->ptr;
         }
-        k_tail_rounds<A, K><<<1, tail_threads<A>(), 0, g_stream>>>(f.d, in, oa, ob, ra, m, n_rounds, mb, timeout_ns);
+        k_tail_rounds<A, K><<<1, tail_threads<A>(), 0, g_stream>>>(f.d, in, oa, ob, ra, m, n_rounds, mb, timeout_ns, p->t[0].p32 ? 1 : 0);
     }));
     LAUNCH_CHECK();
     int rc = SCB_OK;

@@ -131,6 +131,10 @@ extern "C" int scb_hash_to_field(const scb_field* f, const uint8_t* msg, size_t 
 }
 
 // ------------------------------------------------------------------------------------------ Prover
+static int packed_enabled() {
+    static const int v = getenv("SCB_PACKED") ? atoi(getenv("SCB_PACKED")) : 1;
+    return v;
+}
 struct scb_prover {
     scb_poly* g = nullptr;      // g: P
     Fe c_1;                     // c_1: F
@@ -148,6 +152,7 @@ extern "C" int scb_prover_new(const scb_poly* g, scb_prover** out) {
     ARG_TRY(g && out, "null argument");
     auto p = std::make_unique<scb_prover>();
     RC_TRY(scb_poly_clone(g, &p->g));
+    RC_TRY(scb_poly_allow_packed(p->g, packed_enabled()));  // the prover's folded tables are private to it
     RC_TRY(scb_poly_field_impl(g, &p->fi));
     RC_TRY(scb_poly_kind_of(g, &p->kind));
     RC_TRY(scb_poly_n_points(g, &p->np));

@@ -54,6 +54,43 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
     return t;
 }
 
+// one quad (4 adjacent entries) of a table that is either in ark's 8-byte format or packed uint32 (PolSP only)
+template <class A>
+__device__ __forceinline__ void tail_ld_quad(const A& ar, const uint64_t* base, uint64_t i, bool w32, typename A::El (&t)[4]) {
+    constexpr int N = A::N;
+    if constexpr (A::kLight) {
+        if (w32) {
+            uint64_t w[2];
+            ld_words_cg<2>(base + i * 2, w);
+            t[0] = (uint32_t)w[0];
+            t[1] = (uint32_t)(w[0] >> 32);
+            t[2] = (uint32_t)w[1];
+            t[3] = (uint32_t)(w[1] >> 32);
+            return;
+        }
+    }
+    uint64_t w[4 * N];
+    ld_words_cg<4 * N>(base + i * 4 * N, w);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) t[q] = ar.from_words(w + q * N);
+}
+template <class A>
+__device__ __forceinline__ void tail_st_pair(const A& ar, uint64_t* base, uint64_t i, bool w32, const typename A::El& u0,
+                                             const typename A::El& u1) {
+    constexpr int N = A::N;
+    if constexpr (A::kLight) {
+        if (w32) {
+            __stcg(base + i, (uint64_t)u0 | ((uint64_t)u1 << 32));
+            return;
+        }
+    }
+    uint64_t o[2 * N];
+    ar.to_words(u0, o);
+    ar.to_words(u1, o + N);
+#pragma unroll
+    for (int q = 0; q < 2 * N; ++q) __stcg(base + i * 2 * N + q, o[q]);
+}
+
 template <class A>
 constexpr int tail_threads() {
     return A::kLight ? 1024 : (A::N == 1 ? 512 : 256);
@@ -64,7 +101,10 @@ constexpr int tail_threads() {
 template <class A, int K>
 __global__ void __launch_bounds__(tail_threads<A>(), 1)
     k_tail_rounds(FieldDesc f, TabsIn<K> in0, TabsOut<K> buf_a, TabsOut<K> buf_b, ElemArg r0, uint32_t m, uint32_t n_rounds,
-                  TailMailbox* mb, uint64_t timeout_ns) {
+                  TailMailbox* mb, uint64_t timeout_ns, int in0_w32) {
+    // the internal ping-pong buffers are packed uint32 for the small-prime policy; the input may be either
+    bool src_w32 = A::kLight && in0_w32 != 0;
+    const bool buf_w32 = A::kLight;
     constexpr int NP = K + 1, N = A::N;
     const A ar(f);
     __shared__ uint64_t sm[32 * NP * A::AW];
@@ -116,15 +156,11 @@ __global__ void __launch_bounds__(tail_threads<A>(), 1)
             typename A::Lz prod[NP];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                uint64_t w[4 * N];
-                ld_words_cg<4 * N>(src[k] + i * 4 * N, w);
-                typename A::El u0 = ar.fold(ar.from_words(w), ar.from_words(w + N), r);
-                typename A::El u1 = ar.fold(ar.from_words(w + 2 * N), ar.from_words(w + 3 * N), r);
-                uint64_t o[2 * N];
-                ar.to_words(u0, o);
-                ar.to_words(u1, o + N);
-#pragma unroll
-                for (int q = 0; q < 2 * N; ++q) __stcg(dst[k] + i * 2 * N + q, o[q]);
+                typename A::El t4[4];
+                tail_ld_quad<A>(ar, src[k], i, src_w32, t4);
+                typename A::El u0 = ar.fold(t4[0], t4[1], r);
+                typename A::El u1 = ar.fold(t4[2], t4[3], r);
+                tail_st_pair<A>(ar, dst[k], i, buf_w32, u0, u1);
                 pair_into_prod<A, NP>(ar, k == 0, u0, u1, prod);
             }
 #pragma unroll
@@ -144,6 +180,7 @@ __global__ void __launch_bounds__(tail_threads<A>(), 1)
         }
         __syncthreads();  // folded tables written by all threads are visible to the next round
         m -= 1;
+        src_w32 = buf_w32;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const uint64_t* s = dst[k];

@@ -61,6 +61,7 @@ class CudaProductEngine(LocalEngine):
         self.kind = poly.kind
         self.n_points = poly.n_points
         self._keep = keepalive
+        check(lib.scb_poly_allow_packed(poly._h, 1))  # this engine owns its private clone of the tables
         o = C.c_uint32()
         check(lib.scb_poly_n_tables(poly._h, C.byref(o)))
         self.n_tables = o.value
