@@ -37,7 +37,9 @@ typedef enum scb_status {
     SCB_ECUDA = -3,    /* CUDA runtime error or no device */
     SCB_ENCCL = -4,    /* reserved for the multi-GPU exchange */
     SCB_EVERIFY = -5,  /* sum_check_protocol::Error::ProverClaimMismatch (:26-27) */
-    SCB_ENOPOLY = -6   /* sum_check_protocol::Error::NoPolySet (:29-30) */
+    SCB_ENOPOLY = -6,  /* sum_check_protocol::Error::NoPolySet (:29-30) */
+    SCB_ETAIL = -7     /* the resident tail kernel lost lock-step with the host (e.g. under a serialising profiler);
+                          *rounds_done rounds were completed, the caller continues with one launch per round */
 } scb_status;
 
 typedef struct scb_field scb_field;       /* a prime field (MontConfig of the reference, e.g. :349-354) */
@@ -160,7 +162,8 @@ int scb_poly_allow_packed(scb_poly* p, int enable);
  * in mapped pinned memory -- no launches or stream synchronisation between rounds (latency-bound tail).
  * The callback returns SCB_OK or an error, which aborts the kernel.  `p` itself is not modified. */
 typedef int (*scb_round_cb)(void* user, uint32_t round, const uint64_t* evals, uint64_t* next_challenge_out);
-int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, uint32_t n_points, scb_round_cb cb, void* user);
+int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, uint32_t n_points, scb_round_cb cb, void* user,
+                         uint32_t* rounds_done);
 
 /* ------------------------------------------------------------------ round-message algebra (host) */
 /* (d+1) sums at X = 0..d  ->  the SparsePolynomial the reference would send, per implementor:

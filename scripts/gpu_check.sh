@@ -8,8 +8,8 @@ echo "== pytest -m gpu"
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
 echo "== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.log
+echo "== kbench"
+python scripts/kbench.py --iters 20 | tee gpurun_out/kbench.json
 echo "== bench"
 timeout 900 python bench.py --steps 10 --warmup 3 2>gpurun_out/bench.err | tee gpurun_out/bench.json
 tail -5 gpurun_out/bench.err
-echo "== unpacked for comparison"
-SCB_PACKED=0 timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline 2>>gpurun_out/bench.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['gpu_launches'])"

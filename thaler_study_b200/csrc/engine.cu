@@ -868,7 +868,9 @@ extern "C" int scb_poly_round_evals_device(const scb_poly* p, uint32_t n_points,
 template <int K, bool IN32, bool OUT32, int QP>
 static void launch_fold_sp(Ctx* c, const FieldDesc& d, TabsIn<K> in, TabsOut<K> o, ElemArg ra, uint64_t n_quads, uint64_t* res) {
     auto kern = k_fold_round_sp<K, IN32, OUT32, QP>;
-    kern<<<occ_grid(c, kern, n_quads / QP, 0, 5), kThreads, 0, g_stream>>>(d, in, o, ra, n_quads / QP, c->partials, c->ticket, res);
+    static const int bps32 = getenv("SCB_BPS32") ? atoi(getenv("SCB_BPS32")) : 8;
+    const int pref = IN32 ? bps32 : 5;  // measured sweet spots (profiles/r01_kernel_sweep.md)
+    kern<<<occ_grid(c, kern, n_quads / QP, 0, pref), kThreads, 0, g_stream>>>(d, in, o, ra, n_quads / QP, c->partials, c->ticket, res);
 }
 
 // Polynomials with packed tables only exist as descendants of a handle marked with scb_poly_allow_packed; every
@@ -932,6 +934,7 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
             RC_TRY(alloc_buf((size_t)(out32 ? 4 : 8 * N) << q->t[k].nv, &q->t[k].buf));
         }
         const ElemArg ra = elem_arg(f, r);
+        static const int qp32 = getenv("SCB_QP32") && atoi(getenv("SCB_QP32")) > 0 ? atoi(getenv("SCB_QP32")) : 4;
         if (f.policy == POL_SP && (in32 || out32)) {
             DISPATCH_K(p->t.size(), {
                 TabsIn<K> in;
@@ -940,11 +943,15 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
                     in.p[k] = p->t[k].buf->ptr;
                     o.p[k] = q->t[k].buf->ptr;
                 }
-                if (!in32) launch_fold_sp<K, false, true, 1>(c, f.d, in, o, ra, n_quads, res);
-                else if (n_quads >= 2 && out32) launch_fold_sp<K, true, true, 2>(c, f.d, in, o, ra, n_quads, res);
-                else if (n_quads >= 2) launch_fold_sp<K, true, false, 2>(c, f.d, in, o, ra, n_quads, res);
-                else if (out32) launch_fold_sp<K, true, true, 1>(c, f.d, in, o, ra, n_quads, res);
-                else launch_fold_sp<K, true, false, 1>(c, f.d, in, o, ra, n_quads, res);
+                if (!in32) launch_fold_sp<K, false, true, 1>(c, f.d, in, o, ra, n_quads, res);  // out32 holds here
+                else if (out32) {
+                    if (n_quads >= 4 && qp32 >= 4) launch_fold_sp<K, true, true, 4>(c, f.d, in, o, ra, n_quads, res);
+                    else if (n_quads >= 2 && qp32 >= 2) launch_fold_sp<K, true, true, 2>(c, f.d, in, o, ra, n_quads, res);
+                    else launch_fold_sp<K, true, true, 1>(c, f.d, in, o, ra, n_quads, res);
+                } else {
+                    if (n_quads >= 2) launch_fold_sp<K, true, false, 2>(c, f.d, in, o, ra, n_quads, res);
+                    else launch_fold_sp<K, true, false, 1>(c, f.d, in, o, ra, n_quads, res);
+                }
             });
         } else
         DISPATCH_POLICY(f.policy, DISPATCH_K(p->t.size(), {
@@ -1061,8 +1068,10 @@ extern "C" int scb_poly_to_evaluations(const scb_poly* p, uint64_t* out, size_t 
 // ------------------------------------------------------------------------------------------ persistent tail
 // Runs ALL remaining rounds of a product polynomial (m = num_vars >= 2 -> m-1 rounds) in one resident kernel
 // (tail.cuh).  For round t the callback receives the n_points sums and returns the next challenge.
-extern "C" int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, uint32_t n_points, scb_round_cb cb, void* user) {
-    ARG_TRY(p && r_first && cb, "null argument");
+extern "C" int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, uint32_t n_points, scb_round_cb cb, void* user,
+                                    uint32_t* rounds_done) {
+    ARG_TRY(p && r_first && cb && rounds_done, "null argument");
+    *rounds_done = 0;
     ARG_TRY(p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G, "the persistent tail handles product polynomials only");
     ARG_TRY(n_points == poly_n_points(p), "n_points must be the full message size");
     const uint32_t m = p->t[0].nv;
@@ -1081,7 +1090,7 @@ extern "C" int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, 
     std::memset((void*)mb, 0, sizeof(TailMailbox));
     std::atomic_thread_fence(std::memory_order_seq_cst);
     const ElemArg ra = elem_arg(f, r_first);
-    const uint64_t timeout_ns = 5ull * 1000 * 1000 * 1000;
+    const uint64_t timeout_ns = 250ull * 1000 * 1000;  // normal host turn-around is microseconds
     DISPATCH_POLICY(f.policy, DISPATCH_K(p->t.size(), {
         TabsIn<K> in;
         TabsOut<K> oa, ob;
@@ -1099,8 +1108,8 @@ extern "C" int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, 
         uint64_t spins = 0;
         while (mb->seq_dev < (uint64_t)t + 1) {
             if (mb->dev_status == 2) {
-                set_error("tail kernel timed out waiting for a challenge");
-                rc = SCB_ECUDA;
+                set_error("the resident tail kernel lost lock-step with the host (serialising profiler?)");
+                rc = SCB_ETAIL;
                 break;
             }
             if ((++spins & 0xFFFFF) == 0) {  // every ~1M polls make sure the kernel is still alive
@@ -1117,6 +1126,7 @@ extern "C" int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, 
         for (uint32_t i = 0; i < n_points * N; ++i) evals[i] = mb->evals[i];
         rc = cb(user, t, evals, next_r);
         if (rc != SCB_OK) break;
+        *rounds_done = t + 1;
         if (t + 1 < n_rounds) {
             if (!elem_canonical(f, next_r)) {
                 set_error("challenge is not a canonical field element");

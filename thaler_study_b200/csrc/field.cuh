@@ -49,6 +49,28 @@ struct PolSP {
     }
     __device__ __forceinline__ Lz lz_mul(Lz a, Lz b) const { return redc((uint64_t)a * b); }
     __device__ __forceinline__ El mul(El a, El b) const { return reduce_once(lz_mul(a, b)); }
+    // One 32-bit Montgomery step: T * 2^-32 mod p for T < 2^63, result < T/2^32 + p.  The round kernels use it for
+    // every product (3 multiply-class instructions instead of 5) and repair the missing powers of 2^-32 where that
+    // is free: in the fold the factor is folded into the per-kernel constant (fold_const), in the K-fold message
+    // products it is a constant per output sum, applied once by the finishing thread (msg_final).
+    __device__ __forceinline__ uint32_t redc32(uint64_t T) const {
+        uint32_t m = (uint32_t)T * ninv;
+        return (uint32_t)((T + (uint64_t)m * p) >> 32);
+    }
+    using FoldC = uint32_t;
+    __device__ __forceinline__ FoldC fold_const(El r) const { return reduce_once(redc32(r)); }  // r * 2^-32
+    // t0 + r*(t1 - t0) with rc = fold_const(r): redc32(d * rc) = d * r * 2^-64 = the Montgomery product.
+    // d < 2p, rc < p  =>  redc32 < p + 2p^2/2^32 < 1.125 p  =>  sum < 2.125 p: two conditional subtractions.
+    __device__ __forceinline__ El fold_c(El t0, El t1, FoldC rc) const {
+        return reduce_once(reduce_once(t0 + redc32((uint64_t)(t1 - t0 + p) * rc)));
+    }
+    __device__ __forceinline__ Lz msg_mul(Lz a, Lz b) const { return redc32((uint64_t)a * b); }  // a*b*2^-32, < 2^31 + p
+    // sum of products of k Montgomery values each computed with (k-1) msg_mul steps: multiply by 2^(-32(k-1))
+    __device__ __forceinline__ El msg_final(const Acc& a, int k) const {
+        uint32_t x = (uint32_t)(a % p);
+        for (int i = 1; i < k; ++i) x = reduce_once(redc32(x));
+        return x;
+    }
     __device__ __forceinline__ El add(El a, El b) const { return reduce_once(a + b); }
     __device__ __forceinline__ El sub(El a, El b) const { return a >= b ? a - b : a - b + p; }
     // t0 + r*(t1 - t0), canonical
@@ -102,6 +124,11 @@ struct PolG1 {
         return (c || t2 >= p) ? t2 - p : t2;
     }
     __device__ __forceinline__ El fold(El t0, El t1, El r) const { return add(t0, mul(sub(t1, t0), r)); }
+    using FoldC = El;
+    __device__ __forceinline__ FoldC fold_const(const El& r) const { return r; }
+    __device__ __forceinline__ El fold_c(const El& t0, const El& t1, const FoldC& rc) const { return fold(t0, t1, rc); }
+    __device__ __forceinline__ Lz msg_mul(const Lz& a, const Lz& b) const { return lz_mul(a, b); }
+    __device__ __forceinline__ El msg_final(const Acc& a, int) const { return acc_final(a); }
     __device__ __forceinline__ Lz lz(El a) const { return a; }
     __device__ __forceinline__ Lz lz_diff(El a, El b) const { return sub(a, b); }
     __device__ __forceinline__ Lz lz_add(Lz a, Lz b) const { return add(a, b); }
@@ -270,6 +297,11 @@ struct PolGN {
         return r;
     }
     __device__ __forceinline__ El fold(const El& t0, const El& t1, const El& r) const { return add(t0, mul(sub(t1, t0), r)); }
+    using FoldC = El;
+    __device__ __forceinline__ FoldC fold_const(const El& r) const { return r; }
+    __device__ __forceinline__ El fold_c(const El& t0, const El& t1, const FoldC& rc) const { return fold(t0, t1, rc); }
+    __device__ __forceinline__ Lz msg_mul(const Lz& a, const Lz& b) const { return lz_mul(a, b); }
+    __device__ __forceinline__ El msg_final(const Acc& a, int) const { return acc_final(a); }
     __device__ __forceinline__ Lz lz(const El& a) const { return a; }
     __device__ __forceinline__ Lz lz_diff(const El& a, const El& b) const { return sub(a, b); }
     __device__ __forceinline__ Lz lz_add(const Lz& a, const Lz& b) const { return add(a, b); }

@@ -92,7 +92,7 @@ __device__ __forceinline__ void block_reduce(const A& ar, typename A::Acc (&acc)
 // commutative, so the result is bit-identical for any grid size or arrival order.
 template <class A, int NP>
 __device__ __forceinline__ void grid_reduce_finish(const A& ar, typename A::Acc (&acc)[NP], uint64_t* partials,
-                                                   unsigned int* ticket, uint64_t* out) {
+                                                   unsigned int* ticket, uint64_t* out, int msg_k = 0) {
     constexpr int AW = A::AW;
     __shared__ uint64_t sm[32 * NP * AW];
     __shared__ bool is_last;
@@ -130,7 +130,7 @@ __device__ __forceinline__ void grid_reduce_finish(const A& ar, typename A::Acc 
 #pragma unroll
         for (int x = 0; x < NP; ++x) {
             uint64_t w[A::N];
-            ar.to_words(ar.acc_final(acc[x]), w);
+            ar.to_words(ar.msg_final(acc[x], msg_k), w);
 #pragma unroll
             for (int i = 0; i < A::N; ++i) out[x * A::N + i] = w[i];
         }
@@ -151,7 +151,7 @@ __device__ __forceinline__ void pair_into_prod(const A& ar, bool first, const ty
     for (int x = 0; x < NP; ++x) {
         if (x == 1) v = ar.lz(hi);  // exact hi instead of lo + d keeps the lazy bound tight
         else if (x > 1) v = ar.lz_add(v, d);
-        prod[x] = first ? v : ar.lz_mul(prod[x], v);
+        prod[x] = first ? v : ar.msg_mul(prod[x], v);
     }
 }
 
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, (round_min_blocks<A, K, PV>())) k_ro
             for (int x = 0; x < NP; ++x) ar.acc_add(acc[x], prod[x]);
         }
     }
-    grid_reduce_finish<A, NP>(ar, acc, partials, ticket, out);
+    grid_reduce_finish<A, NP>(ar, acc, partials, ticket, out, K);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, (fold_min_blocks<A, K, U>()))
     constexpr int NP = K + 1, N = A::N;
     static_assert(N == 1 || U == 1, "unrolling is only implemented for one-limb fields");
     const A ar(f);
-    const typename A::El r = ar.from_words(rarg.w);
+    const typename A::FoldC r = ar.fold_const(ar.from_words(rarg.w));
     typename A::Acc acc[NP];
 #pragma unroll
     for (int x = 0; x < NP; ++x) ar.acc_zero(acc[x]);
@@ -251,8 +251,8 @@ __global__ void __launch_bounds__(kThreads, (fold_min_blocks<A, K, U>()))
                     typename A::Lz prod[NP];
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        typename A::El u0 = ar.fold(ar.from_words(&w[u][k][0]), ar.from_words(&w[u][k][1]), r);
-                        typename A::El u1 = ar.fold(ar.from_words(&w[u][k][2]), ar.from_words(&w[u][k][3]), r);
+                        typename A::El u0 = ar.fold_c(ar.from_words(&w[u][k][0]), ar.from_words(&w[u][k][1]), r);
+                        typename A::El u1 = ar.fold_c(ar.from_words(&w[u][k][2]), ar.from_words(&w[u][k][3]), r);
                         uint64_t o[2];
                         ar.to_words(u0, &o[0]);
                         ar.to_words(u1, &o[1]);
@@ -270,8 +270,8 @@ __global__ void __launch_bounds__(kThreads, (fold_min_blocks<A, K, U>()))
             for (int k = 0; k < K; ++k) {
                 uint64_t w[4 * N];
                 ld_words<4 * N>(in.p[k] + i * 4 * N, w);
-                typename A::El u0 = ar.fold(ar.from_words(w), ar.from_words(w + N), r);
-                typename A::El u1 = ar.fold(ar.from_words(w + 2 * N), ar.from_words(w + 3 * N), r);
+                typename A::El u0 = ar.fold_c(ar.from_words(w), ar.from_words(w + N), r);
+                typename A::El u1 = ar.fold_c(ar.from_words(w + 2 * N), ar.from_words(w + 3 * N), r);
                 uint64_t o[2 * N];
                 ar.to_words(u0, o);
                 ar.to_words(u1, o + N);
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, (fold_min_blocks<A, K, U>()))
             for (int x = 0; x < NP; ++x) ar.acc_add(acc[x], prod[x]);
         }
     }
-    grid_reduce_finish<A, NP>(ar, acc, partials, ticket, out);
+    grid_reduce_finish<A, NP>(ar, acc, partials, ticket, out, K);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -294,14 +294,14 @@ __global__ void __launch_bounds__(kThreads) k_fold(FieldDesc f, const uint64_t* 
                                                    ElemArg rarg, uint64_t n_groups) {
     constexpr int N = A::N;
     const A ar(f);
-    const typename A::El r = ar.from_words(rarg.w);
+    const typename A::FoldC r = ar.fold_const(ar.from_words(rarg.w));
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_groups; i += stride) {
         uint64_t w[2 * VEC * N], o[VEC * N];
         ld_words<2 * VEC * N>(in + i * 2 * VEC * N, w);
 #pragma unroll
         for (int e = 0; e < VEC; ++e)
-            ar.to_words(ar.fold(ar.from_words(w + (2 * e) * N), ar.from_words(w + (2 * e + 1) * N), r), o + e * N);
+            ar.to_words(ar.fold_c(ar.from_words(w + (2 * e) * N), ar.from_words(w + (2 * e + 1) * N), r), o + e * N);
         st_words<VEC * N>(outp + i * VEC * N, o);
     }
 }

@@ -14,14 +14,14 @@ namespace scb {
 
 // QP adjacent quads per thread-iteration (IN32: QP = 2 makes the load 256-bit and the store 128-bit).
 template <int K, bool IN32, bool OUT32, int QP>
-__global__ void __launch_bounds__(kThreads, (K <= 3 ? 8 : 6))
+__global__ void __launch_bounds__(kThreads, (QP >= 4 ? 4 : (K <= 3 ? 8 : 6)))
     k_fold_round_sp(FieldDesc f, TabsIn<K> in, TabsOut<K> outp, ElemArg rarg, uint64_t n_groups, uint64_t* partials,
                     unsigned int* ticket, uint64_t* out) {
     using A = PolSP;
     constexpr int NP = K + 1;
     static_assert(IN32 || QP == 1, "QP > 1 only for packed input");
     const A ar(f);
-    const uint32_t r = ar.from_words(rarg.w);
+    const A::FoldC r = ar.fold_const(ar.from_words(rarg.w));
     A::Acc acc[NP];
 #pragma unroll
     for (int x = 0; x < NP; ++x) ar.acc_zero(acc[x]);
@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(kThreads, (K <= 3 ? 8 : 6))
             A::Lz prod[NP];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                u[k][2 * q] = ar.fold(t[k][4 * q], t[k][4 * q + 1], r);
-                u[k][2 * q + 1] = ar.fold(t[k][4 * q + 2], t[k][4 * q + 3], r);
+                u[k][2 * q] = ar.fold_c(t[k][4 * q], t[k][4 * q + 1], r);
+                u[k][2 * q + 1] = ar.fold_c(t[k][4 * q + 2], t[k][4 * q + 3], r);
                 pair_into_prod<A, NP>(ar, k == 0, u[k][2 * q], u[k][2 * q + 1], prod);
             }
 #pragma unroll
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kThreads, (K <= 3 ? 8 : 6))
             }
         }
     }
-    grid_reduce_finish<A, NP>(ar, acc, partials, ticket, out);
+    grid_reduce_finish<A, NP>(ar, acc, partials, ticket, out, K);
 }
 
 // packed uint32 table -> ark's 8-byte elements (only when a caller asks for an intermediate table)

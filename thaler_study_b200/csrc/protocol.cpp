@@ -312,7 +312,9 @@ struct TailCtx {
     uint64_t* offsets;
     uint32_t j;   // protocol round of the tail's round 0
     uint32_t np;  // sums per round
+    std::vector<uint64_t> used;  // challenges consumed by the tail's folds, in order (n limbs each)
 };
+static bool g_tail_disabled = false;
 // one tail round on the host: sums -> message polynomial -> bytes -> hash chain -> next challenge
 static int tail_round_cb(void* user, uint32_t t, const uint64_t* evals, uint64_t* next_r) {
     TailCtx* tc = (TailCtx*)user;
@@ -324,6 +326,7 @@ static int tail_round_cb(void* user, uint32_t t, const uint64_t* evals, uint64_t
     tc->chain->absorb(tc->hash_input->data() + before, tc->hash_input->size() - before);
     tc->offsets[tc->j + t + 1] = tc->hash_input->size();
     F.store(tc->chain->challenge(), next_r);
+    tc->used.insert(tc->used.end(), next_r, next_r + F.n);
     return SCB_OK;
 }
 
@@ -344,22 +347,38 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
     offsets[1] = hash_input.size();
     const bool product = p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G;
     const uint32_t tail_vars = tail_max_vars();
-    for (uint32_t j = 1; j < p->num_vars; ++j) {
+    uint32_t j = 1;
+    while (j < p->num_vars) {
         Fe r_j = chain.challenge();  // == hash_to_field(hash_input)
         const uint32_t live = p->num_vars - (j - 1);  // variables of the table about to be folded
-        if (product && tail_vars >= 2 && live <= tail_vars && live >= 2) {
+        if (product && !g_tail_disabled && tail_vars >= 2 && live <= tail_vars && live >= 2) {
             // latency-bound tail: all remaining rounds in one resident kernel, challenges through a mailbox
-            TailCtx tc{&F, p->kind, &hash_input, &chain, offsets, j, p->np};
+            TailCtx tc{&F, p->kind, &hash_input, &chain, offsets, j, p->np, {}};
             uint64_t rw[kHostMaxLimbs];
             F.store(r_j, rw);
-            RC_TRY(scb_poly_tail_rounds(p->g, rw, p->np, tail_round_cb, &tc));
-            break;
+            tc.used.insert(tc.used.end(), rw, rw + F.n);
+            uint32_t done = 0;
+            int rc = scb_poly_tail_rounds(p->g, rw, p->np, tail_round_cb, &tc, &done);
+            if (rc == SCB_OK) break;
+            if (rc != SCB_ETAIL) return rc;
+            // lock-step lost (e.g. a profiler serialises kernel and host): keep what was done, fold the tables by the
+            // challenges already consumed and carry on with one launch per round
+            g_tail_disabled = true;
+            if (done > 0) {
+                scb_poly* folded = nullptr;
+                RC_TRY(scb_poly_fix_variables(p->g, tc.used.data(), done, &folded));
+                scb_poly_free(p->g);
+                p->g = folded;
+                j += done;
+            }
+            continue;
         }
         RC_TRY(prover_round(p, &r_j, j, &sp));
         const size_t before = hash_input.size();
         sp.serialize(F, hash_input);
         chain.absorb(hash_input.data() + before, hash_input.size() - before);
         offsets[j + 1] = hash_input.size();
+        ++j;
     }
     ARG_TRY(hash_input.size() <= cap, "transcript buffer too small");
     std::memcpy(out, hash_input.data(), hash_input.size());

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(tail_threads<A>(), 1)
                 return;
             }
         }
-        const typename A::El r = ar.from_words(r_sm);
+        const typename A::FoldC r = ar.fold_const(ar.from_words(r_sm));
         typename A::Acc acc[NP];
 #pragma unroll
         for (int x = 0; x < NP; ++x) ar.acc_zero(acc[x]);
@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(tail_threads<A>(), 1)
             for (int k = 0; k < K; ++k) {
                 typename A::El t4[4];
                 tail_ld_quad<A>(ar, src[k], i, src_w32, t4);
-                typename A::El u0 = ar.fold(t4[0], t4[1], r);
-                typename A::El u1 = ar.fold(t4[2], t4[3], r);
+                typename A::El u0 = ar.fold_c(t4[0], t4[1], r);
+                typename A::El u1 = ar.fold_c(t4[2], t4[3], r);
                 tail_st_pair<A>(ar, dst[k], i, buf_w32, u0, u1);
                 pair_into_prod<A, NP>(ar, k == 0, u0, u1, prod);
             }
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(tail_threads<A>(), 1)
 #pragma unroll
             for (int x = 0; x < NP; ++x) {
                 uint64_t w[N];
-                ar.to_words(ar.acc_final(acc[x]), w);
+                ar.to_words(ar.msg_final(acc[x], K), w);
 #pragma unroll
                 for (int i = 0; i < N; ++i) st_sys(&mb->evals[x * N + i], w[i]);
             }
