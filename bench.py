@@ -161,7 +161,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import thaler_study_b200 as T
-    from thaler_study_b200.distributed import CudaProductEngine, prove_sharded
+    from thaler_study_b200.distributed import CudaProductEngine, Peers, prove_sharded, prove_sharded_p2p
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -178,10 +178,18 @@ def run_ours(args):
     g = T.ProductMLE.new(tabs)
     T.synchronize()
 
-    def step():
+    exchange = os.environ.get("SCB_EXCHANGE", "p2p")  # p2p: in-kernel exchange over NVLink peer memory; nccl: all-gather
+    peers = Peers() if world > 1 and exchange == "p2p" else None
+
+    def prove(poly):
         if world == 1:
-            return T.generate_transcript(T.Prover(g))
-        return prove_sharded(CudaProductEngine(g.clone()))[1]
+            return T.generate_transcript(T.Prover(poly))
+        if peers is not None:
+            return prove_sharded_p2p(poly, peers)[1]
+        return prove_sharded(CudaProductEngine(poly.clone()))[1]
+
+    def step():
+        return prove(g)
 
     def barrier():
         if world > 1:
@@ -267,9 +275,7 @@ def run_ours(args):
         def e2e_step():
             hs = [T.DenseMultilinearExtension.from_evaluations_vec(F, v, h) for h in host]  # cudaMemcpy H2D
             gg = T.ProductMLE.new(hs)
-            if world == 1:
-                return T.generate_transcript(T.Prover(gg))  # messages come back device -> host every round
-            return prove_sharded(CudaProductEngine(gg))[1]
+            return prove(gg)  # messages come back device -> host every round
 
         e2e_step()
         barrier()
@@ -312,7 +318,8 @@ def run_ours(args):
             "config": {"workload": workload_name(v, n_gpus, p), "tables": K, "vars_per_gpu": v, "total_vars": v + (world.bit_length() - 1),
                        "field_modulus": p, "bytes_per_element": E, "arith_policy": {0: "small-prime 32-bit", 1: "generic 64-bit", 4: "4-limb"}[F.policy],
                        "l2": "inputs (%.1f GB per GPU) larger than L2; no flush needed" % (K * (1 << v) * E / 1e9),
-                       "parallelism": f"tables sharded by top variables over {n_gpus} GPU(s)"},
+                       "parallelism": f"tables sharded by top variables over {n_gpus} GPU(s)"
+                                      + ("" if world == 1 else f"; per-round exchange: {exchange}")},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }))
     if world > 1:

@@ -220,6 +220,26 @@ int scb_transcript_c_1(const scb_transcript* t, uint64_t* out_elem);
 int scb_transcript_bytes(const scb_transcript* t, uint8_t* out, size_t cap, size_t* out_len, uint64_t* offsets, uint32_t cap_msgs,
                          uint32_t* n_msgs);
 
+/* ------------------------------------------------------------------ multi-GPU: peer windows over NVLink
+ * One process per GPU.  Each rank owns a small window in its HBM (cudaMalloc) that every peer maps through CUDA IPC;
+ * the round kernels' finishing thread posts the rank's (d+1) partial sums into all peers' windows with P2P stores,
+ * waits for the peers' posts and adds the rows mod p, so "per-round all-gather + modular sum" is part of the round
+ * kernel (no collective launch).  At consolidation the slabs are published the same way.  The handles (64 bytes per
+ * rank) are exchanged by the caller with any transport (torch.distributed in thaler_study_b200/distributed.py). */
+typedef struct scb_peers scb_peers;
+int scb_peers_create(uint32_t rank, uint32_t world, size_t gather_bytes, scb_peers** out, uint8_t* handle_out /* 64 B */);
+int scb_peers_connect(scb_peers* p, const uint8_t* all_handles /* world * 64 B, rank order */);
+void scb_peers_free(scb_peers* p);
+/* make `p` (or none) the exchange group used by this thread's subsequent scb_poly_round_evals /
+ * scb_poly_fix_and_round_evals calls: their results are then the sums over ALL ranks' slabs */
+int scb_peers_set_current(scb_peers* p);
+/* all-gather the slabs of `slab` (rank-order concatenation of every table) into a replicated polynomial */
+int scb_peers_gather_poly(scb_peers* p, const scb_poly* slab, scb_poly** out);
+/* Prover::new for a polynomial sharded by its top log2(world) variables; `slab` is this rank's part.  The prover
+ * consolidates (scb_peers_gather_poly) once a slab has at most consolidate_at variables; scb_prover_round and
+ * scb_fs_generate_transcript then work as for a single GPU and return identical bytes on every rank. */
+int scb_prover_new_sharded(const scb_poly* slab, scb_peers* peers, uint32_t world, uint32_t consolidate_at, scb_prover** out);
+
 #ifdef __cplusplus
 }
 #endif

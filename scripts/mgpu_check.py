@@ -7,18 +7,24 @@ sys.path.insert(0, ROOT)
 import torch
 import torch.distributed as dist
 import thaler_study_b200 as T
-from thaler_study_b200.distributed import CudaProductEngine, prove_sharded
+from thaler_study_b200.distributed import CudaProductEngine, Peers, prove_sharded, prove_sharded_p2p
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 lg = world.bit_length() - 1
 ok = True
+peers = Peers()
 for p, lv, K, cat in ((1572869, 20, 3, 16), (1572869, 12, 3, 4), (389, 9, 2, 16), (0xFFFFFFFF00000001, 14, 2, 10),
                       (0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001, 12, 3, 8)):
     F = T.Field(p)
     slabs = [T.DenseMultilinearExtension.synthetic(F, lv, 900 + k, start=rank << lv) for k in range(K)]
     c_1, msgs = prove_sharded(CudaProductEngine(T.ProductMLE.new(slabs)), consolidate_at=cat)
+    for rep in range(3):  # back-to-back proofs exercise the window's slot / gather-area reuse
+        c_1b, msgs_b = prove_sharded_p2p(T.ProductMLE.new(slabs), peers, consolidate_at=cat)
+        if msgs_b != msgs or c_1b != c_1:
+            print(f"rank {rank}: P2P transcript differs from the NCCL one (p_bits={F.bits} lv={lv} rep={rep})")
+            ok = False
     if rank == 0:
         full = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, lv + lg, 900 + k) for k in range(K)])
         prover = T.Prover(full)
@@ -26,7 +32,9 @@ for p, lv, K, cat in ((1572869, 20, 3, 16), (1572869, 12, 3, 4), (389, 9, 2, 16)
         good = msgs == want and c_1 == T.Prover(full).c_1() and T.verify_transcript(msgs, T.Verifier(lv + lg, full))
         print(f"p_bits={F.bits} lv={lv} K={K} consolidate_at={cat}: {'ok' if good else 'MISMATCH'}")
         ok = ok and good
-dist.barrier()
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("MGPU_OK" if ok else "MGPU_FAIL")
+    print("MGPU_OK" if flag.item() == 1 else "MGPU_FAIL")
+peers.close()
 dist.destroy_process_group()

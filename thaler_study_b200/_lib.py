@@ -89,6 +89,12 @@ SIGNATURES = {
     "scb_verifier_round": (C.c_int, [vp, u64p, u64p, C.c_uint32, u64p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "scb_fs_generate_transcript": (C.c_int, [vp, u8p, C.c_size_t, C.POINTER(C.c_size_t), u64p]),
     "scb_fs_verify_transcript": (C.c_int, [vp, u8p, u64p, C.c_uint32, C.POINTER(C.c_int)]),
+    "scb_peers_create": (C.c_int, [C.c_uint32, C.c_uint32, C.c_size_t, vpp, u8p]),
+    "scb_peers_connect": (C.c_int, [vp, u8p]),
+    "scb_peers_free": (None, [vp]),
+    "scb_peers_set_current": (C.c_int, [vp]),
+    "scb_peers_gather_poly": (C.c_int, [vp, vp, vpp]),
+    "scb_prover_new_sharded": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vpp]),
     "scb_transcript_new": (C.c_int, [vp, C.c_uint32, vpp]),
     "scb_transcript_free": (None, [vp]),
     "scb_transcript_absorb_round": (C.c_int, [vp, u64p, C.c_uint32, C.c_uint32, u64p]),

@@ -158,6 +158,34 @@ static int tune_unroll() {
         }                                                                                   \
     } while (0)
 
+
+// ------------------------------------------------------------------------------------------ peers (multi-GPU)
+struct scb_peers {
+    uint32_t rank = 0, world = 1;
+    uint64_t* win[kMaxRanks] = {nullptr};  // win[rank] = own window (cudaMalloc), others = IPC mappings
+    size_t gather_bytes = 0;               // capacity of ONE gather buffer (all ranks' slabs of all tables)
+    uint64_t seq = 0, gseq = 0;
+    bool connected = false;
+};
+static thread_local scb_peers* g_cur_peers = nullptr;  // set around the round calls of a sharded prover
+static constexpr size_t kStatusWord = 500;              // word of Ctx::h_res used as exchange status
+
+static int peers_check(Ctx* c);
+static PeerArg peer_arg(Ctx* c) {
+    PeerArg a;
+    std::memset(&a, 0, sizeof a);
+    scb_peers* p = g_cur_peers;
+    if (p && p->world > 1) {
+        for (uint32_t g = 0; g < p->world; ++g) a.win[g] = p->win[g];
+        a.rank = p->rank;
+        a.world = p->world;
+        a.seq = ++p->seq;
+        a.status = c->h_res + kStatusWord;
+        a.timeout_ns = 10ull * 1000 * 1000 * 1000;
+    }
+    return a;
+}
+
 // policy dispatch: binds `A` to the arithmetic policy of the field
 #define DISPATCH_POLICY(pol, ...)                              \
     switch (pol) {                                             \
@@ -814,10 +842,10 @@ static int launch_round_evals(Ctx* c, const scb_poly* p, uint64_t* res) {
             if (A::N == 1 && n_pairs >= 2) {
                 constexpr int PV = A::N == 1 ? 2 : 1;
                 auto kern = k_round_evals<A, K, PV>;
-                kern<<<occ_grid(c, kern, n_pairs / PV, 0, A::kLight ? 16 : 0), kThreads, 0, g_stream>>>(f.d, in, n_pairs / PV, c->partials, c->ticket, res);
+                kern<<<occ_grid(c, kern, n_pairs / PV, 0, A::kLight ? 16 : 0), kThreads, 0, g_stream>>>(f.d, in, n_pairs / PV, c->partials, c->ticket, res, peer_arg(c));
             } else {
                 auto kern = k_round_evals<A, K, 1>;
-                kern<<<occ_grid(c, kern, n_pairs), kThreads, 0, g_stream>>>(f.d, in, n_pairs, c->partials, c->ticket, res);
+                kern<<<occ_grid(c, kern, n_pairs), kThreads, 0, g_stream>>>(f.d, in, n_pairs, c->partials, c->ticket, res, peer_arg(c));
             }
         }));
     } else if (p->kind == SCB_POLY_TRIANGLE_G) {
@@ -854,6 +882,7 @@ static int round_evals_impl(const scb_poly* p, uint32_t n_points, uint64_t* h_ou
     }
     RC_TRY(launch_round_evals(c, p, c->h_res));
     CU_TRY(cudaStreamSynchronize(g_stream));
+    RC_TRY(peers_check(c));
     std::memcpy(h_out, c->h_res, (size_t)8 * N * n_points);
     return SCB_OK;
 }
@@ -870,7 +899,7 @@ static void launch_fold_sp(Ctx* c, const FieldDesc& d, TabsIn<K> in, TabsOut<K> 
     auto kern = k_fold_round_sp<K, IN32, OUT32, QP>;
     static const int bps32 = getenv("SCB_BPS32") ? atoi(getenv("SCB_BPS32")) : 8;
     const int pref = IN32 ? bps32 : 5;  // measured sweet spots (profiles/r01_kernel_sweep.md)
-    kern<<<occ_grid(c, kern, n_quads / QP, 0, pref), kThreads, 0, g_stream>>>(d, in, o, ra, n_quads / QP, c->partials, c->ticket, res);
+    kern<<<occ_grid(c, kern, n_quads / QP, 0, pref), kThreads, 0, g_stream>>>(d, in, o, ra, n_quads / QP, c->partials, c->ticket, res, peer_arg(c));
 }
 
 // Polynomials with packed tables only exist as descendants of a handle marked with scb_poly_allow_packed; every
@@ -964,10 +993,10 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
             if (A::N == 1 && tune_unroll() == 2) {
                 constexpr int U = A::N == 1 ? 2 : 1;
                 auto kern = k_fold_round<A, K, U>;
-                kern<<<occ_grid(c, kern, (n_quads + U - 1) / U), kThreads, 0, g_stream>>>(f.d, in, o, ra, n_quads, c->partials, c->ticket, res);
+                kern<<<occ_grid(c, kern, (n_quads + U - 1) / U), kThreads, 0, g_stream>>>(f.d, in, o, ra, n_quads, c->partials, c->ticket, res, peer_arg(c));
             } else {
                 auto kern = k_fold_round<A, K, 1>;
-                kern<<<occ_grid(c, kern, n_quads, 0, A::kLight ? 5 : 0), kThreads, 0, g_stream>>>(f.d, in, o, ra, n_quads, c->partials, c->ticket, res);
+                kern<<<occ_grid(c, kern, n_quads, 0, A::kLight ? 5 : 0), kThreads, 0, g_stream>>>(f.d, in, o, ra, n_quads, c->partials, c->ticket, res, peer_arg(c));
             }
         }));
         LAUNCH_CHECK();
@@ -981,6 +1010,7 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
         if (res != d_out) CU_TRY(cudaMemcpyAsync(d_out, res, (size_t)8 * N * n_points, cudaMemcpyDeviceToDevice, g_stream));
     } else {
         CU_TRY(cudaStreamSynchronize(g_stream));
+        RC_TRY(peers_check(c));
         std::memcpy(h_out, c->h_res, (size_t)8 * N * n_points);
     }
     *out = q.release();
@@ -1148,6 +1178,142 @@ extern "C" int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, 
         rc = SCB_ECUDA;
     }
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------ peers API
+__global__ void __launch_bounds__(kThreads) k_peer_publish(PeerArg pa, const uint4* __restrict__ src, uint64_t n16, uint64_t dst_byte_off) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = src[i];
+        for (uint32_t g = 0; g < pa.world; ++g) reinterpret_cast<uint4*>(reinterpret_cast<char*>(pa.win[g]) + dst_byte_off)[i] = v;
+    }
+}
+__global__ void k_peer_gather_sync(PeerArg pa) {  // one thread: publish "my slabs are written", wait for everyone's
+    __threadfence_system();
+    for (uint32_t g = 0; g < pa.world; ++g) st_sys(pa.win[g] + kWinGatherFlags + pa.rank, pa.seq);
+    const uint64_t t0 = globaltimer_ns();
+    for (uint32_t g = 0; g < pa.world; ++g) {
+        while (ld_sys(pa.win[pa.rank] + kWinGatherFlags + g) < pa.seq) {
+            if (globaltimer_ns() - t0 > pa.timeout_ns) {
+                st_sys(pa.status, 1);
+                return;
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+extern "C" int scb_peers_create(uint32_t rank, uint32_t world, size_t gather_bytes, scb_peers** out, uint8_t* handle_out) {
+    ARG_TRY(out && handle_out, "null argument");
+    ARG_TRY(world >= 1 && world <= (uint32_t)kMaxRanks && (world & (world - 1)) == 0 && rank < world, "world must be a power of two <= 8");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    auto p = std::make_unique<scb_peers>();
+    p->rank = rank;
+    p->world = world;
+    p->gather_bytes = (gather_bytes + 255) & ~(size_t)255;
+    const size_t bytes = 4096 + 2 * p->gather_bytes;
+    void* w = nullptr;
+    CU_TRY(cudaMalloc(&w, bytes));  // plain cudaMalloc: pool (cudaMallocAsync) memory cannot be exported through IPC
+    CU_TRY(cudaMemset(w, 0, bytes));
+    CU_TRY(cudaDeviceSynchronize());
+    p->win[rank] = (uint64_t*)w;
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, w));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memcpy(handle_out, &h, 64);
+    *out = p.release();
+    return SCB_OK;
+}
+extern "C" int scb_peers_connect(scb_peers* p, const uint8_t* all_handles) {
+    ARG_TRY(p && all_handles, "null argument");
+    for (uint32_t g = 0; g < p->world; ++g) {
+        if (g == p->rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, all_handles + (size_t)g * 64, 64);
+        void* w = nullptr;
+        CU_TRY(cudaIpcOpenMemHandle(&w, h, cudaIpcMemLazyEnablePeerAccess));
+        p->win[g] = (uint64_t*)w;
+    }
+    p->connected = true;
+    return SCB_OK;
+}
+extern "C" void scb_peers_free(scb_peers* p) {
+    if (!p) return;
+    if (g_cur_peers == p) g_cur_peers = nullptr;
+    for (uint32_t g = 0; g < p->world; ++g) {
+        if (!p->win[g]) continue;
+        if (g == p->rank) cudaFree(p->win[g]);
+        else cudaIpcCloseMemHandle(p->win[g]);
+    }
+    delete p;
+}
+extern "C" int scb_peers_set_current(scb_peers* p) {
+    ARG_TRY(!p || p->connected || p->world == 1, "scb_peers_connect has not been called");
+    g_cur_peers = p;
+    if (p) {
+        Ctx* c;
+        RC_TRY(get_ctx(&c));
+        c->h_res[kStatusWord] = 0;
+    }
+    return SCB_OK;
+}
+static int peers_check(Ctx* c) {
+    if (g_cur_peers && c->h_res[kStatusWord] != 0) {
+        set_error("peer exchange timed out (a rank is missing or stuck)");
+        return SCB_ENCCL;
+    }
+    return SCB_OK;
+}
+// Consolidation: every rank writes its slabs into every peer's gather area (NVLink P2P stores); afterwards each
+// rank holds the rank-order concatenation of all slabs and continues replicated, with no further communication.
+extern "C" int scb_peers_gather_poly(scb_peers* p, const scb_poly* slab, scb_poly** out) {
+    ARG_TRY(p && slab && out, "null argument");
+    ARG_TRY(slab->kind == SCB_POLY_PRODUCT || slab->kind == SCB_POLY_MATMUL_G, "only product polynomials shard");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    const FieldImpl& f = *slab->f;
+    const uint32_t lg = 31 - __builtin_clz(p->world);
+    const size_t K = slab->t.size();
+    const bool p32 = slab->t[0].p32;
+    const size_t table_bytes = (size_t)(p32 ? 4 : 8 * f.d.n) << slab->t[0].nv;
+    const size_t region = (p->world * table_bytes + 255) & ~(size_t)255;
+    ARG_TRY(K * region <= p->gather_bytes, "peer window too small for this consolidation (scb_peers_create gather_bytes)");
+    PeerArg pa;
+    std::memset(&pa, 0, sizeof pa);
+    for (uint32_t g = 0; g < p->world; ++g) pa.win[g] = p->win[g];
+    pa.rank = p->rank;
+    pa.world = p->world;
+    pa.seq = ++p->gseq;
+    pa.status = c->h_res + kStatusWord;
+    pa.timeout_ns = 10ull * 1000 * 1000 * 1000;
+    const size_t area = 4096 + (pa.seq & 1) * p->gather_bytes;
+    auto q = std::make_unique<scb_poly>(*slab);
+    for (size_t k = 0; k < K; ++k) {
+        ARG_TRY(slab->t[k].p32 == p32 && slab->t[k].nv == slab->t[0].nv, "tables of one polynomial must share a layout");
+        const size_t off = area + k * region + p->rank * table_bytes;
+        if (table_bytes % 16 == 0) {
+            k_peer_publish<<<grid_for(c, table_bytes / 16), kThreads, 0, g_stream>>>(pa, (const uint4*)slab->t[k].buf->ptr, table_bytes / 16, off);
+            LAUNCH_CHECK();
+        } else {  // tiny slabs: plain copies
+            for (uint32_t g = 0; g < p->world; ++g)
+                CU_TRY(cudaMemcpyAsync((char*)p->win[g] + off, slab->t[k].buf->ptr, table_bytes, cudaMemcpyDefault, g_stream));
+        }
+        q->t[k].nv = slab->t[k].nv + lg;
+        q->t[k].buf = std::make_shared<DevBuf>();
+        q->t[k].buf->ptr = (uint64_t*)((char*)p->win[p->rank] + area + k * region);
+        q->t[k].buf->bytes = p->world * table_bytes;
+        q->t[k].buf->owned = false;
+    }
+    k_peer_gather_sync<<<1, 1, 0, g_stream>>>(pa);
+    LAUNCH_CHECK();
+    CU_TRY(cudaStreamSynchronize(g_stream));
+    if (c->h_res[kStatusWord] != 0) {
+        set_error("peer gather timed out (a rank is missing or stuck)");
+        return SCB_ENCCL;
+    }
+    *out = q.release();
+    return SCB_OK;
 }
 
 // accessor used by protocol.cpp

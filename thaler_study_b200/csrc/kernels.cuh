@@ -28,6 +28,86 @@ struct ElemArg {  // one field element passed by value
     uint64_t w[kMaxLimbs];
 };
 
+__device__ __forceinline__ uint64_t ld_sys(const volatile uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys(volatile uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Peer exchange window (multi-GPU).  Every rank owns one window in its own HBM, mapped into every
+// peer through CUDA IPC; NVLink P2P stores write straight into it.  Word layout (uint64_t):
+//   [0, 320)    sums  [slot 2][rank 8][kMaxPts * kMaxLimbs]   partial round sums posted BY rank g
+//   [320, 336)  flags [slot 2][rank 8]                         sequence number of the post
+//   [336, 344)  gather flags [rank 8]
+//   [512, ...)  gather area (table slabs at consolidation)
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 8;
+constexpr int kWinSumStride = kMaxPts * kMaxLimbs;          // 20 words per (slot, rank)
+constexpr int kWinFlags = 2 * kMaxRanks * kWinSumStride;    // 320
+constexpr int kWinGatherFlags = kWinFlags + 2 * kMaxRanks;  // 336
+constexpr int kWinGatherWords = 512;                        // gather area starts at byte 4096
+struct PeerArg {
+    uint64_t* win[kMaxRanks];  // win[g] = rank g's window as mapped in THIS process
+    uint32_t rank;
+    uint32_t world;            // <= 1: no exchange
+    uint64_t seq;              // exchange number (monotone, identical on all ranks)
+    uint64_t* status;          // mapped host word: set to 1 on timeout
+    uint64_t timeout_ns;
+};
+
+// Posts this rank's NP final sums into every peer's window, waits for all peers' posts of the same exchange,
+// and adds the rows mod p: the per-round "all-gather + modular sum" of the sharded prover, done by the finishing
+// thread of the round kernel itself over NVLink peer memory (no separate collective launch).
+template <class A, int NP>
+__device__ __forceinline__ void peer_exchange_sum(const A& ar, const PeerArg& peer, uint64_t (&w)[NP][A::N]) {
+    constexpr int N = A::N;
+    const int slot = (int)(peer.seq & 1);
+    for (uint32_t g = 0; g < peer.world; ++g) {
+        uint64_t* dst = peer.win[g] + (slot * kMaxRanks + peer.rank) * kWinSumStride;
+#pragma unroll
+        for (int x = 0; x < NP; ++x)
+#pragma unroll
+            for (int i = 0; i < N; ++i) st_sys(dst + x * N + i, w[x][i]);
+    }
+    __threadfence_system();
+    for (uint32_t g = 0; g < peer.world; ++g) st_sys(peer.win[g] + kWinFlags + slot * kMaxRanks + peer.rank, peer.seq);
+    uint64_t* me = peer.win[peer.rank];
+    const uint64_t t0 = globaltimer_ns();
+    for (uint32_t g = 0; g < peer.world; ++g) {
+        while (ld_sys(me + kWinFlags + slot * kMaxRanks + g) != peer.seq) {
+            if (globaltimer_ns() - t0 > peer.timeout_ns) {
+                st_sys(peer.status, 1);
+                return;
+            }
+        }
+    }
+    __threadfence_system();
+    for (uint32_t g = 0; g < peer.world; ++g) {
+        if (g == peer.rank) continue;
+        const uint64_t* src = me + (slot * kMaxRanks + g) * kWinSumStride;
+#pragma unroll
+        for (int x = 0; x < NP; ++x) {
+            uint64_t o[N], a[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                o[i] = ld_sys(src + x * N + i);
+                a[i] = w[x][i];
+            }
+            ar.to_words(ar.add(ar.from_words(a), ar.from_words(o)), w[x]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // block-wide reduction of NP accumulators; result valid in thread 0
 // ------------------------------------------------------------------------------------------
@@ -92,7 +172,8 @@ __device__ __forceinline__ void block_reduce(const A& ar, typename A::Acc (&acc)
 // commutative, so the result is bit-identical for any grid size or arrival order.
 template <class A, int NP>
 __device__ __forceinline__ void grid_reduce_finish(const A& ar, typename A::Acc (&acc)[NP], uint64_t* partials,
-                                                   unsigned int* ticket, uint64_t* out, int msg_k = 0) {
+                                                   unsigned int* ticket, uint64_t* out, int msg_k = 0,
+                                                   const PeerArg* peer = nullptr) {
     constexpr int AW = A::AW;
     __shared__ uint64_t sm[32 * NP * AW];
     __shared__ bool is_last;
@@ -127,13 +208,14 @@ __device__ __forceinline__ void grid_reduce_finish(const A& ar, typename A::Acc 
     }
     block_reduce<A, NP>(ar, acc, sm);
     if (threadIdx.x == 0) {
+        uint64_t w[NP][A::N];
 #pragma unroll
-        for (int x = 0; x < NP; ++x) {
-            uint64_t w[A::N];
-            ar.to_words(ar.msg_final(acc[x], msg_k), w);
+        for (int x = 0; x < NP; ++x) ar.to_words(ar.msg_final(acc[x], msg_k), w[x]);
+        if (peer != nullptr && peer->world > 1) peer_exchange_sum<A, NP>(ar, *peer, w);
 #pragma unroll
-            for (int i = 0; i < A::N; ++i) out[x * A::N + i] = w[i];
-        }
+        for (int x = 0; x < NP; ++x)
+#pragma unroll
+            for (int i = 0; i < A::N; ++i) out[x * A::N + i] = w[x][i];
         *ticket = 0;  // re-arm for the next launch on this stream
         __threadfence_system();
     }
@@ -176,7 +258,8 @@ constexpr int fold_min_blocks() {
 
 template <class A, int K, int PV>
 __global__ void __launch_bounds__(kThreads, (round_min_blocks<A, K, PV>())) k_round_evals(FieldDesc f, TabsIn<K> in, uint64_t n_groups,
-                                                                            uint64_t* partials, unsigned int* ticket, uint64_t* out) {
+                                                                            uint64_t* partials, unsigned int* ticket, uint64_t* out,
+                                                                            PeerArg peer) {
     constexpr int NP = K + 1, N = A::N;
     const A ar(f);
     typename A::Acc acc[NP];
@@ -209,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, (round_min_blocks<A, K, PV>())) k_ro
             for (int x = 0; x < NP; ++x) ar.acc_add(acc[x], prod[x]);
         }
     }
-    grid_reduce_finish<A, NP>(ar, acc, partials, ticket, out, K);
+    grid_reduce_finish<A, NP>(ar, acc, partials, ticket, out, K, &peer);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -224,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, (round_min_blocks<A, K, PV>())) k_ro
 template <class A, int K, int U>
 __global__ void __launch_bounds__(kThreads, (fold_min_blocks<A, K, U>()))
     k_fold_round(FieldDesc f, TabsIn<K> in, TabsOut<K> outp, ElemArg rarg, uint64_t n_quads, uint64_t* partials, unsigned int* ticket,
-                 uint64_t* out) {
+                 uint64_t* out, PeerArg peer) {
     constexpr int NP = K + 1, N = A::N;
     static_assert(N == 1 || U == 1, "unrolling is only implemented for one-limb fields");
     const A ar(f);
@@ -282,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, (fold_min_blocks<A, K, U>()))
             for (int x = 0; x < NP; ++x) ar.acc_add(acc[x], prod[x]);
         }
     }
-    grid_reduce_finish<A, NP>(ar, acc, partials, ticket, out, K);
+    grid_reduce_finish<A, NP>(ar, acc, partials, ticket, out, K, &peer);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -16,7 +16,7 @@ namespace scb {
 template <int K, bool IN32, bool OUT32, int QP>
 __global__ void __launch_bounds__(kThreads, (QP >= 4 ? 4 : (K <= 3 ? 8 : 6)))
     k_fold_round_sp(FieldDesc f, TabsIn<K> in, TabsOut<K> outp, ElemArg rarg, uint64_t n_groups, uint64_t* partials,
-                    unsigned int* ticket, uint64_t* out) {
+                    unsigned int* ticket, uint64_t* out, PeerArg peer) {
     using A = PolSP;
     constexpr int NP = K + 1;
     static_assert(IN32 || QP == 1, "QP > 1 only for packed input");
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kThreads, (QP >= 4 ? 4 : (K <= 3 ? 8 : 6)))
             }
         }
     }
-    grid_reduce_finish<A, NP>(ar, acc, partials, ticket, out, K);
+    grid_reduce_finish<A, NP>(ar, acc, partials, ticket, out, K, &peer);
 }
 
 // packed uint32 table -> ark's 8-byte elements (only when a caller asks for an intermediate table)

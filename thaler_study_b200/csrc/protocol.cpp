@@ -144,10 +144,37 @@ struct scb_prover {
     uint32_t kind = 0, np = 0;
     bool have_round0 = false;   // round-0 sums computed by Prover::new (they also yield c_1)
     std::vector<Fe> round0;
+    // sharded prover (multi-GPU): g is this rank's slab while `sharded`; afterwards the consolidated table
+    scb_peers* peers = nullptr;
+    uint32_t consolidate_at = 0;
+    bool sharded = false;
     ~scb_prover() { scb_poly_free(g); }
 };
 
-extern "C" int scb_prover_new(const scb_poly* g, scb_prover** out) {
+struct PeersScope {  // makes `peers` the current exchange group of this thread for the lifetime of the scope
+    explicit PeersScope(scb_peers* p) : active(p != nullptr) {
+        if (active) scb_peers_set_current(p);
+    }
+    ~PeersScope() {
+        if (active) scb_peers_set_current(nullptr);
+    }
+    bool active;
+};
+// slabs small enough: all-gather them once (P2P stores into every peer's window) and continue replicated
+static int maybe_consolidate(scb_prover* p) {
+    if (!p->sharded) return SCB_OK;
+    uint32_t lv = 0;
+    RC_TRY(scb_poly_num_vars(p->g, &lv));
+    if (lv > p->consolidate_at) return SCB_OK;
+    scb_poly* full = nullptr;
+    RC_TRY(scb_peers_gather_poly(p->peers, p->g, &full));
+    scb_poly_free(p->g);
+    p->g = full;
+    p->sharded = false;
+    return SCB_OK;
+}
+
+static int prover_new_impl(const scb_poly* g, scb_peers* peers, uint32_t world, uint32_t consolidate_at, scb_prover** out) {
     // Prover::new :88-97 -- c_1 = g.to_evaluations().into_iter().sum(), computed on the device
     ARG_TRY(g && out, "null argument");
     auto p = std::make_unique<scb_prover>();
@@ -157,12 +184,25 @@ extern "C" int scb_prover_new(const scb_poly* g, scb_prover** out) {
     RC_TRY(scb_poly_kind_of(g, &p->kind));
     RC_TRY(scb_poly_n_points(g, &p->np));
     RC_TRY(scb_poly_num_vars(g, &p->num_vars));
+    if (peers && world > 1) {
+        ARG_TRY(p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G, "only product polynomials shard");
+        uint32_t lg = 0;
+        while ((1u << lg) < world) ++lg;
+        p->num_vars += lg;  // the top log2(world) variables are the rank index
+        p->peers = peers;
+        p->consolidate_at = consolidate_at < 1 ? 1 : consolidate_at;
+        p->sharded = true;
+        RC_TRY(maybe_consolidate(p.get()));
+    }
     const HostField& F = p->fi->h;
     if (p->num_vars >= 1) {
         // sum over the hypercube = g_1(0) + g_1(1): the round-0 message pass also yields c_1, so the
         // tables are streamed once here and not again by round(_, 0)  (same field elements either way)
         uint64_t w[8 * kHostMaxLimbs];
-        RC_TRY(scb_poly_round_evals(g, p->np, w));
+        {
+            PeersScope scope(p->sharded ? p->peers : nullptr);
+            RC_TRY(scb_poly_round_evals(p->g, p->np, w));
+        }
         p->round0.resize(p->np);
         for (uint32_t i = 0; i < p->np; ++i) F.load(w + (size_t)i * F.n, p->round0[i]);
         p->have_round0 = true;
@@ -175,6 +215,11 @@ extern "C" int scb_prover_new(const scb_poly* g, scb_prover** out) {
     p->r.reserve(p->num_vars);
     *out = p.release();
     return SCB_OK;
+}
+extern "C" int scb_prover_new(const scb_poly* g, scb_prover** out) { return prover_new_impl(g, nullptr, 1, 0, out); }
+extern "C" int scb_prover_new_sharded(const scb_poly* slab, scb_peers* peers, uint32_t world, uint32_t consolidate_at, scb_prover** out) {
+    ARG_TRY(peers || world <= 1, "null peers");
+    return prover_new_impl(slab, peers, world, consolidate_at, out);
 }
 extern "C" void scb_prover_free(scb_prover* p) { delete p; }
 extern "C" int scb_prover_c_1(const scb_prover* p, uint64_t* out_elem) {
@@ -196,7 +241,9 @@ static int prover_round(scb_prover* p, const Fe* r_prev, uint32_t j, SparsePoly*
         uint64_t rw[kHostMaxLimbs];
         F.store(*r_prev, rw);
         p->r.push_back(*r_prev);
+        RC_TRY(maybe_consolidate(p));
         scb_poly* next = nullptr;
+        PeersScope scope(p->sharded ? p->peers : nullptr);  // per-round exchange inside the kernel while sharded
         RC_TRY(scb_poly_fix_and_round_evals(p->g, rw, p->np, &next, w));
         scb_poly_free(p->g);
         p->g = next;
@@ -350,8 +397,10 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
     uint32_t j = 1;
     while (j < p->num_vars) {
         Fe r_j = chain.challenge();  // == hash_to_field(hash_input)
-        const uint32_t live = p->num_vars - (j - 1);  // variables of the table about to be folded
-        if (product && !g_tail_disabled && tail_vars >= 2 && live <= tail_vars && live >= 2) {
+        RC_TRY(maybe_consolidate(p));
+        uint32_t live = 0;  // variables of the table about to be folded
+        RC_TRY(scb_poly_num_vars(p->g, &live));
+        if (product && !p->sharded && !g_tail_disabled && tail_vars >= 2 && live <= tail_vars && live >= 2) {
             // latency-bound tail: all remaining rounds in one resident kernel, challenges through a mailbox
             TailCtx tc{&F, p->kind, &hash_input, &chain, offsets, j, p->np, {}};
             uint64_t rw[kHostMaxLimbs];

@@ -40,20 +40,6 @@ __device__ __forceinline__ void ld_words_cg(const uint64_t* ptr, uint64_t* w) {
         for (int i = 0; i < W; ++i) asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(w[i]) : "l"(ptr + i) : "memory");
     }
 }
-__device__ __forceinline__ uint64_t ld_sys(const volatile uint64_t* p) {
-    uint64_t v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_sys(volatile uint64_t* p, uint64_t v) {
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-    uint64_t t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
 // one quad (4 adjacent entries) of a table that is either in ark's 8-byte format or packed uint32 (PolSP only)
 template <class A>
 __device__ __forceinline__ void tail_ld_quad(const A& ar, const uint64_t* base, uint64_t i, bool w32, typename A::El (&t)[4]) {

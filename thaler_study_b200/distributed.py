@@ -151,3 +151,48 @@ def prove_sharded(engine: LocalEngine, group=None, consolidate_at: int = 16) -> 
         engine.fix_and_round_evals(r, mine)
         r = exchange_and_absorb()
     return transcript.c_1(), transcript.messages()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# NVLink peer-memory exchange (the default on GPUs): the per-round all-gather + modular sum happens INSIDE the round
+# kernel -- its finishing thread posts the rank's partial sums into every peer's window with P2P stores, waits for the
+# peers' posts and adds the rows -- and the whole round loop (hash chain, consolidation, resident tail kernel) runs in
+# the C++ host layer.  torch.distributed is only used to hand the 64-byte IPC handles around at set-up.
+# ---------------------------------------------------------------------------------------------------------------------
+class Peers:
+    """scb_peers: this rank's exchange window + IPC mappings of every peer's window."""
+
+    def __init__(self, group=None, gather_bytes: int = 32 << 20):
+        import torch
+        import torch.distributed as dist
+
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._h = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        check(lib.scb_peers_create(self.rank, self.world, gather_bytes, C.byref(self._h), handle))
+        if self.world > 1:
+            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device="cuda")
+            allh = torch.empty(self.world * 64, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            buf = (C.c_uint8 * (self.world * 64)).from_buffer_copy(bytes(allh.cpu().tolist()))
+            check(lib.scb_peers_connect(self._h, buf))
+            dist.barrier(group)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.scb_peers_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def prove_sharded_p2p(slab_poly: api.SumCheckPolynomial, peers: Peers, consolidate_at: int = 16) -> Tuple[int, List[bytes]]:
+    """Same contract as prove_sharded, with the exchange fused into the round kernels over NVLink peer memory."""
+    prover = api.Prover.__new__(api.Prover)
+    prover.F = slab_poly.F
+    prover._h = C.c_void_p()
+    check(lib.scb_prover_new_sharded(slab_poly._h, peers._h, peers.world, consolidate_at, C.byref(prover._h)))
+    c_1 = prover.c_1()
+    return c_1, api.generate_transcript(prover)
