@@ -15,6 +15,7 @@
 #include <cstdint>
 
 #include "fielddesc.hpp"
+#include "mont32.cuh"
 
 namespace scb {
 
@@ -179,9 +180,31 @@ struct PolGN {
     uint64_t p[NL];
     uint64_t inv;
 
+    Mont8x32 m32;  // 8 x 32-bit carry-chain arithmetic (used when NL == 4)
     __device__ __forceinline__ explicit PolGN(const FieldDesc& f) : inv(f.inv) {
 #pragma unroll
         for (int i = 0; i < NL; ++i) p[i] = f.p[i];
+        if constexpr (NL == 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                m32.p[2 * i] = (uint32_t)f.p[i];
+                m32.p[2 * i + 1] = (uint32_t)(f.p[i] >> 32);
+            }
+            m32.n0 = (uint32_t)f.inv;
+        }
+    }
+    __device__ __forceinline__ static void split8(const El& a, uint32_t (&w)[8]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            w[2 * i] = (uint32_t)a.l[i];
+            w[2 * i + 1] = (uint32_t)(a.l[i] >> 32);
+        }
+    }
+    __device__ __forceinline__ static El join8(const uint32_t (&w)[8]) {
+        El e;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e.l[i] = (uint64_t)w[2 * i] | ((uint64_t)w[2 * i + 1] << 32);
+        return e;
     }
 
     __device__ __forceinline__ El from_words(const uint64_t* w) const {
@@ -223,6 +246,13 @@ struct PolGN {
         }
     }
     __device__ __forceinline__ El add(const El& a, const El& b) const {
+        if constexpr (NL == 4) {
+            uint32_t x[8], y[8], r[8];
+            split8(a, x);
+            split8(b, y);
+            m32.add(r, x, y);
+            return join8(r);
+        }
         El s;
         uint64_t c = 0;
 #pragma unroll
@@ -238,6 +268,13 @@ struct PolGN {
         return s;
     }
     __device__ __forceinline__ El sub(const El& a, const El& b) const {
+        if constexpr (NL == 4) {
+            uint32_t x[8], y[8], r[8];
+            split8(a, x);
+            split8(b, y);
+            m32.sub(r, x, y);
+            return join8(r);
+        }
         El d;
         uint64_t borrow = 0;
 #pragma unroll
@@ -264,6 +301,13 @@ struct PolGN {
         return d;
     }
     __device__ __forceinline__ El mul(const El& a, const El& b) const {
+        if constexpr (NL == 4) {
+            uint32_t x[8], y[8], r[8];
+            split8(a, x);
+            split8(b, y);
+            m32.mul(r, x, y);
+            return join8(r);
+        }
         uint64_t t[NL + 2];
 #pragma unroll
         for (int i = 0; i < NL + 2; ++i) t[i] = 0;

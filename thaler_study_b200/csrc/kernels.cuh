@@ -245,13 +245,13 @@ __device__ __forceinline__ void pair_into_prod(const A& ar, bool first, const ty
 // ------------------------------------------------------------------------------------------
 template <class A, int K, int PV>
 constexpr int round_min_blocks() {  // resident CTAs per SM the register budget is tuned for
-    if (A::N > 1) return 1;
+    if (A::N > 1) return K <= 3 ? 2 : 1;
     if (A::kLight) return (PV == 1 || K <= 2) ? 8 : 6;
     return K <= 2 ? 6 : 4;
 }
 template <class A, int K, int U>
 constexpr int fold_min_blocks() {
-    if (A::N > 1) return 1;
+    if (A::N > 1) return K <= 3 ? 2 : 1;
     if (A::kLight) return U == 1 ? (K <= 3 ? 8 : 6) : 5;
     return K <= 2 ? 6 : (U == 1 ? 4 : 3);
 }
