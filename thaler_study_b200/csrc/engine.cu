@@ -14,6 +14,7 @@
 
 #include "internal.hpp"
 #include "kernels.cuh"
+#include "eqfix.cuh"
 #include "packed.cuh"
 #include "tail.cuh"
 #include "sumcheck_b200.h"
@@ -472,8 +473,41 @@ static int fold_table(Ctx* c, const FieldImpl& f, const Table& in, const uint64_
     *out = o;
     return SCB_OK;
 }
+static int build_eq_tables(Ctx* c, const FieldImpl& f, const uint64_t* bitpt, uint32_t lb, uint32_t v, BufRef* lo, BufRef* hi);
+// Several variables at once: out[j] = sum_i eq(point; i) * t[..] in ONE pass over the table (eqfix.cuh).
+// high == false: the LOW n variables ([ARK] fix_variables(point)); high == true: the TOP n variables, point[t] bound
+// to variable nv-n+t (= relabel + fix_variables, matrix-multiplication/src/lib.rs:82-83).
+static int fix_table_eq(Ctx* c, const FieldImpl& f, const Table& in, const uint64_t* point, uint32_t n, bool high, Table* out) {
+    for (uint32_t j = 0; j < n; ++j) ARG_TRY(elem_canonical(f, point + (size_t)j * f.d.n), "challenge is not a canonical field element");
+    BufRef eq, unused;
+    RC_TRY(build_eq_tables(c, f, point, n, n, &eq, &unused));
+    Table o;
+    o.nv = in.nv - n;
+    RC_TRY(alloc_buf((size_t)8 * f.d.n << o.nv, &o.buf));
+    const uint64_t n_out = o.len();
+    if (high) {
+        // enough (j, row-slice) threads to fill the machine; slices are summed by a second tiny kernel
+        uint32_t n_slices = 1;
+        while (n_slices < (1u << n) && n_out * n_slices < (uint64_t)c->sms * 2048) n_slices *= 2;
+        BufRef scratch;
+        RC_TRY(alloc_buf((size_t)8 * f.d.n * n_out * n_slices, &scratch));
+        DISPATCH_POLICY(f.policy, {
+            k_fix_high_eq<A><<<grid_for(c, n_out * n_slices), kThreads, 0, g_stream>>>(f.d, in.buf->ptr, eq->ptr, n, scratch->ptr, n_out, n_slices);
+            LAUNCH_CHECK();
+            k_fix_high_finish<A><<<grid_for(c, n_out), kThreads, 0, g_stream>>>(f.d, scratch->ptr, o.buf->ptr, n_out, n_slices);
+        });
+    } else {
+        DISPATCH_POLICY(f.policy, { k_fix_low_eq<A><<<grid_for(c, n_out * 32), kThreads, 0, g_stream>>>(f.d, in.buf->ptr, eq->ptr, n, o.buf->ptr, n_out); });
+    }
+    LAUNCH_CHECK();
+    *out = o;
+    return SCB_OK;
+}
+static uint32_t eq_fix_max_vars(const FieldImpl& f) { return f.d.n == 1 ? 12 : 10; }
+
 static int fix_table(Ctx* c, const FieldImpl& f, const Table& in, const uint64_t* point, uint32_t n, Table* out) {
     ARG_TRY(n <= in.nv, "invalid size of partial point");  // [ARK] assert in fix_variables
+    if (n >= 2 && n <= eq_fix_max_vars(f) && !in.p32) return fix_table_eq(c, f, in, point, n, false, out);
     Table cur = in;
     for (uint32_t i = 0; i < n; ++i) {
         Table nxt;
@@ -495,6 +529,23 @@ extern "C" int scb_mle_fix_variables(const scb_mle* m, const uint64_t* partial_p
     return SCB_OK;
 }
 
+// eq tables over index bits [0, lb) and [lb, v) for the coordinates bitpt[j] (host memory, Montgomery limbs),
+// built by one launch with the point as a kernel argument (eqfix.cuh)
+static int build_eq_tables(Ctx* c, const FieldImpl& f, const uint64_t* bitpt, uint32_t lb, uint32_t v, BufRef* lo, BufRef* hi) {
+    const uint32_t N = f.d.n;
+    ARG_TRY(v <= (uint32_t)kMaxPointCoords, "too many coordinates");
+    RC_TRY(alloc_buf((size_t)8 * N << lb, lo));
+    RC_TRY(alloc_buf((size_t)8 * N << (v - lb), hi));
+    PointArg pa;
+    std::memset(&pa, 0, sizeof pa);
+    if (v) std::memcpy(pa.w, bitpt, (size_t)8 * N * v);
+    const uint32_t cap_bits = N == 1 ? 12 : 10;
+    const size_t smem = (size_t)8 * N << cap_bits;
+    DISPATCH_POLICY(f.policy, { k_eq_tables<A><<<2, 1024, smem, g_stream>>>(f.d, pa, lb, v, (*lo)->ptr, (*hi)->ptr, cap_bits); });
+    LAUNCH_CHECK();
+    return SCB_OK;
+}
+
 // MLE evaluation through eq tables (K4).  bitpt[j] = coordinate bound to index bit j (host memory).
 // Result goes to host (h_out) or, if d_out != nullptr, stays on the device.
 static int eval_table(Ctx* c, const FieldImpl& f, const Table& t, const uint64_t* bitpt, uint64_t* h_out, uint64_t* d_out) {
@@ -503,15 +554,10 @@ static int eval_table(Ctx* c, const FieldImpl& f, const Table& t, const uint64_t
     for (uint32_t j = 0; j < v; ++j) ARG_TRY(elem_canonical(f, bitpt + (size_t)j * N), "point coordinate is not canonical");
     const uint32_t lb_max = N == 1 ? 12 : 10;
     const uint32_t lb = v < lb_max ? v : lb_max;
-    BufRef pt, lo, hi;
-    RC_TRY(alloc_buf((size_t)8 * N * (v ? v : 1), &pt));
-    RC_TRY(alloc_buf((size_t)8 * N << lb, &lo));
-    RC_TRY(alloc_buf((size_t)8 * N << (v - lb), &hi));
-    if (v) CU_TRY(cudaMemcpyAsync(pt->ptr, bitpt, (size_t)8 * N * v, cudaMemcpyHostToDevice, g_stream));
+    BufRef lo, hi;
+    RC_TRY(build_eq_tables(c, f, bitpt, lb, v, &lo, &hi));
     uint64_t* res = d_out ? d_out : c->h_res;
     DISPATCH_POLICY(f.policy, {
-        k_eq_build<A><<<2, 1024, 0, g_stream>>>(f.d, pt->ptr, lb, v, lo->ptr, hi->ptr);
-        LAUNCH_CHECK();
         const size_t smem = (size_t)8 * N << lb;
         const uint64_t n = t.len();
         if (A::N == 1 && lb >= 2) {
@@ -660,8 +706,17 @@ extern "C" int scb_poly_matmul_g_new(const scb_field* f, uint32_t n, const uint6
     const uint32_t N = f->impl->d.n;
     scb_mle *ma = nullptr, *mar = nullptr, *maf = nullptr, *mb = nullptr, *mbf = nullptr;
     int rc = scb_mle_from_host(f, 2 * n, a, &ma);                              // :81
-    if (rc == SCB_OK) rc = scb_mle_relabel(ma, 0, n, n, &mar);                 // :82
-    if (rc == SCB_OK) rc = scb_mle_fix_variables(mar, point, n, &maf);         // :83
+    if (rc == SCB_OK && n >= 2 && n <= eq_fix_max_vars(*f->impl)) {
+        // :82-83 relabel(0, n, n) + fix_variables(&point[..n]) == fixing the HIGH variable block directly (one pass)
+        Ctx* c = nullptr;
+        rc = get_ctx(&c);
+        Table t;
+        if (rc == SCB_OK) rc = fix_table_eq(c, *ma->f, ma->t, point, n, true, &t);
+        if (rc == SCB_OK) maf = new scb_mle{ma->f, t};
+    } else {
+        if (rc == SCB_OK) rc = scb_mle_relabel(ma, 0, n, n, &mar);             // :82
+        if (rc == SCB_OK) rc = scb_mle_fix_variables(mar, point, n, &maf);     // :83
+    }
     if (rc == SCB_OK) rc = scb_mle_from_host(f, 2 * n, b, &mb);                // :85
     if (rc == SCB_OK) rc = scb_mle_fix_variables(mb, point + (size_t)n * N, n, &mbf);  // :86
     if (rc == SCB_OK) rc = scb_poly_matmul_g(maf, mbf, out);

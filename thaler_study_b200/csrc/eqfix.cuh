@@ -1,0 +1,146 @@
+// eqfix.cuh -- eq/chi tables and the kernels that contract a table against one.
+//
+// * k_eq_tables: builds up to two eq tables (low / high index bits) by parallel doubling, in shared memory, with the
+//   point passed as a kernel argument (no allocation, no H2D copy): multilinear-extensions/src/lib.rs:9-18.
+// * k_fix_low_eq / k_fix_high_eq: [ARK] fix_variables of SEVERAL variables in ONE pass -- out[j] = sum_i eq(r; i) *
+//   t[...] -- instead of one fold pass per variable.  Exact field arithmetic, so the result equals the reference's
+//   sequence of folds element for element.  Used by G::new (matrix-multiplication/src/lib.rs:77-92), where the
+//   set-up folds are ~1000x the work of the sum-check itself: f_A is obtained by fixing the HIGH
+//   variable block of the row-major matrix directly, which equals relabel(0,n,n) followed by fixing the low block.
+#pragma once
+#include <cstdint>
+
+#include "kernels.cuh"
+
+namespace scb {
+
+constexpr int kMaxPointCoords = 40;
+struct PointArg {  // coordinate bound to index bit j at w[j * n_limbs ...]
+    uint64_t w[kMaxPointCoords * kMaxLimbs];
+};
+
+// Block b builds table b: bits [first_b, first_b + nb_b) of the index, first_0 = 0 / nb_0 = lb, first_1 = lb / nb_1 = v - lb.
+// Level l appends index bit l:  t[i + 2^l] = t[i]*c ; t[i] -= t[i + 2^l]  (= t[i]*(1-c)).  Levels that fit are done in
+// shared memory (cap_bits), the rest in global memory.
+template <class A>
+__global__ void __launch_bounds__(1024) k_eq_tables(FieldDesc f, PointArg pt, uint32_t lb, uint32_t v, uint64_t* lo_tab, uint64_t* hi_tab,
+                                                    uint32_t cap_bits) {
+    constexpr int N = A::N;
+    extern __shared__ uint64_t eq_sm[];
+    const A ar(f);
+    const uint32_t first = blockIdx.x == 0 ? 0 : lb;
+    const uint32_t nb = blockIdx.x == 0 ? lb : v - lb;
+    uint64_t* out = blockIdx.x == 0 ? lo_tab : hi_tab;
+    const uint32_t nb_sm = nb < cap_bits ? nb : cap_bits;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) eq_sm[i] = f.one[i];
+    }
+    __syncthreads();
+    for (uint32_t l = 0; l < nb_sm; ++l) {
+        const typename A::El c = ar.from_words(pt.w + (size_t)(first + l) * N);
+        const uint32_t half = 1u << l;
+        for (uint32_t i = threadIdx.x; i < half; i += blockDim.x) {
+            typename A::El cur = ar.from_words(eq_sm + (size_t)i * N);
+            typename A::El hi = ar.mul(cur, c);
+            ar.to_words(hi, eq_sm + (size_t)(i + half) * N);
+            ar.to_words(ar.sub(cur, hi), eq_sm + (size_t)i * N);
+        }
+        __syncthreads();
+    }
+    const uint64_t words = ((uint64_t)N) << nb_sm;
+    for (uint64_t i = threadIdx.x; i < words; i += blockDim.x) out[i] = eq_sm[i];
+    __syncthreads();
+    for (uint32_t l = nb_sm; l < nb; ++l) {  // large tables: remaining levels in global memory
+        const typename A::El c = ar.from_words(pt.w + (size_t)(first + l) * N);
+        const uint64_t half = 1ull << l;
+        for (uint64_t i = threadIdx.x; i < half; i += blockDim.x) {
+            typename A::El cur = ar.from_words(out + i * N);
+            typename A::El hi = ar.mul(cur, c);
+            ar.to_words(hi, out + (i + half) * N);
+            ar.to_words(ar.sub(cur, hi), out + i * N);
+        }
+        __syncthreads();
+    }
+}
+
+// out[j] = sum_{i < 2^m} eq[i] * t[j * 2^m + i]      (the LOW m variables fixed); one warp per output
+template <class A>
+__global__ void __launch_bounds__(kThreads) k_fix_low_eq(FieldDesc f, const uint64_t* __restrict__ tab, const uint64_t* __restrict__ eq,
+                                                         uint32_t m, uint64_t* __restrict__ outp, uint64_t n_out) {
+    constexpr int N = A::N, AW = A::AW;
+    const A ar(f);
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t len = 1ull << m;
+    for (uint64_t j = warp0; j < n_out; j += n_warps) {
+        typename A::Acc acc;
+        ar.acc_zero(acc);
+        for (uint64_t i = lane; i < len; i += 32) {
+            uint64_t e[N];
+#pragma unroll
+            for (int q = 0; q < N; ++q) e[q] = __ldg(eq + i * N + q);
+            ar.acc_add(acc, ar.lz_mul(ar.lz(ld_el(ar, tab, j * len + i)), ar.lz(ar.from_words(e))));
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            uint64_t w[AW];
+            ar.acc_to_words(acc, w);
+#pragma unroll
+            for (int q = 0; q < AW; ++q) w[q] = __shfl_xor_sync(0xffffffffu, w[q], off);
+            typename A::Acc o;
+            ar.acc_from_words(o, w);
+            ar.acc_merge(acc, o);
+        }
+        if (lane == 0) {
+            uint64_t o[N];
+            ar.to_words(ar.acc_final(acc), o);
+            st_words<N>(outp + j * N, o);
+        }
+    }
+}
+
+// out[j] = sum_{i < 2^m} eq[i] * t[i * n_out + j]    (the HIGH m variables fixed): a vector-matrix product.
+// Thread (j, slice s) accumulates rows i = s, s + S, s + 2S, ... (rows are read coalesced across j, several
+// independent loads in flight); the S partial rows go to scratch and k_fix_high_finish adds them.
+template <class A>
+__global__ void __launch_bounds__(kThreads) k_fix_high_eq(FieldDesc f, const uint64_t* __restrict__ tab, const uint64_t* __restrict__ eq,
+                                                          uint32_t m, uint64_t* __restrict__ scratch, uint64_t n_out, uint32_t n_slices) {
+    constexpr int N = A::N;
+    const A ar(f);
+    const uint64_t len = 1ull << m;
+    const uint64_t total = n_out * n_slices;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const uint64_t j = t % n_out, s = t / n_out;
+        typename A::Acc acc;
+        ar.acc_zero(acc);
+#pragma unroll 4
+        for (uint64_t i = s; i < len; i += n_slices) {
+            uint64_t e[N];
+#pragma unroll
+            for (int q = 0; q < N; ++q) e[q] = __ldg(eq + i * N + q);
+            ar.acc_add(acc, ar.lz_mul(ar.lz(ld_el(ar, tab, i * n_out + j)), ar.lz(ar.from_words(e))));
+        }
+        uint64_t o[N];
+        ar.to_words(ar.acc_final(acc), o);
+        st_words<N>(scratch + t * N, o);
+    }
+}
+template <class A>
+__global__ void __launch_bounds__(kThreads) k_fix_high_finish(FieldDesc f, const uint64_t* __restrict__ scratch, uint64_t* __restrict__ outp,
+                                                              uint64_t n_out, uint32_t n_slices) {
+    constexpr int N = A::N;
+    const A ar(f);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_out; j += stride) {
+        typename A::El acc = ld_el(ar, scratch, j);
+        for (uint32_t s = 1; s < n_slices; ++s) acc = ar.add(acc, ld_el(ar, scratch, (uint64_t)s * n_out + j));
+        uint64_t o[N];
+        ar.to_words(acc, o);
+        st_words<N>(outp + j * N, o);
+    }
+}
+
+}  // namespace scb
