@@ -220,6 +220,33 @@ int scb_transcript_c_1(const scb_transcript* t, uint64_t* out_elem);
 int scb_transcript_bytes(const scb_transcript* t, uint8_t* out, size_t cap, size_t* out_len, uint64_t* offsets, uint32_t cap_msgs,
                          uint32_t* n_msgs);
 
+/* ------------------------------------------------------------------ GKR with gate-list wiring
+ * gkr_protocol::Circuit (gkr-protocol/src/circuit.rs:70-124) and the layer prover of gkr_protocol::Prover
+ * (gkr-protocol/src/lib.rs:346-456) without the reference's dense 2^(k_i + 2 k_{i+1})-entry wiring tables: each layer is
+ * two k-round sum-checks of the form P*Q + S over 2^k-entry tables built from the gate list (thaler_study_b200/csrc/gkr.cuh).
+ * Messages are the same polynomials as the reference's W::to_univariate (round_polynomial.rs:78-90). */
+typedef struct scb_circuit scb_circuit;
+typedef struct scb_gkr_prover scb_gkr_prover;
+/* Circuit::new(layers, num_inputs): layer 0 = outputs; gates concatenated layer after layer; type 0 = Add, 1 = Mul;
+ * in0/in1 index the next layer (the inputs for the last layer).  All sizes must be powers of two. */
+int scb_circuit_create(const scb_field* f, uint32_t n_layers, const uint32_t* layer_sizes, const uint8_t* types, const uint32_t* in0,
+                       const uint32_t* in1, uint32_t num_inputs, scb_circuit** out);
+void scb_circuit_free(scb_circuit* c);
+int scb_circuit_num_vars_at(const scb_circuit* c, uint32_t layer, uint32_t* out);              /* circuit.rs:86-96 */
+/* add~_i(r_i, b, c) and mul~_i(r_i, b, c) (circuit.rs:152-212 evaluated at (b, c)) in O(#gates) */
+int scb_circuit_wiring_eval(const scb_circuit* c, uint32_t layer, const uint64_t* r_i, const uint64_t* b, const uint64_t* cpt,
+                            uint64_t* add_out, uint64_t* mul_out);
+int scb_gkr_prover_new(const scb_circuit* c, const uint64_t* input, size_t n_input, scb_gkr_prover** out); /* lib.rs:346-357 */
+void scb_gkr_prover_free(scb_gkr_prover* p);
+/* CircuitEvaluation::layers[layer] as a dense MLE handle (layer 0 = outputs: start_protocol, lib.rs:363-367) */
+int scb_gkr_prover_layer(const scb_gkr_prover* p, uint32_t layer, scb_mle** out);
+/* start_round(i, r_i) lib.rs:373-436 -> StartSumCheck { c_1, num_vars = 2 k_{i+1} } */
+int scb_gkr_prover_start_round(scb_gkr_prover* p, uint32_t i, const uint64_t* r_i, uint64_t* c_1_out, uint32_t* num_vars_out);
+/* round_msg(j) lib.rs:439-456 as the sums at X = 0,1,2 (-> scb_evals_to_univariate, kind SCB_POLY_GKR_W); r_prev = r_{j-1} */
+int scb_gkr_prover_round_evals(scb_gkr_prover* p, uint32_t j, const uint64_t* r_prev, uint64_t* out_evals);
+/* q = restrict_poly(b*, c*, W~_{i+1}) lib.rs:291-321 as its k+1 values at t = 0..k; r_final = the final random point */
+int scb_gkr_prover_restrict_evals(scb_gkr_prover* p, const uint64_t* r_final, uint64_t* out_evals, uint32_t cap, uint32_t* n_out);
+
 /* ------------------------------------------------------------------ multi-GPU: peer windows over NVLink
  * One process per GPU.  Each rank owns a small window in its HBM (cudaMalloc) that every peer maps through CUDA IPC;
  * the round kernels' finishing thread posts the rank's (d+1) partial sums into all peers' windows with P2P stores,

@@ -89,6 +89,16 @@ SIGNATURES = {
     "scb_verifier_round": (C.c_int, [vp, u64p, u64p, C.c_uint32, u64p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "scb_fs_generate_transcript": (C.c_int, [vp, u8p, C.c_size_t, C.POINTER(C.c_size_t), u64p]),
     "scb_fs_verify_transcript": (C.c_int, [vp, u8p, u64p, C.c_uint32, C.POINTER(C.c_int)]),
+    "scb_circuit_create": (C.c_int, [vp, C.c_uint32, u32p, u8p, u32p, u32p, C.c_uint32, vpp]),
+    "scb_circuit_free": (None, [vp]),
+    "scb_circuit_num_vars_at": (C.c_int, [vp, C.c_uint32, u32p]),
+    "scb_circuit_wiring_eval": (C.c_int, [vp, C.c_uint32, u64p, u64p, u64p, u64p, u64p]),
+    "scb_gkr_prover_new": (C.c_int, [vp, u64p, C.c_size_t, vpp]),
+    "scb_gkr_prover_free": (None, [vp]),
+    "scb_gkr_prover_layer": (C.c_int, [vp, C.c_uint32, vpp]),
+    "scb_gkr_prover_start_round": (C.c_int, [vp, C.c_uint32, u64p, u64p, u32p]),
+    "scb_gkr_prover_round_evals": (C.c_int, [vp, C.c_uint32, u64p, u64p]),
+    "scb_gkr_prover_restrict_evals": (C.c_int, [vp, u64p, u64p, C.c_uint32, u32p]),
     "scb_peers_create": (C.c_int, [C.c_uint32, C.c_uint32, C.c_size_t, vpp, u8p]),
     "scb_peers_connect": (C.c_int, [vp, u8p]),
     "scb_peers_free": (None, [vp]),

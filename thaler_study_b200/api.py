@@ -18,7 +18,7 @@ import numpy as np
 
 from ._lib import SCB_OK, ScbError, check, lib, u8p, u64p
 
-MAX_TERMS = 8
+MAX_TERMS = 64
 
 
 def _p64(a: np.ndarray):
@@ -256,6 +256,14 @@ def evals_to_univariate(F: Field, kind: int, evals: Sequence[int]) -> SparsePoly
     deg, co, n = _terms_out(F)
     ev = F.to_mont(list(evals))
     check(lib.scb_evals_to_univariate(F._h, kind, _p64(ev), len(evals), _p64(deg), _p64(co), MAX_TERMS, C.byref(n)))
+    return _poly_from_out(F, deg, co, n)
+
+
+def evals_to_univariate_mont(F: Field, kind: int, ev_mont: np.ndarray) -> SparsePolynomial:
+    """Same as evals_to_univariate with the sums given as Montgomery limbs uint64[n_points, n_limbs]."""
+    deg, co, n = _terms_out(F)
+    ev = np.ascontiguousarray(ev_mont.reshape(-1, F.n))
+    check(lib.scb_evals_to_univariate(F._h, kind, _p64(ev), ev.shape[0], _p64(deg), _p64(co), MAX_TERMS, C.byref(n)))
     return _poly_from_out(F, deg, co, n)
 
 

@@ -15,6 +15,7 @@
 #include "internal.hpp"
 #include "kernels.cuh"
 #include "eqfix.cuh"
+#include "gkr.cuh"
 #include "packed.cuh"
 #include "tail.cuh"
 #include "sumcheck_b200.h"
@@ -1377,3 +1378,6 @@ extern "C" int scb_poly_field_impl(const scb_poly* p, const FieldImpl** out) {
     *out = p->f.get();
     return SCB_OK;
 }
+
+// ------------------------------------------------------------------------------------------ GKR (sparse wiring)
+#include "gkr_engine.inc"

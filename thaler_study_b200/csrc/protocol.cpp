@@ -32,7 +32,7 @@ extern "C" int scb_poly_field_impl(const scb_poly* p, const FieldImpl** out);
         if (rc__ != SCB_OK) return rc__; \
     } while (0)
 
-static constexpr uint32_t kMaxTerms = 8;
+static constexpr uint32_t kMaxTerms = 64;  // restrict_poly of a 2^40-gate layer has 41 points
 
 // (d+1) sums -> the univariate::SparsePolynomial each implementor's to_univariate returns
 static SparsePoly evals_to_poly(const HostField& F, uint32_t kind, const std::vector<Fe>& ev) {
