@@ -45,7 +45,7 @@ class Field:
         self.policy = pol.value
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib.scb_field_free(self._h)
             self._h = None
 
@@ -110,7 +110,7 @@ class DenseMultilinearExtension:
         self._h = handle
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib.scb_mle_free(self._h)
             self._h = None
 
@@ -279,7 +279,7 @@ class SumCheckPolynomial:
         self._h = handle
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib.scb_poly_free(self._h)
             self._h = None
 
@@ -439,7 +439,7 @@ class Prover:
         check(lib.scb_prover_new(g._h, C.byref(self._h)))
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib.scb_prover_free(self._h)
             self._h = None
 
@@ -471,7 +471,7 @@ class Verifier:
         check(lib.scb_verifier_new(self.F._h, n, g._h if g is not None else None, C.byref(self._h)))
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib.scb_verifier_free(self._h)
             self._h = None
 
@@ -525,7 +525,7 @@ class Transcript:
         self._r = np.zeros((1, F.n), dtype=np.uint64)
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib.scb_transcript_free(self._h)
             self._h = None
 

@@ -47,7 +47,7 @@ class Circuit:
         return self
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib.scb_circuit_free(self._h)
             self._h = None
 
@@ -80,7 +80,7 @@ class GkrProver:
         self.r: List[int] = []
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib.scb_gkr_prover_free(self._h)
             self._h = None
 
