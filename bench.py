@@ -179,7 +179,20 @@ def run_ours(args):
     T.synchronize()
 
     exchange = os.environ.get("SCB_EXCHANGE", "p2p")  # p2p: in-kernel exchange over NVLink peer memory; nccl: all-gather
-    peers = Peers() if world > 1 and exchange == "p2p" else None
+    peers = None
+    if world > 1 and exchange == "p2p":
+        # CUDA IPC windows need peer access between the ranks' GPUs; every rank must take the same path, so the
+        # outcome is agreed on with an all-reduce and NCCL all-gather is the (slower) alternative exchange
+        try:
+            peers = Peers()
+            ok_local = 1
+        except Exception as ex:  # noqa: BLE001
+            print(f"[bench] rank {rank}: peer windows unavailable ({ex}); using the NCCL exchange", file=sys.stderr)
+            ok_local = 0
+        flag = torch.tensor([ok_local], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() == 0:
+            peers, exchange = None, "nccl"
 
     def prove(poly):
         if world == 1:
@@ -247,8 +260,11 @@ def run_ours(args):
         peak, peak_src = hbm_peak()
         achieved = alg_bytes / (kms * 1e-3) / 1e9
         kname = "k_fold_round_sp<3,in=u64,out=u32>" if packed else "k_fold_round<%s,3>" % {0: "PolSP", 1: "PolG1", 4: "PolGN<4>"}[F.policy]
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size from the committed ncu --set full
+        # capture (profiles/r01_ncu_summary_final.md: 6.442495 GB + 1.613603 GB per launch); null for other shapes
+        traffic = 8.056098e9 if (packed and v == 28 and K == 3 and p == MODULUS) else None
         roof = {"bound": "hbm", "kernel": kname + " (fused fold + round message), 2^%d-entry tables" % v,
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "survey_bytes_per_launch_unpacked": survey_bytes, "frac_vs_survey_bytes": survey_bytes / (kms * 1e-3) / 1e9 / peak,
                 "proof_bytes_moved": proof_bytes, "proof_frac_of_hbm_roofline": (proof_bytes / (ms * 1e-3) / 1e9) / peak,

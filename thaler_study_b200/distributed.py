@@ -170,14 +170,26 @@ class Peers:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._h = C.c_void_p()
         handle = (C.c_uint8 * 64)()
-        check(lib.scb_peers_create(self.rank, self.world, gather_bytes, C.byref(self._h), handle))
+        # every rank takes part in every collective below even if a local step fails; the outcome is agreed on last
+        err = None
+        rc = lib.scb_peers_create(self.rank, self.world, gather_bytes, C.byref(self._h), handle)
+        if rc != 0:
+            err = (lib.scb_last_error() or b"").decode()
         if self.world > 1:
             mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device="cuda")
             allh = torch.empty(self.world * 64, dtype=torch.uint8, device="cuda")
             dist.all_gather_into_tensor(allh, mine, group=group)
-            buf = (C.c_uint8 * (self.world * 64)).from_buffer_copy(bytes(allh.cpu().tolist()))
-            check(lib.scb_peers_connect(self._h, buf))
-            dist.barrier(group)
+            if err is None:
+                buf = (C.c_uint8 * (self.world * 64)).from_buffer_copy(bytes(allh.cpu().tolist()))
+                if lib.scb_peers_connect(self._h, buf) != 0:
+                    err = (lib.scb_last_error() or b"").decode()
+            flag = torch.tensor([0 if err is None else 1], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            if flag.item() != 0:
+                self.close()
+                raise RuntimeError(f"peer windows unavailable on at least one rank ({err or 'error on another rank'})")
+        elif err is not None:
+            raise RuntimeError(err)
 
     def close(self):
         if getattr(self, "_h", None):
