@@ -145,11 +145,6 @@ static int occ_grid(const Ctx* c, KernelT kernel, uint64_t items, size_t dyn_sme
     if (want < 1) want = 1;
     return (int)(want < cap ? want : cap);
 }
-static int tune_unroll() {
-    static const int u = getenv("SCB_UNROLL") ? atoi(getenv("SCB_UNROLL")) : 1;
-    return u;
-}
-
 #define LAUNCH_CHECK()                                                                      \
     do {                                                                                    \
         g_launches.fetch_add(1, std::memory_order_relaxed);                                 \
@@ -1046,14 +1041,8 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
                 in.p[k] = p->t[k].buf->ptr;
                 o.p[k] = q->t[k].buf->ptr;
             }
-            if (A::N == 1 && tune_unroll() == 2) {
-                constexpr int U = A::N == 1 ? 2 : 1;
-                auto kern = k_fold_round<A, K, U>;
-                kern<<<occ_grid(c, kern, (n_quads + U - 1) / U), kThreads, 0, g_stream>>>(f.d, in, o, ra, n_quads, c->partials, c->ticket, res, peer_arg(c));
-            } else {
-                auto kern = k_fold_round<A, K, 1>;
-                kern<<<occ_grid(c, kern, n_quads, 0, A::kLight ? 5 : 0), kThreads, 0, g_stream>>>(f.d, in, o, ra, n_quads, c->partials, c->ticket, res, peer_arg(c));
-            }
+            auto kern = k_fold_round<A, K, 1>;
+            kern<<<occ_grid(c, kern, n_quads, 0, A::kLight ? 5 : 0), kThreads, 0, g_stream>>>(f.d, in, o, ra, n_quads, c->partials, c->ticket, res, peer_arg(c));
         }));
         LAUNCH_CHECK();
     } else {

@@ -447,37 +447,8 @@ __global__ void __launch_bounds__(kThreads) k_product_table(FieldDesc f, TabsIn<
 // LSB-first order).  The 2^v-entry chi table of the reference is never materialised: it is the
 // outer product of a table over the low `lb` index bits and one over the high v-lb bits.
 //
-// k_eq_build: block b builds table b (0 = low bits, 1 = high bits) in global memory by parallel
-// doubling: level l appends index bit l:  t[i + 2^l] = t[i]*c ; t[i] -= t[i + 2^l]   (= t[i]*(1-c)).
-// bitpt[j] is the point coordinate bound to index bit j (host resolves BE/LE order).
+// The two tables are built by k_eq_tables (eqfix.cuh).
 // ------------------------------------------------------------------------------------------
-template <class A>
-__global__ void __launch_bounds__(1024) k_eq_build(FieldDesc f, const uint64_t* __restrict__ bitpt, uint32_t lb, uint32_t v,
-                                                   uint64_t* lo_tab, uint64_t* hi_tab) {
-    constexpr int N = A::N;
-    const A ar(f);
-    const uint32_t first = blockIdx.x == 0 ? 0 : lb;
-    const uint32_t nb = blockIdx.x == 0 ? lb : v - lb;
-    uint64_t* t = blockIdx.x == 0 ? lo_tab : hi_tab;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) t[i] = f.one[i];
-    }
-    __syncthreads();
-    for (uint32_t l = 0; l < nb; ++l) {
-        const typename A::El c = ar.from_words(bitpt + (size_t)(first + l) * N);
-        const uint64_t half = 1ull << l;
-        for (uint64_t i = threadIdx.x; i < half; i += blockDim.x) {
-            typename A::El cur = ar.from_words(t + i * N);
-            typename A::El hi = ar.mul(cur, c);
-            typename A::El lo = ar.sub(cur, hi);
-            ar.to_words(hi, t + (i + half) * N);
-            ar.to_words(lo, t + i * N);
-        }
-        __syncthreads();
-    }
-}
-
 // k_mle_dot: sum_i evals[i] * lo[i & (2^lb-1)] * hi[i >> lb].  VEC consecutive entries (same row)
 // per thread-iteration; lo table staged in shared memory.
 template <class A, int VEC>
