@@ -164,6 +164,13 @@ int scb_poly_allow_packed(scb_poly* p, int enable);
 typedef int (*scb_round_cb)(void* user, uint32_t round, const uint64_t* evals, uint64_t* next_challenge_out);
 int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, uint32_t n_points, scb_round_cb cb, void* user,
                          uint32_t* rounds_done);
+/* Same, for at most `max_rounds` rounds (0 = all m-1): small tables run in a single-CTA kernel, large ones in a
+ * grid-wide cooperative kernel whose CTAs meet at a ticket/flag barrier between rounds.  With a current peer group
+ * (scb_peers_set_current) the grid-wide kernel also exchanges the round sums with the peer GPUs every round.
+ * `*out_folded` (optional) receives the polynomial after the rounds that ran -- what max_rounds calls of
+ * scb_poly_fix_and_round_evals would have returned last. */
+int scb_poly_resident_rounds(const scb_poly* p, const uint64_t* r_first, uint32_t n_points, uint32_t max_rounds, scb_round_cb cb,
+                             void* user, uint32_t* rounds_done, scb_poly** out_folded);
 
 /* ------------------------------------------------------------------ round-message algebra (host) */
 /* (d+1) sums at X = 0..d  ->  the SparsePolynomial the reference would send, per implementor:

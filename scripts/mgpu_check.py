@@ -15,8 +15,10 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 lg = world.bit_length() - 1
 ok = True
 peers = Peers()
-for p, lv, K, cat in ((1572869, 20, 3, 16), (1572869, 12, 3, 4), (389, 9, 2, 16), (0xFFFFFFFF00000001, 14, 2, 10),
-                      (0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001, 12, 3, 8)):
+BLS = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+# lv >= 15: the sharded rounds run in the grid-wide resident kernel (exchange inside it); smaller: one launch per round
+for p, lv, K, cat in ((1572869, 20, 3, 16), (1572869, 18, 3, 3), (1572869, 17, 4, 16), (1572869, 12, 3, 4), (389, 9, 2, 16),
+                      (0xFFFFFFFF00000001, 14, 2, 10), (0xFFFFFFFF00000001, 16, 3, 10), (BLS, 12, 3, 8), (BLS, 15, 2, 9)):
     F = T.Field(p)
     slabs = [T.DenseMultilinearExtension.synthetic(F, lv, 900 + k, start=rank << lv) for k in range(K)]
     c_1, msgs = prove_sharded(CudaProductEngine(T.ProductMLE.new(slabs)), consolidate_at=cat)

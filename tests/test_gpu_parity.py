@@ -417,3 +417,31 @@ def test_tail_kernel_matches_per_round_launches():
     tabs = [cf.from_mont(cf.synth(50 + k, 0, 1 << 13)) for k in range(3)]
     want = O.generate_transcript(OF, O.Prover(O.ProductMLE(OF, [O.DenseMLE(OF, 13, t) for t in tabs])))
     assert outs[0].stdout.split()[0] == b"".join(want).hex()
+
+
+def test_grid_resident_kernel_matches_per_round_launches():
+    """The grid-wide resident kernel (persist.cuh: all rounds in one cooperative launch, ticket/flag barrier between
+    rounds) must give the same transcript bytes as one launch per round.  SCB_PERSIST_VARS=4 forces it onto tiny
+    tables too (single active CTA, the u32 quad-pair path running out of pairs)."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import thaler_study_b200 as T\n"
+        "for p, v, K in ((1572869, 19, 3), (1572869, 16, 4), (1572869, 6, 1), (5, 15, 2), (0xFFFFFFFF00000001, 17, 3), (%d, 15, 2)):\n"
+        "    F = T.Field(p)\n"
+        "    g = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, 90 + k) for k in range(K)])\n"
+        "    print(b''.join(T.generate_transcript(T.Prover(g))).hex())\n"
+        "    a = T.DenseMultilinearExtension.synthetic(F, v, 7); b = T.DenseMultilinearExtension.synthetic(F, v, 8)\n"
+        "    print(b''.join(T.generate_transcript(T.Prover(T.MatMulG.from_tables(a, b)))).hex())\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), O.BLS12_381_FR.p)
+    outs = []
+    for env_add in ({"SCB_TAIL_VARS": "0"}, {"SCB_PERSIST_VARS": "0"}, {"SCB_PERSIST_VARS": "4"}, {}, {"SCB_PERSIST_VARS": "17"}):
+        env = dict(os.environ, **env_add)
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600))
+    for o in outs:
+        assert o.returncode == 0, o.stderr[-2000:]
+    assert len(outs[0].stdout.split()) == 12
+    assert len(set(o.stdout for o in outs)) == 1

@@ -74,6 +74,7 @@ SIGNATURES = {
     "scb_poly_fix_and_round_evals_device": (C.c_int, [vp, u64p, C.c_uint32, vpp, vp]),
     "scb_poly_allow_packed": (C.c_int, [vp, C.c_int]),
     "scb_poly_tail_rounds": (C.c_int, [vp, u64p, C.c_uint32, ROUND_CB, vp, u32p]),
+    "scb_poly_resident_rounds": (C.c_int, [vp, u64p, C.c_uint32, C.c_uint32, ROUND_CB, vp, u32p, C.POINTER(vp)]),
     "scb_evals_to_univariate": (C.c_int, [vp, C.c_uint32, u64p, C.c_uint32, u64p, u64p, C.c_uint32, u32p]),
     "scb_unipoly_serialize": (C.c_int, [vp, u64p, u64p, C.c_uint32, u8p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "scb_unipoly_evaluate": (C.c_int, [vp, u64p, u64p, C.c_uint32, u64p, u64p]),

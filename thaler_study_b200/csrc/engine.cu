@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -18,6 +20,7 @@
 #include "gkr.cuh"
 #include "packed.cuh"
 #include "tail.cuh"
+#include "persist.cuh"
 #include "sumcheck_b200.h"
 
 using namespace scb;
@@ -68,6 +71,8 @@ struct Ctx {
     uint64_t* h_res = nullptr;     // mapped pinned host memory: kernels write round sums here directly
     uint64_t* d_scratch = nullptr; // small device scratch (points, results)
     TailMailbox* mailbox = nullptr; // mapped pinned host memory shared with the persistent tail kernel
+    PersistCtl* persist_ctl = nullptr; // device memory: barrier state of the grid-wide resident kernel
+    int coop = 0;                   // cooperative launches supported
 };
 static constexpr int kMaxGrid = 148 * 16;
 static constexpr int kMaxDev = 16;
@@ -99,6 +104,8 @@ static int get_ctx(Ctx** out) {
             CU_TRY(cudaMalloc(&c.d_scratch, 64 * 1024));
             CU_TRY(cudaHostAlloc(&c.mailbox, sizeof(TailMailbox), cudaHostAllocMapped | cudaHostAllocPortable));
             std::memset((void*)c.mailbox, 0, sizeof(TailMailbox));
+            CU_TRY(cudaMalloc(&c.persist_ctl, sizeof(PersistCtl)));
+            CU_TRY(cudaDeviceGetAttribute(&c.coop, cudaDevAttrCooperativeLaunch, dev));
             c.sms = sms;
             c.dev = dev;
         }
@@ -1143,62 +1150,155 @@ extern "C" int scb_poly_to_evaluations(const scb_poly* p, uint64_t* out, size_t 
 // ------------------------------------------------------------------------------------------ persistent tail
 // Runs ALL remaining rounds of a product polynomial (m = num_vars >= 2 -> m-1 rounds) in one resident kernel
 // (tail.cuh).  For round t the callback receives the n_points sums and returns the next challenge.
+// Resident-kernel thresholds (variables of the table about to be folded):
+//   m <= SCB_TAIL_VARS (14)               single-CTA tail (tail.cuh); 0 disables both resident kernels
+//   SCB_PERSIST_VARS (15) <= m <= limit   grid-wide resident kernel (persist.cuh); 0 disables it.  The limit is 32 for
+//                                         the small-prime policy (HBM-bound: saves launch + ramp per round) and
+//                                         SCB_PERSIST_MAX_GENERIC (22) for the integer-bound policies, whose big
+//                                         rounds run faster in the leaner per-round kernels.
+static uint32_t env_u32(const char* name, uint32_t dflt) { return getenv(name) ? (uint32_t)atoi(getenv(name)) : dflt; }
+static uint32_t tail_max_vars() {
+    static const uint32_t v = env_u32("SCB_TAIL_VARS", 14);
+    return v > 24 ? 24 : v;
+}
+static uint32_t persist_min_vars() {
+    static const uint32_t v = env_u32("SCB_PERSIST_VARS", 15);
+    return v == 0 ? 1000 : (v < 4 ? 4 : v);
+}
+static uint32_t persist_max_vars(uint32_t policy) {
+    static const uint32_t g = env_u32("SCB_PERSIST_MAX_GENERIC", 22);
+    return policy == POL_SP ? 32 : (g > kTailMaxRounds + 1 ? kTailMaxRounds + 1 : g);
+}
+bool scb::resident_rounds_ok(const scb_poly* p, bool need_grid) {
+    if (!p || !(p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) || p->t.empty()) return false;
+    const uint32_t m = p->t[0].nv, tv = tail_max_vars();
+    if (tv < 2 || m < 2) return false;
+    if (m <= tv && m < persist_min_vars()) return !need_grid;
+    Ctx* c;
+    if (get_ctx(&c) != SCB_OK || !c->coop) return false;
+    return m >= persist_min_vars() && m <= persist_max_vars(p->f->policy);
+}
 extern "C" int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, uint32_t n_points, scb_round_cb cb, void* user,
                                     uint32_t* rounds_done) {
+    return scb_poly_resident_rounds(p, r_first, n_points, 0, cb, user, rounds_done, nullptr);
+}
+extern "C" int scb_poly_resident_rounds(const scb_poly* p, const uint64_t* r_first, uint32_t n_points, uint32_t max_rounds, scb_round_cb cb,
+                                        void* user, uint32_t* rounds_done, scb_poly** out_folded) {
     ARG_TRY(p && r_first && cb && rounds_done, "null argument");
     *rounds_done = 0;
+    if (out_folded) *out_folded = nullptr;
     ARG_TRY(p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G, "the persistent tail handles product polynomials only");
     ARG_TRY(n_points == poly_n_points(p), "n_points must be the full message size");
     const uint32_t m = p->t[0].nv;
-    ARG_TRY(m >= 2 && m <= 24, "tail needs 2..24 variables");
+    ARG_TRY(m >= 2 && m <= kTailMaxRounds + 1, "resident rounds need 2..33 variables");
     Ctx* c;
     RC_TRY(get_ctx(&c));
     const FieldImpl& f = *p->f;
-    const uint32_t N = f.d.n, n_rounds = m - 1;
+    const uint32_t N = f.d.n, n_rounds = (max_rounds == 0 || max_rounds > m - 1) ? m - 1 : max_rounds;
+    ARG_TRY(f.policy != POL_SP || m <= 32, "table too large for the small-prime path");
     ARG_TRY(elem_canonical(f, r_first), "challenge is not a canonical field element");
+    // tables above 2^persist_min_vars() entries use the grid-wide kernel (persist.cuh), smaller ones a single CTA
+    const bool grid_wide = m >= persist_min_vars() && c->coop != 0;
+    if (!grid_wide && m > 24) {
+        set_error("the single-CTA tail takes at most 24 variables");
+        return SCB_ETAIL;  // caller falls back to one launch per round
+    }
+    const bool exchanging = g_cur_peers && g_cur_peers->world > 1;
+    ARG_TRY(grid_wide || !exchanging, "sharded rounds need the grid-wide resident kernel");
+    const size_t esz = f.policy == POL_SP ? 4 : (size_t)8 * N;  // internal ping-pong buffers (packed for small primes)
     std::vector<BufRef> ba(p->t.size()), bb(p->t.size());
     for (size_t k = 0; k < p->t.size(); ++k) {
-        RC_TRY(alloc_buf((size_t)8 * N << (m - 1), &ba[k]));
-        RC_TRY(alloc_buf((size_t)8 * N << (m - 1), &bb[k]));
+        RC_TRY(alloc_buf(std::max<size_t>(esz << (m - 1), 32), &ba[k]));
+        RC_TRY(alloc_buf(std::max<size_t>(esz << (m >= 3 ? m - 2 : 1), 32), &bb[k]));
     }
     TailMailbox* mb = c->mailbox;
     std::memset((void*)mb, 0, sizeof(TailMailbox));
     std::atomic_thread_fence(std::memory_order_seq_cst);
     const ElemArg ra = elem_arg(f, r_first);
-    const uint64_t timeout_ns = 250ull * 1000 * 1000;  // normal host turn-around is microseconds
-    DISPATCH_POLICY(f.policy, DISPATCH_K(p->t.size(), {
-        TabsIn<K> in;
-        TabsOut<K> oa, ob;
-        for (int k = 0; k < K; ++k) {
-            in.p[k] = p->t[k].buf->ptr;
-            oa.p[k] = ba[k]->ptr;
-            ob.p[k] = bb[k]->ptr;
+    uint64_t timeout_ns = 250ull * 1000 * 1000;  // normal host turn-around is microseconds
+    const int in_w32 = p->t[0].p32 ? 1 : 0;
+    if (grid_wide) {
+        CU_TRY(cudaMemsetAsync(c->persist_ctl, 0, sizeof(PersistCtl), g_stream));
+        cudaError_t le = cudaSuccess;
+        DISPATCH_POLICY(f.policy, DISPATCH_K(p->t.size(), {
+            TabsIn<K> in;
+            TabsOut<K> oa, ob;
+            for (int k = 0; k < K; ++k) {
+                in.p[k] = p->t[k].buf->ptr;
+                oa.p[k] = ba[k]->ptr;
+                ob.p[k] = bb[k]->ptr;
+            }
+            auto kern = k_persist_rounds<A, K>;
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, 0) != cudaSuccess || nb < 1) nb = 1;
+            if (nb > persist_blocks<A, K>()) nb = persist_blocks<A, K>();
+            int grid = c->sms * nb;
+            if (grid > kMaxGrid) grid = kMaxGrid;
+            FieldDesc fd = f.d;
+            ElemArg rr = ra;
+            uint32_t mm = m, nr = n_rounds;
+            int w32 = in_w32;
+            PersistCtl* ctl = c->persist_ctl;
+            uint64_t* parts = c->partials;
+            PeerArg pa = peer_arg(c);  // exchange numbers pa.seq .. pa.seq + n_rounds - 1, one per round
+            if (exchanging) g_cur_peers->seq += n_rounds - 1;
+            void* args[] = {&fd, &in, &oa, &ob, &rr, &mm, &nr, &w32, &mb, &ctl, &parts, &timeout_ns, &pa};
+            le = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), args, 0, g_stream);
+        }));
+        if (le != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cooperative launch failed: %s", cudaGetErrorString(le));
+            return SCB_ECUDA;
         }
-        k_tail_rounds<A, K><<<1, tail_threads<A>(), 0, g_stream>>>(f.d, in, oa, ob, ra, m, n_rounds, mb, timeout_ns, p->t[0].p32 ? 1 : 0);
-    }));
+    } else {
+        DISPATCH_POLICY(f.policy, DISPATCH_K(p->t.size(), {
+            TabsIn<K> in;
+            TabsOut<K> oa, ob;
+            for (int k = 0; k < K; ++k) {
+                in.p[k] = p->t[k].buf->ptr;
+                oa.p[k] = ba[k]->ptr;
+                ob.p[k] = bb[k]->ptr;
+            }
+            k_tail_rounds<A, K><<<1, tail_threads<A>(), 0, g_stream>>>(f.d, in, oa, ob, ra, m, n_rounds, mb, timeout_ns, in_w32);
+        }));
+    }
     LAUNCH_CHECK();
     int rc = SCB_OK;
     uint64_t evals[kMaxPts * kMaxLimbs], next_r[kMaxLimbs];
+    // mailbox words are self-validating: (tag << 32) | 32-bit payload, one word per limb for the small-prime policy
+    // (values < 2^32), two otherwise (tail.cuh)
+    const uint32_t H = f.policy == POL_SP ? 1 : 2, n_words = n_points * N;
     for (uint32_t t = 0; t < n_rounds && rc == SCB_OK; ++t) {
+        const uint64_t tag = (uint64_t)t + 1;
         uint64_t spins = 0;
-        while (mb->seq_dev < (uint64_t)t + 1) {
+        for (;;) {
+            bool ready = true;
+            for (uint32_t i = 0; i < n_words * H; ++i) {
+                if ((mb->evals[i] >> 32) != tag) {
+                    ready = false;
+                    break;
+                }
+            }
+            if (ready) break;
             if (mb->dev_status == 2) {
-                set_error("the resident tail kernel lost lock-step with the host (serialising profiler?)");
+                set_error("the resident kernel lost lock-step with the host (serialising profiler?)");
                 rc = SCB_ETAIL;
                 break;
             }
             if ((++spins & 0xFFFFF) == 0) {  // every ~1M polls make sure the kernel is still alive
                 cudaError_t q = cudaStreamQuery(g_stream);
-                if (q != cudaErrorNotReady && mb->seq_dev < (uint64_t)t + 1) {
-                    set_error("tail kernel ended early: %s", cudaGetErrorString(q));
-                    rc = SCB_ECUDA;
+                if (q != cudaErrorNotReady) {
+                    set_error("resident kernel ended early: %s", cudaGetErrorString(q));
+                    rc = q == cudaSuccess ? SCB_ETAIL : SCB_ECUDA;
                     break;
                 }
             }
         }
         if (rc != SCB_OK) break;
-        std::atomic_thread_fence(std::memory_order_acquire);
-        for (uint32_t i = 0; i < n_points * N; ++i) evals[i] = mb->evals[i];
+        for (uint32_t i = 0; i < n_words; ++i) {
+            if (H == 1) evals[i] = (uint32_t)mb->evals[i];
+            else evals[i] = (uint64_t)(uint32_t)mb->evals[2 * i] | (mb->evals[2 * i + 1] << 32);
+        }
         rc = cb(user, t, evals, next_r);
         if (rc != SCB_OK) break;
         *rounds_done = t + 1;
@@ -1208,19 +1308,48 @@ extern "C" int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, 
                 rc = SCB_EINVAL;
                 break;
             }
-            for (uint32_t i = 0; i < N; ++i) mb->challenge[i] = next_r[i];
-            std::atomic_thread_fence(std::memory_order_release);
-            mb->seq_host = (uint64_t)t + 1;
+            for (uint32_t i = 0; i < N; ++i) {
+                if (H == 1) {
+                    mb->challenge[i] = (tag << 32) | (uint32_t)next_r[i];
+                } else {
+                    mb->challenge[2 * i] = (tag << 32) | (uint32_t)next_r[i];
+                    mb->challenge[2 * i + 1] = (tag << 32) | (next_r[i] >> 32);
+                }
+            }
         }
     }
     if (rc != SCB_OK) {
-        mb->abort_flag = 1;
+        mb->challenge[0] = (uint64_t)kMbAbortTag << 32;
         std::atomic_thread_fence(std::memory_order_seq_cst);
     }
     cudaError_t e = cudaStreamSynchronize(g_stream);
+    static const bool trace = getenv("SCB_PERSIST_TRACE") && atoi(getenv("SCB_PERSIST_TRACE")) != 0;
+    if (trace && grid_wide && rc == SCB_OK) {  // per-round device time (sums posted) and host turn-around, in microseconds
+        fprintf(stderr, "[persist m=%u]", m);
+        for (uint32_t t = 0; t < n_rounds; ++t) {
+            const double work = (double)(mb->stamp[2 * t] - (t == 0 ? mb->stamp[2 * kTailMaxRounds + 1] : mb->stamp[2 * t - 1])) * 1e-3;
+            const double turn = t + 1 < n_rounds ? (double)(mb->stamp[2 * t + 1] - mb->stamp[2 * t]) * 1e-3 : 0.0;
+            fprintf(stderr, " %.1f/%.1f", work, turn);
+        }
+        fprintf(stderr, "\n");
+    }
     if (e != cudaSuccess && rc == SCB_OK) {
         set_error("tail kernel failed: %s", cudaGetErrorString(e));
         rc = SCB_ECUDA;
+    }
+    if (rc == SCB_OK && exchanging) rc = peers_check(c);
+    if (rc == SCB_OK && out_folded) {  // the tables after n_rounds folds: what the last round wrote
+        auto q = std::make_unique<scb_poly>(*p);
+        const bool in_b = ((n_rounds - 1) & 1) != 0;
+        for (size_t k = 0; k < p->t.size(); ++k) {
+            Table tk;
+            tk.nv = m - n_rounds;
+            tk.buf = in_b ? bb[k] : ba[k];
+            tk.p32 = f.policy == POL_SP;
+            if (tk.p32 && !p->allow_packed) RC_TRY(unpack_table(c, f, tk, &q->t[k]));
+            else q->t[k] = tk;
+        }
+        *out_folded = q.release();
     }
     return rc;
 }

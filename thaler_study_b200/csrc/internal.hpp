@@ -10,6 +10,8 @@
 #include "fielddesc.hpp"
 #include "host/hostfield.hpp"
 
+struct scb_poly;
+
 namespace scb {
 
 struct FieldImpl {
@@ -19,6 +21,11 @@ struct FieldImpl {
 };
 
 void set_error(const char* fmt, ...);
+
+// engine.cu: should all remaining rounds of this product polynomial run in a resident kernel (tail.cuh for small
+// tables, persist.cuh for large ones)?  Decided per field policy and table size.  need_grid: only if the grid-wide
+// kernel would be used (the one that can exchange partial sums with peer GPUs every round).
+bool resident_rounds_ok(const struct ::scb_poly* p, bool need_grid);
 
 }  // namespace scb
 

@@ -346,11 +346,8 @@ extern "C" int scb_verifier_round(scb_verifier* v, const uint64_t* degrees, cons
 }
 
 // ------------------------------------------------------------------------------------------ fiat-shamir
-// Tables of at most 2^tail_max_vars() entries are finished by the persistent tail kernel (0 disables it).
-static uint32_t tail_max_vars() {
-    static const uint32_t v = getenv("SCB_TAIL_VARS") ? (uint32_t)atoi(getenv("SCB_TAIL_VARS")) : 14;
-    return v > 24 ? 24 : v;
-}
+// Small tables are finished by the single-CTA tail kernel, large ones by the grid-wide resident kernel; the engine
+// decides (resident_rounds_ok, engine.cu).
 struct TailCtx {
     const HostField* F;
     uint32_t kind;
@@ -393,31 +390,44 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
     offsets[0] = 0;
     offsets[1] = hash_input.size();
     const bool product = p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G;
-    const uint32_t tail_vars = tail_max_vars();
     uint32_t j = 1;
     while (j < p->num_vars) {
         Fe r_j = chain.challenge();  // == hash_to_field(hash_input)
         RC_TRY(maybe_consolidate(p));
         uint32_t live = 0;  // variables of the table about to be folded
         RC_TRY(scb_poly_num_vars(p->g, &live));
-        if (product && !p->sharded && !g_tail_disabled && tail_vars >= 2 && live <= tail_vars && live >= 2) {
-            // latency-bound tail: all remaining rounds in one resident kernel, challenges through a mailbox
+        if (product && !g_tail_disabled && live >= 2 && resident_rounds_ok(p->g, p->sharded)) {
+            // all remaining rounds (sharded: all rounds up to the consolidation point, with the per-round exchange
+            // inside the kernel) in one resident kernel, challenges through a mailbox
             TailCtx tc{&F, p->kind, &hash_input, &chain, offsets, j, p->np, {}};
             uint64_t rw[kHostMaxLimbs];
             F.store(r_j, rw);
             tc.used.insert(tc.used.end(), rw, rw + F.n);
+            const bool was_sharded = p->sharded;
+            const uint32_t max_rounds = was_sharded ? live - p->consolidate_at : 0;
             uint32_t done = 0;
-            int rc = scb_poly_tail_rounds(p->g, rw, p->np, tail_round_cb, &tc, &done);
-            if (rc == SCB_OK) break;
+            scb_poly* folded = nullptr;
+            int rc;
+            {
+                PeersScope scope(was_sharded ? p->peers : nullptr);
+                rc = scb_poly_resident_rounds(p->g, rw, p->np, max_rounds, tail_round_cb, &tc, &done, was_sharded ? &folded : nullptr);
+            }
+            if (rc == SCB_OK) {
+                if (!was_sharded) break;
+                scb_poly_free(p->g);  // carry on from the slab the kernel left behind: consolidation comes next
+                p->g = folded;
+                j += done;
+                continue;
+            }
             if (rc != SCB_ETAIL) return rc;
             // lock-step lost (e.g. a profiler serialises kernel and host): keep what was done, fold the tables by the
             // challenges already consumed and carry on with one launch per round
             g_tail_disabled = true;
             if (done > 0) {
-                scb_poly* folded = nullptr;
-                RC_TRY(scb_poly_fix_variables(p->g, tc.used.data(), done, &folded));
+                scb_poly* refolded = nullptr;
+                RC_TRY(scb_poly_fix_variables(p->g, tc.used.data(), done, &refolded));
                 scb_poly_free(p->g);
-                p->g = folded;
+                p->g = refolded;
                 j += done;
             }
             continue;

@@ -6,7 +6,7 @@
 // instead ONE kernel stays resident for all remaining rounds and talks to the host through a mailbox in
 // mapped pinned memory: it posts the (d+1) round sums, the host derives the challenge with the unchanged
 // transcript code (interpolation, serialization, SHA-256 -- the part that decides transcript bytes) and
-// posts it back.  No kernel launches, no stream synchronisation, two PCIe posted writes per round.
+// posts it back.  No kernel launches, no stream synchronisation, no fences: self-validating tagged words.
 //
 // Same arithmetic as k_fold_round (kernels.cuh); buffers written inside this kernel are read back with
 // ld.global.cg (never through the non-coherent path).
@@ -19,15 +19,77 @@ namespace scb {
 
 constexpr uint32_t kTailMaxRounds = 32;
 
-// Mapped pinned host memory.  seq_dev / seq_host count completed posts (monotone within one kernel).
+// Mapped pinned host memory.  Every 8-byte word validates itself: it carries a 32-bit payload (one half of a limb,
+// or a whole limb for the small-prime policy) under a 32-bit tag, so neither side needs a fence or a second
+// "ready" word -- posted PCIe writes may land in any order and the reader just waits until every word it needs
+// shows the expected tag.  One PCIe posted write per word on the way out, one read round trip per poll on the way in.
+constexpr uint32_t kMbAbortTag = 0xFFFFFFFFu;
 struct TailMailbox {
-    volatile uint64_t seq_dev;                    // device -> host: round sums of round `seq_dev` are valid
-    uint64_t evals[kMaxPts * kMaxLimbs];
-    volatile uint64_t seq_host;                   // host -> device: challenge number `seq_host` is valid
-    uint64_t challenge[kMaxLimbs];
-    volatile uint64_t abort_flag;                 // host -> device: give up (error on the host side)
-    volatile uint64_t dev_status;                 // device -> host: 0 running, 1 done, 2 timed out
+    volatile uint64_t evals[2 * kMaxPts * kMaxLimbs];  // device -> host, tag = round + 1
+    volatile uint64_t challenge[2 * kMaxLimbs];        // host -> device, tag = challenge number (>= 1) or kMbAbortTag
+    volatile uint64_t dev_status;                      // device -> host: 0 running, 1 done, 2 timed out
+    // %globaltimer stamps written by the grid-wide kernel: [2t] round t's sums posted, [2t+1] challenge t+1 received
+    uint64_t stamp[2 * (kTailMaxRounds + 1)];
 };
+template <class A>
+struct MailboxHalves {  // tagged words per limb
+    static constexpr int value = A::kLight ? 1 : 2;
+};
+
+template <class A, int NP>
+__device__ __forceinline__ void mailbox_post(TailMailbox* mb, uint32_t tag, const uint64_t (&w)[NP][A::N]) {
+    constexpr int H = MailboxHalves<A>::value, N = A::N;
+    const uint64_t hi = (uint64_t)tag << 32;
+#pragma unroll
+    for (int x = 0; x < NP; ++x)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            st_sys(&mb->evals[(x * N + i) * H], hi | (uint32_t)w[x][i]);
+            if constexpr (H == 2) st_sys(&mb->evals[(x * N + i) * H + 1], hi | (w[x][i] >> 32));
+        }
+}
+// Waits until every tagged word of a challenge shows `tag`; 0 = ok (r filled), 1 = abort tag seen or timeout.
+// SYS: the words live in mapped host memory (one PCIe read round trip per poll), else in device memory.
+template <class A, bool SYS>
+__device__ __forceinline__ int tagged_wait(const volatile uint64_t* words, uint32_t tag, uint64_t timeout_ns, uint64_t* r) {
+    constexpr int H = MailboxHalves<A>::value, N = A::N, W = N * H;
+    const uint64_t t0 = globaltimer_ns();
+    for (;;) {
+        uint64_t c[W];
+        if constexpr (W == 1) {
+            if constexpr (SYS) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(c[0]) : "l"(words) : "memory");
+            else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(c[0]) : "l"(words) : "memory");
+        } else {
+#pragma unroll
+            for (int i = 0; i < W; i += 2) {
+                if constexpr (SYS)
+                    asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(c[i]), "=l"(c[i + 1]) : "l"(words + i) : "memory");
+                else
+                    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(c[i]), "=l"(c[i + 1]) : "l"(words + i) : "memory");
+            }
+        }
+        bool ok = true, ab = false;
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            const uint32_t tg = (uint32_t)(c[i] >> 32);
+            ok = ok && tg == tag;
+            ab = ab || tg == kMbAbortTag;
+        }
+        if (ok) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                if constexpr (H == 1) r[i] = (uint32_t)c[i];
+                else r[i] = (uint64_t)(uint32_t)c[2 * i] | (c[2 * i + 1] << 32);
+            }
+            return 0;
+        }
+        if (ab || globaltimer_ns() - t0 > timeout_ns) return 1;
+    }
+}
+template <class A>
+__device__ __forceinline__ int mailbox_wait_challenge(TailMailbox* mb, uint32_t tag, uint64_t timeout_ns, uint64_t* r) {
+    return tagged_wait<A, true>(mb->challenge, tag, timeout_ns, r);
+}
 
 template <int W>
 __device__ __forceinline__ void ld_words_cg(const uint64_t* ptr, uint64_t* w) {
@@ -111,22 +173,7 @@ __global__ void __launch_bounds__(tail_threads<A>(), 1)
     __syncthreads();
     for (uint32_t t = 0; t < n_rounds; ++t) {
         if (t > 0) {
-            if (threadIdx.x == 0) {  // wait for the host's challenge number t
-                const uint64_t t0 = globaltimer_ns();
-                int bad = 0;
-                while (ld_sys(&mb->seq_host) < t) {
-                    if (ld_sys(&mb->abort_flag) != 0 || globaltimer_ns() - t0 > timeout_ns) {
-                        bad = 1;
-                        break;
-                    }
-                }
-                __threadfence_system();
-                if (!bad) {
-#pragma unroll
-                    for (int i = 0; i < N; ++i) r_sm[i] = ld_sys(&mb->challenge[i]);
-                }
-                abort_sm = bad;
-            }
+            if (threadIdx.x == 0) abort_sm = mailbox_wait_challenge<A>(mb, t, timeout_ns, r_sm);  // the host's challenge number t
             __syncthreads();
             if (abort_sm) {
                 if (threadIdx.x == 0) st_sys(&mb->dev_status, 2);
@@ -154,15 +201,10 @@ __global__ void __launch_bounds__(tail_threads<A>(), 1)
         }
         block_reduce<A, NP>(ar, acc, sm);
         if (threadIdx.x == 0) {
+            uint64_t w[NP][N];
 #pragma unroll
-            for (int x = 0; x < NP; ++x) {
-                uint64_t w[N];
-                ar.to_words(ar.msg_final(acc[x], K), w);
-#pragma unroll
-                for (int i = 0; i < N; ++i) st_sys(&mb->evals[x * N + i], w[i]);
-            }
-            __threadfence_system();
-            st_sys(&mb->seq_dev, (uint64_t)t + 1);
+            for (int x = 0; x < NP; ++x) ar.to_words(ar.msg_final(acc[x], K), w[x]);
+            mailbox_post<A, NP>(mb, t + 1, w);
         }
         __syncthreads();  // folded tables written by all threads are visible to the next round
         m -= 1;
