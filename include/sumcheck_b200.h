@@ -172,6 +172,27 @@ int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, uint32_t n_
 int scb_poly_resident_rounds(const scb_poly* p, const uint64_t* r_first, uint32_t n_points, uint32_t max_rounds, scb_round_cb cb,
                              void* user, uint32_t* rounds_done, scb_poly** out_folded);
 
+/* Two rounds per pass over the tables (small-prime fields, product polynomials; csrc/pairs.cuh).
+ * H[a][b] = sum over x'' of prod_k f_k(a, b, x'') for a, b in {0..K} is a bivariate polynomial whose slices are two
+ * consecutive round messages: Prover::round j sends g_j(X) = H(X,0) + H(X,1) and round j+1 sends g_{j+1}(Y) = H(r_j, Y)
+ * (sum-check-protocol/src/lib.rs:105-112 applied twice), so one pass yields both and the next pass folds two
+ * variables at once.  grid_evals: the (K+1)^2 sums, a-major, of the polynomial as it is.  pair_pass: fold the two
+ * lowest variables by (ra, rb), then the grid of the folded polynomial (needs >= 4 variables).  resident_pairs: every
+ * pair pass of a proof in one cooperative kernel; the callback gets the grid ((K+1)^2 values) or, when a single
+ * variable is left, the line ((K+1) values) and returns the next challenge pair. */
+typedef int (*scb_pair_cb)(void* user, uint32_t pass, uint32_t n_vals, const uint64_t* vals, uint64_t* next_pair_out);
+int scb_poly_grid_evals(const scb_poly* p, uint64_t* out_elems);
+int scb_poly_pair_pass(const scb_poly* p, const uint64_t* ra, const uint64_t* rb, scb_poly** out, uint64_t* out_elems);
+int scb_poly_resident_pairs(const scb_poly* p, const uint64_t* ra, const uint64_t* rb, scb_pair_cb cb, void* user,
+                            uint32_t* passes_done);
+
+/* Measurement hooks for the resident kernels (bench.py's roofline): launches and summed CUDA-event kernel time since
+ * the last reset, and for the last grid-wide launch the per-round device time up to "sums posted" and the host
+ * turn-around (posted -> next challenge seen by the kernel), microseconds, from %globaltimer stamps. */
+int scb_resident_stats(uint64_t* launches, double* total_kernel_ms, uint32_t* last_rounds, double* last_work_us,
+                       double* last_turn_us, uint32_t cap);
+void scb_resident_stats_reset(void);
+
 /* ------------------------------------------------------------------ round-message algebra (host) */
 /* (d+1) sums at X = 0..d  ->  the SparsePolynomial the reference would send, per implementor:
  * MATMUL_G: interpolate_quadratic_poly (matrix-multiplication/src/lib.rs:17-60, explicit zero terms kept);

@@ -1,0 +1,110 @@
+"""Two sum-check rounds per pass over the tables (csrc/pairs.cuh, small-prime fields): the (K+1)^2 grid sums against the
+Python oracle's definition, the two-variable fold against two oracle folds, and the transcripts of the resident pair
+kernel byte for byte against one launch per round and against the oracle."""
+import os
+import random
+import subprocess
+import sys
+
+import pytest
+
+from oracle import pyoracle as O
+
+pytestmark = pytest.mark.gpu
+
+T = pytest.importorskip("thaler_study_b200")
+
+SP_FIELDS = [O.FP5, O.FP389, O.FP1572869, O.Field(268435399)]  # the reference's moduli + the largest prime below 2^28
+
+
+def fid(f):
+    return f"p{f.p}"
+
+
+def oracle_grid(OF, tabs, K):
+    p, NP = OF.p, K + 1
+    n = len(tabs[0])
+    H = [[0] * NP for _ in range(NP)]
+    for g in range(n // 4):
+        for a in range(NP):
+            for b in range(NP):
+                pr = 1
+                for k in range(K):
+                    c = tabs[k][4 * g:4 * g + 4]
+                    v0 = (c[0] + a * (c[1] - c[0])) % p
+                    v1 = (c[2] + a * (c[3] - c[2])) % p
+                    pr = pr * ((v0 + b * (v1 - v0)) % p) % p
+                H[a][b] = (H[a][b] + pr) % p
+    return H
+
+
+@pytest.mark.parametrize("OF", SP_FIELDS, ids=fid)
+@pytest.mark.parametrize("K", [1, 2, 3, 4])
+def test_grid_evals_and_pair_pass_vs_oracle(OF, K):
+    F = T.Field(OF.p)
+    rnd = random.Random(1000 * K + OF.p % 997)
+    for v in (2, 3, 4, 5, 8, 11):
+        tabs = [[rnd.randrange(OF.p) for _ in range(1 << v)] for _ in range(K)]
+        g = T.ProductMLE.new([T.DenseMultilinearExtension.from_evaluations_vec(F, v, t) for t in tabs])
+        assert g.grid_evals() == oracle_grid(OF, tabs, K), (v, K)
+        if v >= 4:
+            ra, rb = rnd.randrange(OF.p), rnd.randrange(OF.p)
+            folded = [O.DenseMLE(OF, v, t).fix_variables([ra, rb]).evals for t in tabs]
+            g2, H2 = g.pair_pass(ra, rb)
+            assert g2.num_vars() == v - 2
+            assert H2 == oracle_grid(OF, folded, K), (v, K)
+            for k in range(K):
+                assert g2.table(k).to_evaluations() == folded[k]
+            if v >= 6:  # packed input this time
+                rc, rd = rnd.randrange(OF.p), rnd.randrange(OF.p)
+                folded2 = [O.DenseMLE(OF, v - 2, t).fix_variables([rc, rd]).evals for t in folded]
+                g3, H3 = g2.pair_pass(rc, rd)
+                assert H3 == oracle_grid(OF, folded2, K)
+                assert g3.grid_evals() == H3
+                assert [g3.table(k).to_evaluations() for k in range(K)] == folded2
+
+
+@pytest.mark.parametrize("OF", SP_FIELDS[:3], ids=fid)
+@pytest.mark.parametrize("kind", ["product1", "product2", "product3", "product4", "matmul"])
+def test_pair_transcripts_vs_oracle(OF, kind):
+    """generate_transcript routes small-prime product polynomials through the pair kernel: bytes == oracle, every v."""
+    F = T.Field(OF.p)
+    rnd = random.Random(5)
+    for v in (2, 3, 4, 5, 6, 7, 10):
+        if kind == "matmul":
+            a = [rnd.randrange(OF.p) for _ in range(1 << v)]
+            b = [rnd.randrange(OF.p) for _ in range(1 << v)]
+            og = O.MatMulG(OF, O.DenseMLE(OF, v, a), O.DenseMLE(OF, v, b))
+            dg = T.MatMulG.from_tables(T.DenseMultilinearExtension.from_evaluations_vec(F, v, a), T.DenseMultilinearExtension.from_evaluations_vec(F, v, b))
+        else:
+            K = int(kind[-1])
+            vals = [[rnd.randrange(OF.p) for _ in range(1 << v)] for _ in range(K)]
+            og = O.ProductMLE(OF, [O.DenseMLE(OF, v, t) for t in vals])
+            dg = T.ProductMLE.new([T.DenseMultilinearExtension.from_evaluations_vec(F, v, t) for t in vals])
+        want = O.generate_transcript(OF, O.Prover(og))
+        got = T.generate_transcript(T.Prover(dg))
+        assert got == want, (kind, v)
+        assert T.verify_transcript(got, T.Verifier(v, dg))
+
+
+def test_pair_kernel_matches_one_round_per_pass():
+    """SCB_PAIRS=0 (one round per pass) and the default must print identical transcripts at sizes where the grid-wide
+    barrier, the packed layouts and the solo endgame all take part."""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import thaler_study_b200 as T\n"
+        "for p, v, K in ((1572869, 20, 3), (1572869, 19, 3), (1572869, 17, 4), (1572869, 16, 2), (389, 15, 1), (5, 14, 3), (268435399, 18, 3)):\n"
+        "    F = T.Field(p)\n"
+        "    g = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, 70 + k) for k in range(K)])\n"
+        "    print(b''.join(T.generate_transcript(T.Prover(g))).hex())\n"
+        "    a = T.DenseMultilinearExtension.synthetic(F, v, 7); b = T.DenseMultilinearExtension.synthetic(F, v, 8)\n"
+        "    print(b''.join(T.generate_transcript(T.Prover(T.MatMulG.from_tables(a, b)))).hex())\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    outs = []
+    for env_add in ({"SCB_PAIRS": "0", "SCB_TAIL_VARS": "0"}, {"SCB_PAIRS": "0"}, {}, {"SCB_PAIR_BPS": "1"}):
+        env = dict(os.environ, **env_add)
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600))
+    for o in outs:
+        assert o.returncode == 0, o.stderr[-2000:]
+    assert len(outs[0].stdout.split()) == 14
+    assert len(set(o.stdout for o in outs)) == 1

@@ -19,6 +19,7 @@ u8p = C.POINTER(C.c_uint8)
 vp = C.c_void_p
 vpp = C.POINTER(C.c_void_p)
 # scb_round_cb: int (*)(void* user, uint32_t round, const uint64_t* evals, uint64_t* next_challenge_out)
+PAIR_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
 ROUND_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, u64p, u64p)
 
 # name -> (restype, argtypes); every symbol include/sumcheck_b200.h declares
@@ -74,6 +75,11 @@ SIGNATURES = {
     "scb_poly_fix_and_round_evals_device": (C.c_int, [vp, u64p, C.c_uint32, vpp, vp]),
     "scb_poly_allow_packed": (C.c_int, [vp, C.c_int]),
     "scb_poly_tail_rounds": (C.c_int, [vp, u64p, C.c_uint32, ROUND_CB, vp, u32p]),
+    "scb_poly_grid_evals": (C.c_int, [vp, u64p]),
+    "scb_poly_pair_pass": (C.c_int, [vp, u64p, u64p, C.POINTER(vp), u64p]),
+    "scb_poly_resident_pairs": (C.c_int, [vp, u64p, u64p, PAIR_CB, vp, u32p]),
+    "scb_resident_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_double), u32p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint32]),
+    "scb_resident_stats_reset": (None, []),
     "scb_poly_resident_rounds": (C.c_int, [vp, u64p, C.c_uint32, C.c_uint32, ROUND_CB, vp, u32p, C.POINTER(vp)]),
     "scb_evals_to_univariate": (C.c_int, [vp, C.c_uint32, u64p, C.c_uint32, u64p, u64p, C.c_uint32, u32p]),
     "scb_unipoly_serialize": (C.c_int, [vp, u64p, u64p, C.c_uint32, u8p, C.c_size_t, C.POINTER(C.c_size_t)]),

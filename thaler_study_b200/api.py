@@ -364,6 +364,24 @@ class SumCheckPolynomial:
         check(lib.scb_poly_fix_and_round_evals(self._h, _p64(self.F.elem(r)), npts, C.byref(h), _p64(out)))
         return self._wrap(h), self.F.from_mont(out[:npts])
 
+    # ---- two rounds per pass (small-prime fields, product polynomials; csrc/pairs.cuh)
+    def grid_evals(self) -> List[List[int]]:
+        """H[a][b] = sum over x'' of prod_k f_k(a, b, x'') for a, b in 0..K (canonical integers)."""
+        npts = self.n_points
+        out = np.zeros((npts * npts, self.F.n), dtype=np.uint64)
+        check(lib.scb_poly_grid_evals(self._h, _p64(out)))
+        flat = self.F.from_mont(out)
+        return [flat[a * npts:(a + 1) * npts] for a in range(npts)]
+
+    def pair_pass(self, ra: int, rb: int):
+        """Fold the two lowest variables by (ra, rb); returns (folded polynomial, its grid)."""
+        npts = self.n_points
+        out = np.zeros((npts * npts, self.F.n), dtype=np.uint64)
+        h = C.c_void_p()
+        check(lib.scb_poly_pair_pass(self._h, _p64(self.F.elem(ra)), _p64(self.F.elem(rb)), C.byref(h), _p64(out)))
+        flat = self.F.from_mont(out)
+        return self._wrap(h), [flat[a * npts:(a + 1) * npts] for a in range(npts)]
+
     def round_evals_device(self, d_out_ptr: int, n_points: Optional[int] = None) -> None:
         npts = self.n_points if n_points is None else n_points
         check(lib.scb_poly_round_evals_device(self._h, npts, C.c_void_p(d_out_ptr)))

@@ -54,9 +54,13 @@ struct PolSP {
     // every product (3 multiply-class instructions instead of 5) and repair the missing powers of 2^-32 where that
     // is free: in the fold the factor is folded into the per-kernel constant (fold_const), in the K-fold message
     // products it is a constant per output sum, applied once by the finishing thread (msg_final).
+    // Written as mad.wide.u32 (IMAD.WIDE with the 64-bit addend T): left to itself the compiler splits the sum into
+    // IMAD.HI + carry fix-ups, and IMAD.HI issues at half the rate of IMAD.WIDE on sm_100 (profiles/r01_imad_peak.md).
     __device__ __forceinline__ uint32_t redc32(uint64_t T) const {
-        uint32_t m = (uint32_t)T * ninv;
-        return (uint32_t)((T + (uint64_t)m * p) >> 32);
+        const uint32_t m = (uint32_t)T * ninv;
+        uint64_t s;
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(s) : "r"(m), "r"(p), "l"(T));
+        return (uint32_t)(s >> 32);
     }
     using FoldC = uint32_t;
     __device__ __forceinline__ FoldC fold_const(El r) const { return reduce_once(redc32(r)); }  // r * 2^-32

@@ -26,6 +26,8 @@ void set_error(const char* fmt, ...);
 // tables, persist.cuh for large ones)?  Decided per field policy and table size.  need_grid: only if the grid-wide
 // kernel would be used (the one that can exchange partial sums with peer GPUs every round).
 bool resident_rounds_ok(const struct ::scb_poly* p, bool need_grid);
+// engine.cu: can this polynomial's proof run two rounds per pass over the tables (pairs.cuh)?
+bool pair_passes_ok(const struct ::scb_poly* p);
 
 }  // namespace scb
 

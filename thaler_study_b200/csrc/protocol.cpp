@@ -144,6 +144,10 @@ struct scb_prover {
     uint32_t kind = 0, np = 0;
     bool have_round0 = false;   // round-0 sums computed by Prover::new (they also yield c_1)
     std::vector<Fe> round0;
+    // small-prime fields: Prover::new's pass accumulates the (K+1)^2 grid H[a][b] (pairs.cuh) instead of the K+1
+    // line sums; it yields c_1, g_1 and -- once r_1 is known -- g_2 without another pass over the tables
+    bool have_grid = false;
+    std::vector<Fe> grid;       // a-major
     // sharded prover (multi-GPU): g is this rank's slab while `sharded`; afterwards the consolidated table
     scb_peers* peers = nullptr;
     uint32_t consolidate_at = 0;
@@ -195,7 +199,19 @@ static int prover_new_impl(const scb_poly* g, scb_peers* peers, uint32_t world, 
         RC_TRY(maybe_consolidate(p.get()));
     }
     const HostField& F = p->fi->h;
-    if (p->num_vars >= 1) {
+    if (!p->sharded && p->num_vars >= 2 && pair_passes_ok(p->g)) {
+        // g_1(X) = H(X,0) + H(X,1) and c_1 = g_1(0) + g_1(1), from the grid pass
+        uint64_t w[32];
+        RC_TRY(scb_poly_grid_evals(p->g, w));
+        const uint32_t np = p->np;
+        p->grid.resize((size_t)np * np);
+        for (uint32_t i = 0; i < np * np; ++i) F.load(w + i, p->grid[i]);
+        p->have_grid = true;
+        p->round0.resize(np);
+        for (uint32_t x = 0; x < np; ++x) p->round0[x] = F.add(p->grid[x * np], p->grid[x * np + 1]);
+        p->have_round0 = true;
+        p->c_1 = F.add(p->round0[0], p->round0[1]);
+    } else if (p->num_vars >= 1) {
         // sum over the hypercube = g_1(0) + g_1(1): the round-0 message pass also yields c_1, so the
         // tables are streamed once here and not again by round(_, 0)  (same field elements either way)
         uint64_t w[8 * kHostMaxLimbs];
@@ -374,6 +390,71 @@ static int tail_round_cb(void* user, uint32_t t, const uint64_t* evals, uint64_t
     return SCB_OK;
 }
 
+// Two rounds per pass (pairs.cuh): host half.  From a grid H (a-major, (K+1)^2 values) the next two messages are
+// g(X) = H(X,0) + H(X,1) and, with r = hash(transcript so far), g'(Y) = H(r, Y): column Y of the grid interpolated
+// in `a` on the nodes 0..K and evaluated at r -- exact field arithmetic, hence the reference's field elements.
+struct PairCtx {
+    const HostField* F;
+    uint32_t kind, np;
+    std::vector<uint8_t>* hash_input;
+    FsChain* chain;
+    uint64_t* offsets;
+    uint32_t msgs;                // messages emitted so far (g_1 .. g_msgs)
+    std::vector<uint64_t> used;   // challenges derived so far, in order (one limb each)
+
+    void emit(const std::vector<Fe>& ev) {
+        const size_t before = hash_input->size();
+        evals_to_poly(*F, kind, ev).serialize(*F, *hash_input);
+        chain->absorb(hash_input->data() + before, hash_input->size() - before);
+        offsets[++msgs] = hash_input->size();
+    }
+    Fe next_challenge() {
+        Fe r = chain->challenge();
+        uint64_t w[kHostMaxLimbs];
+        F->store(r, w);
+        used.push_back(w[0]);
+        return r;
+    }
+    void emit_first(const std::vector<Fe>& H) {
+        std::vector<Fe> ev(np);
+        for (uint32_t x = 0; x < np; ++x) ev[x] = F->add(H[x * np], H[x * np + 1]);
+        emit(ev);
+    }
+    void emit_second(const std::vector<Fe>& H, const Fe& r) {
+        const InterpConsts& c = interp_consts(*F);
+        std::vector<Fe> ev(np), col(np);
+        for (uint32_t y = 0; y < np; ++y) {
+            for (uint32_t a = 0; a < np; ++a) col[a] = H[a * np + y];
+            const std::vector<Fe> coef = (np < 10 && !c.basis[np].empty()) ? lagrange_to_coeffs_cached(*F, c, col) : lagrange_to_coeffs(*F, col);
+            Fe acc = F->zero();
+            for (size_t i = coef.size(); i-- > 0;) acc = F->add(F->mul(acc, r), coef[i]);
+            ev[y] = acc;
+        }
+        emit(ev);
+    }
+};
+static int pair_pass_cb(void* user, uint32_t, uint32_t n_vals, const uint64_t* vals, uint64_t* next_pair) {
+    PairCtx* pc = (PairCtx*)user;
+    const HostField& F = *pc->F;
+    std::vector<Fe> v(n_vals);
+    for (uint32_t i = 0; i < n_vals; ++i) F.load(vals + i, v[i]);
+    next_pair[0] = next_pair[1] = 0;
+    if (n_vals == pc->np) {  // a single variable was left: its line sums are the last message
+        pc->emit(v);
+        return SCB_OK;
+    }
+    pc->emit_first(v);
+    const Fe ra = pc->next_challenge();
+    pc->emit_second(v, ra);
+    const Fe rb = pc->next_challenge();
+    uint64_t w[kHostMaxLimbs];
+    F.store(ra, w);
+    next_pair[0] = w[0];
+    F.store(rb, w);
+    next_pair[1] = w[0];
+    return SCB_OK;
+}
+
 extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t cap, size_t* out_len, uint64_t* offsets) {
     // fiat-shamir/src/lib.rs:75-98 with InteractiveProver for Prover (:44-66)
     ARG_TRY(p && out && out_len && offsets, "null argument");
@@ -391,6 +472,30 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
     offsets[1] = hash_input.size();
     const bool product = p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G;
     uint32_t j = 1;
+    if (p->have_grid && !p->sharded && !g_tail_disabled && p->num_vars >= 2 && pair_passes_ok(p->g)) {
+        // two rounds per pass: g_2 comes from Prover::new's grid, then every pass of the resident kernel folds two
+        // variables and returns the grid for the next two messages
+        PairCtx pc{&F, p->kind, p->np, &hash_input, &chain, offsets, 1, {}};
+        const Fe r1 = pc.next_challenge();
+        pc.emit_second(p->grid, r1);
+        int rc = SCB_OK;
+        if (p->num_vars > 2) {
+            pc.next_challenge();
+            uint32_t done = 0;
+            rc = scb_poly_resident_pairs(p->g, &pc.used[0], &pc.used[1], pair_pass_cb, &pc, &done);
+            if (rc != SCB_OK && rc != SCB_ETAIL) return rc;
+        }
+        j = pc.msgs;
+        if (rc == SCB_ETAIL) {
+            // lock-step lost (e.g. a profiler serialises kernel and host): keep the messages that are out, fold the
+            // tables by the challenges they were derived with and carry on with one launch per round
+            g_tail_disabled = true;
+            scb_poly* refolded = nullptr;
+            RC_TRY(scb_poly_fix_variables(p->g, pc.used.data(), j - 1, &refolded));
+            scb_poly_free(p->g);
+            p->g = refolded;
+        }
+    }
     while (j < p->num_vars) {
         Fe r_j = chain.challenge();  // == hash_to_field(hash_input)
         RC_TRY(maybe_consolidate(p));
