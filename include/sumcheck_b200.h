@@ -178,13 +178,15 @@ int scb_poly_resident_rounds(const scb_poly* p, const uint64_t* r_first, uint32_
  * (sum-check-protocol/src/lib.rs:105-112 applied twice), so one pass yields both and the next pass folds two
  * variables at once.  grid_evals: the (K+1)^2 sums, a-major, of the polynomial as it is.  pair_pass: fold the two
  * lowest variables by (ra, rb), then the grid of the folded polynomial (needs >= 4 variables).  resident_pairs: every
- * pair pass of a proof in one cooperative kernel; the callback gets the grid ((K+1)^2 values) or, when a single
- * variable is left, the line ((K+1) values) and returns the next challenge pair. */
+ * pair pass of a proof (at most max_passes, 0 = all) in one cooperative kernel; the callback gets the grid ((K+1)^2
+ * values) or, when a single variable is left, the line ((K+1) values) and returns the next challenge pair;
+ * *out_folded (optional) receives the polynomial the last pass left behind.  With a current peer group the grid
+ * kernels add the peer GPUs' sums (sharded prover). */
 typedef int (*scb_pair_cb)(void* user, uint32_t pass, uint32_t n_vals, const uint64_t* vals, uint64_t* next_pair_out);
 int scb_poly_grid_evals(const scb_poly* p, uint64_t* out_elems);
 int scb_poly_pair_pass(const scb_poly* p, const uint64_t* ra, const uint64_t* rb, scb_poly** out, uint64_t* out_elems);
-int scb_poly_resident_pairs(const scb_poly* p, const uint64_t* ra, const uint64_t* rb, scb_pair_cb cb, void* user,
-                            uint32_t* passes_done);
+int scb_poly_resident_pairs(const scb_poly* p, const uint64_t* ra, const uint64_t* rb, uint32_t max_passes, scb_pair_cb cb,
+                            void* user, uint32_t* passes_done, scb_poly** out_folded);
 
 /* Measurement hooks for the resident kernels (bench.py's roofline): launches and summed CUDA-event kernel time since
  * the last reset, and for the last grid-wide launch the per-round device time up to "sums posted" and the host

@@ -156,6 +156,18 @@ static int occ_grid(const Ctx* c, KernelT kernel, uint64_t items, size_t dyn_sme
     if (want < 1) want = 1;
     return (int)(want < cap ? want : cap);
 }
+// opt in to more than 48 KB of dynamic shared memory (once per kernel)
+template <class KernelT>
+static int allow_smem(KernelT kernel, size_t bytes) {
+    if (bytes <= 32 * 1024) return SCB_OK;  // static + dynamic must stay under 48 KB without the opt-in
+    static std::unordered_map<const void*, size_t> done;
+    std::lock_guard<std::mutex> lk(g_occ_mu);
+    auto it = done.find((const void*)kernel);
+    if (it != done.end() && it->second >= bytes) return SCB_OK;
+    CU_TRY(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    done[(const void*)kernel] = bytes;
+    return SCB_OK;
+}
 #define LAUNCH_CHECK()                                                                      \
     do {                                                                                    \
         g_launches.fetch_add(1, std::memory_order_relaxed);                                 \
@@ -1399,6 +1411,12 @@ extern "C" int scb_poly_resident_rounds(const scb_poly* p, const uint64_t* r_fir
 
 // ------------------------------------------------------------------------------------------ two rounds per pass
 // pairs.cuh: small-prime policy, product polynomials.  SCB_PAIRS=0 switches the scheme off.
+// SCB_PAIR_STAGE=1: the pair kernels prefetch the next iteration's tiles into shared memory with cp.async
+// (measured slower than plain 256-bit loads on B200 for these integer-bound passes, profiles/r01_pairs.md)
+static bool pair_staging() {
+    static const bool on = env_u32("SCB_PAIR_STAGE", 0) != 0;
+    return on;
+}
 bool scb::pair_passes_ok(const scb_poly* p) {
     static const bool on = env_u32("SCB_PAIRS", 1) != 0;
     if (!on || !p || !(p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) || p->t.empty()) return false;
@@ -1419,22 +1437,49 @@ extern "C" int scb_poly_grid_evals(const scb_poly* p, uint64_t* out_elems) {
     const uint64_t n_groups = p->t[0].len() / 4;
     const bool in32 = p->t[0].p32;
     const uint32_t NP = (uint32_t)p->t.size() + 1;
+    const PeerArg pa = peer_arg(c);  // sharded prover: the finishing thread adds the peer GPUs' grid sums
     DISPATCH_K(p->t.size(), {
         TabsIn<K> in;
         for (int k = 0; k < K; ++k) {
             ARG_TRY(p->t[k].p32 == in32, "tables of one polynomial must share a layout");
             in.p[k] = p->t[k].buf->ptr;
         }
-        if (in32) {
-            auto kern = k_grid_sp<K, true>;
-            kern<<<occ_grid(c, kern, n_groups), kThreads, 0, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res);
+        static const bool use_tma = env_u32("SCB_GRID_TMA", 0) != 0;
+        if (use_tma) {
+            if (in32) {
+                auto kern = k_grid_sp_tma<K, true>;
+                const size_t smem = tma_ring_bytes<K, 2>();
+                RC_TRY(allow_smem(kern, smem));
+                kern<<<c->sms * 2, kThreads + 32, smem, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
+            } else {
+                auto kern = k_grid_sp_tma<K, false>;
+                const size_t smem = tma_ring_bytes<K, 4>();
+                RC_TRY(allow_smem(kern, smem));
+                kern<<<c->sms * 2, kThreads + 32, smem, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
+            }
+        } else if (pair_staging()) {
+            if (in32) {
+                auto kern = k_grid_sp<K, true, true>;
+                const size_t smem = Stager<K, 2>::bytes(kThreads);
+                RC_TRY(allow_smem(kern, smem));
+                kern<<<occ_grid(c, kern, n_groups, smem), kThreads, smem, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
+            } else {
+                auto kern = k_grid_sp<K, false, true>;
+                const size_t smem = Stager<K, 4>::bytes(kThreads);
+                RC_TRY(allow_smem(kern, smem));
+                kern<<<occ_grid(c, kern, n_groups, smem), kThreads, smem, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
+            }
+        } else if (in32) {
+            auto kern = k_grid_sp<K, true, false>;
+            kern<<<occ_grid(c, kern, n_groups), kThreads, 0, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
         } else {
-            auto kern = k_grid_sp<K, false>;
-            kern<<<occ_grid(c, kern, n_groups), kThreads, 0, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res);
+            auto kern = k_grid_sp<K, false, false>;
+            kern<<<occ_grid(c, kern, n_groups), kThreads, 0, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
         }
     });
     LAUNCH_CHECK();
     CU_TRY(cudaStreamSynchronize(g_stream));
+    RC_TRY(peers_check(c));
     std::memcpy(out_elems, c->h_res, (size_t)8 * NP * NP);
     return SCB_OK;
 }
@@ -1468,11 +1513,16 @@ extern "C" int scb_poly_pair_pass(const scb_poly* p, const uint64_t* ra, const u
             in.p[k] = p->t[k].buf->ptr;
             o.p[k] = q->t[k].buf->ptr;
         }
-        if (in32) {
-            auto kern = k_pair_pass_sp<K, true>;
+        if (in32 && pair_staging()) {
+            auto kern = k_pair_pass_sp<K, true, true>;
+            const size_t smem = pair_stage_bytes<K>();
+            RC_TRY(allow_smem(kern, smem));
+            kern<<<occ_grid(c, kern, n_groups, smem), kThreads, smem, g_stream>>>(f.d, in, o, a, b, n_groups, c->partials, c->ticket, c->h_res);
+        } else if (in32) {
+            auto kern = k_pair_pass_sp<K, true, false>;
             kern<<<occ_grid(c, kern, n_groups), kThreads, 0, g_stream>>>(f.d, in, o, a, b, n_groups, c->partials, c->ticket, c->h_res);
         } else {
-            auto kern = k_pair_pass_sp<K, false>;
+            auto kern = k_pair_pass_sp<K, false, false>;
             kern<<<occ_grid(c, kern, n_groups), kThreads, 0, g_stream>>>(f.d, in, o, a, b, n_groups, c->partials, c->ticket, c->h_res);
         }
     });
@@ -1485,10 +1535,11 @@ extern "C" int scb_poly_pair_pass(const scb_poly* p, const uint64_t* ra, const u
 // All pair passes of a proof in one resident kernel (k_persist_pairs_sp).  `p` has m >= 3 variables; pass t folds two
 // variables by challenge pair t ((ra, rb) first, then what the callback returned) and hands the callback the grid
 // ((K+1)^2 values, folded table still has >= 2 variables) or the line ((K+1) values, exactly one variable left).
-extern "C" int scb_poly_resident_pairs(const scb_poly* p, const uint64_t* ra, const uint64_t* rb, scb_pair_cb cb, void* user,
-                                       uint32_t* passes_done) {
+extern "C" int scb_poly_resident_pairs(const scb_poly* p, const uint64_t* ra, const uint64_t* rb, uint32_t max_passes, scb_pair_cb cb,
+                                       void* user, uint32_t* passes_done, scb_poly** out_folded) {
     ARG_TRY(p && ra && rb && cb && passes_done, "null argument");
     *passes_done = 0;
+    if (out_folded) *out_folded = nullptr;
     ARG_TRY(p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G, "pair passes are defined for product polynomials");
     ARG_TRY(p->f->policy == POL_SP, "pair passes are implemented for the small-prime policy");
     const uint32_t m = p->t[0].nv;
@@ -1501,7 +1552,10 @@ extern "C" int scb_poly_resident_pairs(const scb_poly* p, const uint64_t* ra, co
         set_error("cooperative launches are not supported on this device");
         return SCB_ETAIL;
     }
-    const uint32_t n_passes = (m - 2 + 1) / 2, NP = (uint32_t)p->t.size() + 1;
+    const uint32_t all_passes = (m - 2 + 1) / 2, NP = (uint32_t)p->t.size() + 1;
+    const uint32_t n_passes = (max_passes == 0 || max_passes > all_passes) ? all_passes : max_passes;
+    const bool exchanging = g_cur_peers && g_cur_peers->world > 1;
+    ARG_TRY(!exchanging || m >= 2 * n_passes + 2, "sharded pair passes must leave two local variables (grid sums)");
     std::vector<BufRef> ba(p->t.size()), bb(p->t.size());
     for (size_t k = 0; k < p->t.size(); ++k) {
         ARG_TRY(p->t[k].p32 == p->t[0].p32, "tables of one polynomial must share a layout");
@@ -1524,8 +1578,11 @@ extern "C" int scb_poly_resident_pairs(const scb_poly* p, const uint64_t* ra, co
             ob.p[k] = bb[k]->ptr;
         }
         auto kern = k_persist_pairs_sp<K>;
+        int use_stage = pair_staging() ? 1 : 0;
+        const size_t smem = use_stage ? pair_stage_bytes<K>() : 0;
+        RC_TRY(allow_smem(kern, smem));
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, 0) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
         static const int bps_env = (int)env_u32("SCB_PAIR_BPS", 0);
         if (bps_env > 0 && bps_env < nb) nb = bps_env;
         int grid = c->sms * nb;
@@ -1536,8 +1593,10 @@ extern "C" int scb_poly_resident_pairs(const scb_poly* p, const uint64_t* ra, co
         int w32 = p->t[0].p32 ? 1 : 0;
         PersistCtl* ctl = c->persist_ctl;
         uint64_t* parts = c->partials;
-        void* args[] = {&fd, &in, &oa, &ob, &a, &b, &mm, &np_, &w32, &mb, &ctl, &parts, &timeout_ns};
-        le = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), args, 0, g_stream);
+        PeerArg pa = peer_arg(c);  // exchange numbers pa.seq .. pa.seq + n_passes - 1, one per pass
+        if (exchanging) g_cur_peers->seq += n_passes - 1;
+        void* args[] = {&fd, &in, &oa, &ob, &a, &b, &mm, &np_, &w32, &mb, &ctl, &parts, &timeout_ns, &use_stage, &pa};
+        le = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), args, smem, g_stream);
     });
     if (le != cudaSuccess) {
         cudaGetLastError();
@@ -1619,6 +1678,18 @@ extern "C" int scb_poly_resident_pairs(const scb_poly* p, const uint64_t* ra, co
         set_error("resident kernel failed: %s", cudaGetErrorString(e));
         rc = SCB_ECUDA;
     }
+    if (rc == SCB_OK && exchanging) rc = peers_check(c);
+    if (rc == SCB_OK && out_folded) {  // the tables after n_passes two-variable folds: what the last pass wrote
+        auto q = std::make_unique<scb_poly>(*p);
+        q->allow_packed = true;
+        const bool in_b = ((n_passes - 1) & 1) != 0;
+        for (size_t k = 0; k < p->t.size(); ++k) {
+            q->t[k].nv = m - 2 * n_passes;
+            q->t[k].buf = in_b ? bb[k] : ba[k];
+            q->t[k].p32 = true;
+        }
+        *out_folded = q.release();
+    }
     return rc;
 }
 
@@ -1654,7 +1725,7 @@ extern "C" int scb_peers_create(uint32_t rank, uint32_t world, size_t gather_byt
     p->rank = rank;
     p->world = world;
     p->gather_bytes = (gather_bytes + 255) & ~(size_t)255;
-    const size_t bytes = 4096 + 2 * p->gather_bytes;
+    const size_t bytes = (size_t)kWinGatherWords * 8 + 2 * p->gather_bytes;
     void* w = nullptr;
     CU_TRY(cudaMalloc(&w, bytes));  // plain cudaMalloc: pool (cudaMallocAsync) memory cannot be exported through IPC
     CU_TRY(cudaMemset(w, 0, bytes));
@@ -1729,7 +1800,7 @@ extern "C" int scb_peers_gather_poly(scb_peers* p, const scb_poly* slab, scb_pol
     pa.seq = ++p->gseq;
     pa.status = c->h_res + kStatusWord;
     pa.timeout_ns = 10ull * 1000 * 1000 * 1000;
-    const size_t area = 4096 + (pa.seq & 1) * p->gather_bytes;
+    const size_t area = (size_t)kWinGatherWords * 8 + (pa.seq & 1) * p->gather_bytes;
     auto q = std::make_unique<scb_poly>(*slab);
     for (size_t k = 0; k < K; ++k) {
         ARG_TRY(slab->t[k].p32 == p32 && slab->t[k].nv == slab->t[0].nv, "tables of one polynomial must share a layout");

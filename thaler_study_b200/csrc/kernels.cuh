@@ -46,16 +46,18 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 // ------------------------------------------------------------------------------------------
 // Peer exchange window (multi-GPU).  Every rank owns one window in its own HBM, mapped into every
 // peer through CUDA IPC; NVLink P2P stores write straight into it.  Word layout (uint64_t):
-//   [0, 320)    sums  [slot 2][rank 8][kMaxPts * kMaxLimbs]   partial round sums posted BY rank g
-//   [320, 336)  flags [slot 2][rank 8]                         sequence number of the post
-//   [336, 344)  gather flags [rank 8]
-//   [512, ...)  gather area (table slabs at consolidation)
+//   [0, 512)    sums  [slot 2][rank 8][32]    partial sums posted BY rank g: (d+1) limbs-wide round sums, or the
+//                                             (K+1)^2 one-limb grid sums of the two-rounds-per-pass kernels
+//   [512, 528)  flags [slot 2][rank 8]        sequence number of the post
+//   [528, 536)  gather flags [rank 8]
+//   [1024, ...) gather area (table slabs at consolidation)
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxRanks = 8;
-constexpr int kWinSumStride = kMaxPts * kMaxLimbs;          // 20 words per (slot, rank)
-constexpr int kWinFlags = 2 * kMaxRanks * kWinSumStride;    // 320
-constexpr int kWinGatherFlags = kWinFlags + 2 * kMaxRanks;  // 336
-constexpr int kWinGatherWords = 512;                        // gather area starts at byte 4096
+constexpr int kWinSumStride = 32;                           // words per (slot, rank): >= kMaxPts * kMaxLimbs and >= 25
+constexpr int kWinFlags = 2 * kMaxRanks * kWinSumStride;    // 512
+constexpr int kWinGatherFlags = kWinFlags + 2 * kMaxRanks;  // 528
+constexpr int kWinGatherWords = 1024;                       // gather area starts at byte 8192
+static_assert(kWinSumStride >= kMaxPts * kMaxLimbs, "window slot too small");
 struct PeerArg {
     uint64_t* win[kMaxRanks];  // win[g] = rank g's window as mapped in THIS process
     uint32_t rank;

@@ -24,6 +24,38 @@ namespace scb {
 constexpr int kMaxGridPts = 25;  // (K+1)^2 for K <= 4
 
 // Accumulates prod_k v_k(a, b) into acc[a * NP + b] for one 2x2 block of every table: c[k][y1 + 2 y2] canonical.
+//
+// The LAST factor is multiplied in without a Montgomery step and straight into the 64-bit accumulator (one
+// IMAD.WIDE with the accumulator as addend): per grid point K-2 reduced products + 1 fused multiply-accumulate
+// instead of K-1 reduced products + a 64-bit add.  Terms are < 13 p^2 (K <= 3) / 20 p^2 (K = 4), so an accumulator
+// takes GridConsts<K>::fold_every terms before grid_fold() has to bring it back under 2^60.1; the sums carry K-2 factors
+// of 2^-32, i.e. GridConsts<K>::msg_k restores the Montgomery form in msg_final.
+template <int K>
+struct GridConsts {
+    static constexpr int fold_every = K <= 3 ? 16 : 8;
+    // msg_final(acc, k) applies k-1 single REDC steps: 2(K-1) are due, K-2 were done inline and 2 by grid_canon
+    static constexpr int msg_k = K >= 2 ? K - 1 : 1;
+};
+__device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c) {
+    uint64_t d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+template <int NG>
+__device__ __forceinline__ void grid_fold(uint32_t c32, uint64_t (&acc)[NG]) {  // c32 = 2^32 mod p; value mod p unchanged
+#pragma unroll
+    for (int i = 0; i < NG; ++i) acc[i] = mad_wide((uint32_t)(acc[i] >> 32), c32, (uint64_t)(uint32_t)acc[i]);
+}
+// Before sums across threads: bring every accumulator down to <= p.  A 64-bit `%` costs ~50 instructions; one fold
+// (< 2^60.1) and one two-step REDC (x 2^-64, accounted for in GridConsts::msg_k) cost 8.  K = 1 sums are small.
+template <int K, int NG>
+__device__ __forceinline__ void grid_canon(const PolSP& ar, uint32_t c32, uint64_t (&acc)[NG]) {
+    if constexpr (K >= 2) {
+        grid_fold(c32, acc);
+#pragma unroll
+        for (int i = 0; i < NG; ++i) acc[i] = ar.redc(acc[i]);
+    }
+}
 template <int K>
 __device__ __forceinline__ void grid_accumulate(const PolSP& ar, const uint32_t (&c)[K][4], uint64_t (&acc)[(K + 1) * (K + 1)]) {
     constexpr int NP = K + 1;
@@ -51,12 +83,13 @@ __device__ __forceinline__ void grid_accumulate(const PolSP& ar, const uint32_t 
             for (int b = 0; b < NP; ++b) {
                 if (b == 1) v = va1[a];
                 else if (b > 1) v = ar.lz_add(v, e);
-                P[a * NP + b] = k == 0 ? v : ar.msg_mul(P[a * NP + b], v);
+                const int i = a * NP + b;
+                if (K == 1) acc[i] += v;
+                else if (k == K - 1) acc[i] = mad_wide(P[i], v, acc[i]);
+                else P[i] = k == 0 ? v : ar.msg_mul(P[i], v);
             }
         }
     }
-#pragma unroll
-    for (int i = 0; i < NP * NP; ++i) ar.acc_add(acc[i], P[i]);
 }
 
 // Pass without a fold (the first pass of a proof, or the first after a consolidation): grid of the table as it is.
@@ -64,7 +97,10 @@ __device__ __forceinline__ void grid_accumulate(const PolSP& ar, const uint32_t 
 template <int K, bool IN32, bool NC>
 __device__ __forceinline__ void grid_pass_sp(const PolSP& ar, const uint64_t* const (&src)[K], uint64_t n_groups, uint64_t start, uint64_t stride,
                                              uint64_t (&acc)[(K + 1) * (K + 1)]) {
+    const uint32_t c32 = (uint32_t)((1ull << 32) % ar.p);
+    uint32_t it = 0;
     for (uint64_t g = start; g < n_groups; g += stride) {
+        if ((++it % GridConsts<K>::fold_every) == 0) grid_fold(c32, acc);
         uint32_t c[K][4];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -84,6 +120,7 @@ __device__ __forceinline__ void grid_pass_sp(const PolSP& ar, const uint64_t* co
         }
         grid_accumulate<K>(ar, c, acc);
     }
+    grid_canon<K>(ar, c32, acc);
 }
 
 // Fold two variables (challenges ra, rb as fold constants) and accumulate the grid of the folded table: 16 adjacent
@@ -92,7 +129,10 @@ template <int K, bool IN32, bool NC, bool GRID>
 __device__ __forceinline__ void pair_pass_sp(const PolSP& ar, const PolSP::FoldC ra, const PolSP::FoldC rb, const uint64_t* const (&src)[K],
                                              uint64_t* const (&dst)[K], uint64_t n_groups, uint64_t start, uint64_t stride,
                                              uint64_t (&acc)[(K + 1) * (K + 1)]) {
+    const uint32_t c32 = (uint32_t)((1ull << 32) % ar.p);
+    uint32_t it = 0;
     for (uint64_t g = start; g < n_groups; g += stride) {
+        if (GRID && (++it % GridConsts<K>::fold_every) == 0) grid_fold(c32, acc);
         uint32_t c[K][4];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -121,13 +161,269 @@ __device__ __forceinline__ void pair_pass_sp(const PolSP& ar, const PolSP::FoldC
         }
         if constexpr (GRID) grid_accumulate<K>(ar, c, acc);
     }
+    grid_canon<K>(ar, c32, acc);
+}
+
+// ------------------------------------------------------------------------------------------ staged loads
+// The grid passes spend ~300 issue cycles per thread-iteration at 2-3 CTAs per SM, so loads issued at the top of an
+// iteration leave HBM idle while the warp computes (ncu: long_scoreboard dominates, issue active 54 %).  cp.async
+// keeps the NEXT iteration's bytes in flight while the current one is being multiplied out, at no register cost:
+// every thread owns WPT/2 16-byte slots per table and stage in shared memory (consecutive threads -> consecutive
+// slots: conflict-free for the asynchronous writes and for the LDS.128 reads), so no CTA barrier is involved, only
+// cp.async.wait_group.  `.cg` copies go through L2, which keeps them coherent with the buffers the resident kernel
+// rewrites every other pass.
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <int K, int WPT>  // WPT = u64 words per table per thread-iteration
+struct Stager {
+    // A warp's 32 consecutive groups are one contiguous tile of 32 * WPT words per table: chunk c of the tile is
+    // copied by ONE warp-wide instruction (lane i moves bytes [512 c + 16 i, +16)), i.e. whole 128-byte lines per
+    // request, and lane j then reads its own WPT words back from the tile.
+    static constexpr int CH = WPT / 2;          // 512-byte chunks per warp tile
+    static constexpr int TILE = 32 * WPT * 8;   // bytes per warp, table and stage
+    uint32_t wbase;                             // shared-space address of this warp's stage-0 table-0 tile
+    uint32_t lane;
+    __device__ __forceinline__ Stager(void* smem)
+        : wbase((uint32_t)__cvta_generic_to_shared(smem) + (threadIdx.x >> 5) * (2u * K * TILE)), lane(threadIdx.x & 31) {}
+    static constexpr size_t bytes(int threads) { return (size_t)2 * K * TILE * (threads / 32); }
+    // g0 = group of lane 0 (warp-uniform); chunks that lie entirely beyond the table are skipped
+    __device__ __forceinline__ void issue(int s, const uint64_t* const (&src)[K], uint64_t g0, uint64_t n_groups) const {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const uint32_t off = c * 512u + lane * 16u;  // byte offset inside the tile
+                if (g0 + off / (WPT * 8) < n_groups) cp_async16(wbase + (s * K + k) * TILE + off, src[k] + g0 * WPT + off / 8);
+            }
+        cp_async_commit();
+    }
+    __device__ __forceinline__ void read(int s, int k, uint64_t (&w)[WPT]) const {
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+            asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];"
+                         : "=l"(w[2 * c]), "=l"(w[2 * c + 1])
+                         : "r"(wbase + (s * K + k) * TILE + lane * (WPT * 8) + c * 16)
+                         : "memory");
+    }
+};
+
+template <int K, bool IN32>
+__device__ __forceinline__ void grid_pass_sp_staged(const PolSP& ar, void* smem, const uint64_t* const (&src)[K], uint64_t n_groups, uint64_t start,
+                                                    uint64_t stride, uint64_t (&acc)[(K + 1) * (K + 1)]) {
+    constexpr int WPT = IN32 ? 2 : 4;
+    const Stager<K, WPT> st(smem);
+    int s = 0;
+    const uint32_t c32 = (uint32_t)((1ull << 32) % ar.p);
+    uint32_t it = 0;
+    uint64_t g0 = start - st.lane;  // warp-uniform loop: start and stride are multiples of 32 plus the lane
+    if (g0 < n_groups) st.issue(0, src, g0, n_groups);
+    while (g0 < n_groups) {
+        if ((++it % GridConsts<K>::fold_every) == 0) grid_fold(c32, acc);
+        const uint64_t gn = g0 + stride;
+        __syncwarp();  // every lane is done reading the stage that is refilled next
+        if (gn < n_groups) st.issue(s ^ 1, src, gn, n_groups);
+        else cp_async_commit();  // empty group: keeps "all but the newest group" == "this iteration's data"
+        cp_async_wait<1>();
+        __syncwarp();  // ... and every lane's share of this iteration's tile has landed
+        if (g0 + st.lane < n_groups) {
+            uint32_t c[K][4];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                uint64_t w[WPT];
+                st.read(s, k, w);
+                if constexpr (IN32) {
+                    c[k][0] = (uint32_t)w[0];
+                    c[k][1] = (uint32_t)(w[0] >> 32);
+                    c[k][2] = (uint32_t)w[1];
+                    c[k][3] = (uint32_t)(w[1] >> 32);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) c[k][q] = (uint32_t)w[q];
+                }
+            }
+            grid_accumulate<K>(ar, c, acc);
+        }
+        g0 = gn;
+        s ^= 1;
+    }
+    cp_async_wait<0>();
+    grid_canon<K>(ar, c32, acc);
+}
+
+// packed uint32 input: 16 entries = 64 bytes per table per thread-iteration
+template <int K>
+__device__ __forceinline__ void pair_pass_sp_staged(const PolSP& ar, void* smem, const PolSP::FoldC ra, const PolSP::FoldC rb,
+                                                    const uint64_t* const (&src)[K], uint64_t* const (&dst)[K], uint64_t n_groups, uint64_t start,
+                                                    uint64_t stride, uint64_t (&acc)[(K + 1) * (K + 1)]) {
+    const Stager<K, 8> st(smem);
+    int s = 0;
+    const uint32_t c32 = (uint32_t)((1ull << 32) % ar.p);
+    uint32_t it = 0;
+    uint64_t g0 = start - st.lane;
+    if (g0 < n_groups) st.issue(0, src, g0, n_groups);
+    while (g0 < n_groups) {
+        if ((++it % GridConsts<K>::fold_every) == 0) grid_fold(c32, acc);
+        const uint64_t gn = g0 + stride;
+        __syncwarp();
+        if (gn < n_groups) st.issue(s ^ 1, src, gn, n_groups);
+        else cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        const uint64_t g = g0 + st.lane;
+        if (g < n_groups) {
+            uint32_t c[K][4];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                uint64_t w[8];
+                st.read(s, k, w);
+                uint32_t t[16];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    t[2 * q] = (uint32_t)w[q];
+                    t[2 * q + 1] = (uint32_t)(w[q] >> 32);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t lo = ar.fold_c(t[4 * q], t[4 * q + 1], ra), hi = ar.fold_c(t[4 * q + 2], t[4 * q + 3], ra);
+                    c[k][q] = ar.fold_c(lo, hi, rb);
+                }
+                uint64_t o[2] = {(uint64_t)c[k][0] | ((uint64_t)c[k][1] << 32), (uint64_t)c[k][2] | ((uint64_t)c[k][3] << 32)};
+                st_words<2>(dst[k] + g * 2, o);
+            }
+            grid_accumulate<K>(ar, c, acc);
+        }
+        g0 = gn;
+        s ^= 1;
+    }
+    cp_async_wait<0>();
+    grid_canon<K>(ar, c32, acc);
+}
+// dynamic shared memory the staged passes of a K-table kernel need (threads = kThreads)
+template <int K>
+constexpr size_t pair_stage_bytes() {
+    return Stager<K, 8>::bytes(kThreads);  // the packed pair pass is the largest: 2 stages x K x 64 B x threads
+}
+
+// ------------------------------------------------------------------------------------------ TMA-staged tiles
+// Producer/consumer ring in shared memory: one elected thread of a dedicated producer warp streams whole CTA tiles
+// (kThreads groups per table, contiguous in HBM) with cp.async.bulk (TMA 1-D bulk copies) that complete on an
+// mbarrier; the compute warps wait on that "full" barrier, read their own groups back with LDS.128 and release the
+// stage through an "empty" barrier.  Bytes in flight are set by the ring depth, not by registers or occupancy.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+
+constexpr int kTmaStages = 4;
+template <int K, int WPT>
+constexpr size_t tma_ring_bytes() {
+    return (size_t)kTmaStages * K * kThreads * WPT * 8;
+}
+
+// K6a'  grid of a table as it is, TMA-staged.  blockDim = kThreads compute threads + one producer warp.
+template <int K, bool IN32>
+__global__ void __launch_bounds__(kThreads + 32, 2)
+    k_grid_sp_tma(FieldDesc f, TabsIn<K> in, uint64_t n_groups, uint64_t* partials, unsigned int* ticket, uint64_t* out, PeerArg peer) {
+    constexpr int NG = (K + 1) * (K + 1), WPT = IN32 ? 2 : 4, S = kTmaStages;
+    constexpr uint32_t TILE_B = kThreads * WPT * 8;  // bytes per table and stage
+    extern __shared__ __align__(128) uint8_t ring[];
+    __shared__ __align__(8) uint64_t full_bar[S], empty_bar[S];
+    const PolSP ar(f);
+    uint64_t acc[NG];
+#pragma unroll
+    for (int i = 0; i < NG; ++i) acc[i] = 0;
+    const uint64_t n_tiles = (n_groups + kThreads - 1) / kThreads;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), kThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == kThreads / 32) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t s = it % S, ph = (it / S) & 1;
+                if (it >= (uint32_t)S) mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+                const uint64_t left = n_groups - tile * kThreads;
+                const uint32_t bytes = (uint32_t)(left < kThreads ? left : kThreads) * WPT * 8;
+                mbar_expect_tx(smem_u32(&full_bar[s]), K * bytes);
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    bulk_g2s(smem_u32(ring + (size_t)(s * K + k) * TILE_B), in.p[k] + tile * kThreads * WPT, bytes, smem_u32(&full_bar[s]));
+            }
+        }
+    } else {
+        const uint32_t c32 = (uint32_t)((1ull << 32) % ar.p);
+        uint32_t it = 0;
+        for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t s = it % S, ph = (it / S) & 1;
+            if (((it + 1) % GridConsts<K>::fold_every) == 0) grid_fold(c32, acc);
+            mbar_wait(smem_u32(&full_bar[s]), ph);
+            if (tile * kThreads + threadIdx.x < n_groups) {
+                uint32_t c[K][4];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    uint64_t w[WPT];
+                    const uint32_t a = smem_u32(ring + (size_t)(s * K + k) * TILE_B) + threadIdx.x * (WPT * 8);
+#pragma unroll
+                    for (int q = 0; q < WPT; q += 2)
+                        asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(w[q]), "=l"(w[q + 1]) : "r"(a + q * 8) : "memory");
+                    if constexpr (IN32) {
+                        c[k][0] = (uint32_t)w[0];
+                        c[k][1] = (uint32_t)(w[0] >> 32);
+                        c[k][2] = (uint32_t)w[1];
+                        c[k][3] = (uint32_t)(w[1] >> 32);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) c[k][q] = (uint32_t)w[q];
+                    }
+                }
+                grid_accumulate<K>(ar, c, acc);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&empty_bar[s]));
+        }
+        grid_canon<K>(ar, c32, acc);
+    }
+    grid_reduce_finish<PolSP, NG>(ar, acc, partials, ticket, out, GridConsts<K>::msg_k, &peer);
 }
 
 // ------------------------------------------------------------------------------------------ stand-alone kernels
 // K6a  grid of a table as it is (Prover::new for the small-prime policy: c_1, g_1 and g_2 from one pass).
-template <int K, bool IN32>
+template <int K, bool IN32, bool STAGED>
 __global__ void __launch_bounds__(kThreads, 3)
-    k_grid_sp(FieldDesc f, TabsIn<K> in, uint64_t n_groups, uint64_t* partials, unsigned int* ticket, uint64_t* out) {
+    k_grid_sp(FieldDesc f, TabsIn<K> in, uint64_t n_groups, uint64_t* partials, unsigned int* ticket, uint64_t* out, PeerArg peer) {
     constexpr int NG = (K + 1) * (K + 1);
     const PolSP ar(f);
     uint64_t acc[NG];
@@ -136,12 +432,15 @@ __global__ void __launch_bounds__(kThreads, 3)
     const uint64_t* src[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) src[k] = in.p[k];
-    grid_pass_sp<K, IN32, true>(ar, src, n_groups, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, (uint64_t)gridDim.x * blockDim.x, acc);
-    grid_reduce_finish<PolSP, NG>(ar, acc, partials, ticket, out, K, nullptr);
+    extern __shared__ uint4 stage_smem[];
+    const uint64_t start = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    if constexpr (STAGED) grid_pass_sp_staged<K, IN32>(ar, stage_smem, src, n_groups, start, stride, acc);
+    else grid_pass_sp<K, IN32, true>(ar, src, n_groups, start, stride, acc);
+    grid_reduce_finish<PolSP, NG>(ar, acc, partials, ticket, out, GridConsts<K>::msg_k, &peer);
 }
 // K6b  one pair pass as its own launch (what the resident kernel runs per pass; used for profiling and as the
 // non-resident path).
-template <int K, bool IN32>
+template <int K, bool IN32, bool STAGED>
 __global__ void __launch_bounds__(kThreads, 3)
     k_pair_pass_sp(FieldDesc f, TabsIn<K> in, TabsOut<K> outp, ElemArg ra_arg, ElemArg rb_arg, uint64_t n_groups, uint64_t* partials,
                    unsigned int* ticket, uint64_t* out) {
@@ -158,9 +457,11 @@ __global__ void __launch_bounds__(kThreads, 3)
         src[k] = in.p[k];
         dst[k] = outp.p[k];
     }
-    pair_pass_sp<K, IN32, true, true>(ar, ra, rb, src, dst, n_groups, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x,
-                                      (uint64_t)gridDim.x * blockDim.x, acc);
-    grid_reduce_finish<PolSP, NG>(ar, acc, partials, ticket, out, K, nullptr);
+    extern __shared__ uint4 stage_smem[];
+    const uint64_t start = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    if constexpr (IN32 && STAGED) pair_pass_sp_staged<K>(ar, stage_smem, ra, rb, src, dst, n_groups, start, stride, acc);
+    else pair_pass_sp<K, IN32, true, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);
+    grid_reduce_finish<PolSP, NG>(ar, acc, partials, ticket, out, GridConsts<K>::msg_k, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------ resident kernel
@@ -171,11 +472,12 @@ __global__ void __launch_bounds__(kThreads, 3)
 template <int K>
 __global__ void __launch_bounds__(kThreads, (K <= 2 ? 3 : 2))
     k_persist_pairs_sp(FieldDesc f, TabsIn<K> in0, TabsOut<K> buf_a, TabsOut<K> buf_b, ElemArg ra0, ElemArg rb0, uint32_t m, uint32_t n_passes,
-                       int in0_w32, TailMailbox* mb, PersistCtl* ctl, uint64_t* partials, uint64_t timeout_ns) {
+                       int in0_w32, TailMailbox* mb, PersistCtl* ctl, uint64_t* partials, uint64_t timeout_ns, int use_stage, PeerArg peer) {
     using A = PolSP;
     constexpr int NP = K + 1, NG = NP * NP;
     bool src_w32 = in0_w32 != 0;
     const A ar(f);
+    extern __shared__ uint4 stage_smem[];  // pair_stage_bytes<K>()
     __shared__ uint64_t sm[32 * NG];
     __shared__ uint64_t r_sm[2];
     __shared__ int flag_sm;  // 1: this CTA took the last ticket, 2: abort
@@ -230,6 +532,7 @@ __global__ void __launch_bounds__(kThreads, (K <= 2 ? 3 : 2))
             const uint64_t start = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = active * blockDim.x;
             if (m >= 4) {
                 if (!src_w32) pair_pass_sp<K, false, true, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);  // only the caller's tables
+                else if (use_stage) pair_pass_sp_staged<K>(ar, stage_smem, ra, rb, src, dst, n_groups, start, stride, acc);
                 else if (t == 0) pair_pass_sp<K, true, true, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);
                 else pair_pass_sp<K, true, false, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);
             } else if (start == 0) {  // 8 entries per table -> 2 -> line sums; nothing reads the folded pair again
@@ -280,9 +583,17 @@ __global__ void __launch_bounds__(kThreads, (K <= 2 ? 3 : 2))
             if (finisher && threadIdx.x == 0) {
                 const uint64_t hi = (uint64_t)(t + 1) << 32;
                 const int n_out = grid_out ? NG : NP;
+                uint64_t w[NG][1];
+#pragma unroll
+                for (int i = 0; i < NG; ++i) w[i][0] = ar.msg_final(acc[i], grid_out ? GridConsts<K>::msg_k : K);
+                if (peer.world > 1) {  // sharded prover: add the peer GPUs' sums of this pass (NVLink peer windows)
+                    PeerArg pa = peer;
+                    pa.seq += t;
+                    peer_exchange_sum<A, NG>(ar, pa, w);
+                }
 #pragma unroll
                 for (int i = 0; i < NG; ++i)
-                    if (i < n_out) st_sys(&mb->evals[i], hi | ar.msg_final(acc[i], K));
+                    if (i < n_out) st_sys(&mb->evals[i], hi | w[i][0]);
                 st_sys(&mb->stamp[2 * t], globaltimer_ns());
                 int bad = 0;
                 if (t + 1 < n_passes) {

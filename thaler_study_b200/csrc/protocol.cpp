@@ -165,11 +165,11 @@ struct PeersScope {  // makes `peers` the current exchange group of this thread 
     bool active;
 };
 // slabs small enough: all-gather them once (P2P stores into every peer's window) and continue replicated
-static int maybe_consolidate(scb_prover* p) {
+static int maybe_consolidate(scb_prover* p, bool force = false) {
     if (!p->sharded) return SCB_OK;
     uint32_t lv = 0;
     RC_TRY(scb_poly_num_vars(p->g, &lv));
-    if (lv > p->consolidate_at) return SCB_OK;
+    if (lv > p->consolidate_at && !force) return SCB_OK;
     scb_poly* full = nullptr;
     RC_TRY(scb_peers_gather_poly(p->peers, p->g, &full));
     scb_poly_free(p->g);
@@ -199,10 +199,14 @@ static int prover_new_impl(const scb_poly* g, scb_peers* peers, uint32_t world, 
         RC_TRY(maybe_consolidate(p.get()));
     }
     const HostField& F = p->fi->h;
-    if (!p->sharded && p->num_vars >= 2 && pair_passes_ok(p->g)) {
-        // g_1(X) = H(X,0) + H(X,1) and c_1 = g_1(0) + g_1(1), from the grid pass
+    if (p->num_vars >= 2 && pair_passes_ok(p->g)) {
+        // g_1(X) = H(X,0) + H(X,1) and c_1 = g_1(0) + g_1(1), from the grid pass (sharded: summed over the peer
+        // GPUs by the kernel's finishing thread)
         uint64_t w[32];
-        RC_TRY(scb_poly_grid_evals(p->g, w));
+        {
+            PeersScope scope(p->sharded ? p->peers : nullptr);
+            RC_TRY(scb_poly_grid_evals(p->g, w));
+        }
         const uint32_t np = p->np;
         p->grid.resize((size_t)np * np);
         for (uint32_t i = 0; i < np * np; ++i) F.load(w + i, p->grid[i]);
@@ -472,26 +476,51 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
     offsets[1] = hash_input.size();
     const bool product = p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G;
     uint32_t j = 1;
-    if (p->have_grid && !p->sharded && !g_tail_disabled && p->num_vars >= 2 && pair_passes_ok(p->g)) {
+    if (p->have_grid && !g_tail_disabled && p->num_vars >= 2 && pair_passes_ok(p->g)) {
         // two rounds per pass: g_2 comes from Prover::new's grid, then every pass of the resident kernel folds two
-        // variables and returns the grid for the next two messages
+        // variables and returns the grid for the next two messages.  Invariant at the top of the loop: p->g is folded
+        // by used[0 .. size-2), the last two challenges are the pair the next pass folds by, and the messages for
+        // those two variables are already out.
         PairCtx pc{&F, p->kind, p->np, &hash_input, &chain, offsets, 1, {}};
         const Fe r1 = pc.next_challenge();
         pc.emit_second(p->grid, r1);
         int rc = SCB_OK;
-        if (p->num_vars > 2) {
-            pc.next_challenge();
+        size_t base = 0;  // challenges already folded into p->g
+        if (p->num_vars > 2) pc.next_challenge();
+        while (pc.msgs < p->num_vars && rc == SCB_OK) {
+            base = pc.used.size() - 2;
+            const uint64_t* pair = &pc.used[base];
+            uint32_t live = 0, max_passes = 0;
+            RC_TRY(maybe_consolidate(p));
+            RC_TRY(scb_poly_num_vars(p->g, &live));
+            if (p->sharded) {
+                // sharded passes stop at the consolidation point and always leave two local variables for the grid
+                for (uint32_t mm = live; mm > p->consolidate_at && mm >= 4; mm -= 2) ++max_passes;
+                if (max_passes == 0) {
+                    RC_TRY(maybe_consolidate(p, true));
+                    RC_TRY(scb_poly_num_vars(p->g, &live));
+                }
+            }
+            const bool was_sharded = p->sharded;
             uint32_t done = 0;
-            rc = scb_poly_resident_pairs(p->g, &pc.used[0], &pc.used[1], pair_pass_cb, &pc, &done);
-            if (rc != SCB_OK && rc != SCB_ETAIL) return rc;
+            scb_poly* folded = nullptr;
+            {
+                PeersScope scope(was_sharded ? p->peers : nullptr);
+                rc = scb_poly_resident_pairs(p->g, pair, pair + 1, max_passes, pair_pass_cb, &pc, &done, was_sharded ? &folded : nullptr);
+            }
+            if (rc == SCB_OK && was_sharded) {  // carry on from the slab the kernel left behind: consolidation comes next
+                scb_poly_free(p->g);
+                p->g = folded;
+            }
         }
+        if (rc != SCB_OK && rc != SCB_ETAIL) return rc;
         j = pc.msgs;
         if (rc == SCB_ETAIL) {
             // lock-step lost (e.g. a profiler serialises kernel and host): keep the messages that are out, fold the
             // tables by the challenges they were derived with and carry on with one launch per round
             g_tail_disabled = true;
             scb_poly* refolded = nullptr;
-            RC_TRY(scb_poly_fix_variables(p->g, pc.used.data(), j - 1, &refolded));
+            RC_TRY(scb_poly_fix_variables(p->g, pc.used.data() + base, (uint32_t)(j - 1 - base), &refolded));
             scb_poly_free(p->g);
             p->g = refolded;
         }
