@@ -93,7 +93,7 @@ def test_pair_kernel_matches_one_round_per_pass():
     code = (
         "import sys; sys.path.insert(0, %r)\n"
         "import thaler_study_b200 as T\n"
-        "for p, v, K in ((1572869, 20, 3), (1572869, 19, 3), (1572869, 17, 4), (1572869, 16, 2), (389, 15, 1), (5, 14, 3), (268435399, 18, 3)):\n"
+        "for p, v, K in ((1572869, 20, 3), (1572869, 19, 3), (1572869, 17, 4), (1572869, 16, 2), (389, 15, 1), (5, 14, 3), (268435399, 18, 3), (1572869, 5, 3), (1572869, 4, 2)):\n"
         "    F = T.Field(p)\n"
         "    g = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, 70 + k) for k in range(K)])\n"
         "    print(b''.join(T.generate_transcript(T.Prover(g))).hex())\n"
@@ -101,10 +101,11 @@ def test_pair_kernel_matches_one_round_per_pass():
         "    print(b''.join(T.generate_transcript(T.Prover(T.MatMulG.from_tables(a, b)))).hex())\n"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
     outs = []
-    for env_add in ({"SCB_PAIRS": "0", "SCB_TAIL_VARS": "0"}, {"SCB_PAIRS": "0"}, {}, {"SCB_PAIR_BPS": "1"}):
+    for env_add in ({"SCB_PAIRS": "0", "SCB_TAIL_VARS": "0"}, {"SCB_PAIRS": "0"}, {}, {"SCB_PAIR_BPS": "1"}, {"SCB_PAIR_RESIDENT": "0"},
+                    {"SCB_PAIR_STAGE": "1"}, {"SCB_GRID_TMA": "1"}):
         env = dict(os.environ, **env_add)
         outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600))
     for o in outs:
         assert o.returncode == 0, o.stderr[-2000:]
-    assert len(outs[0].stdout.split()) == 14
+    assert len(outs[0].stdout.split()) == 18
     assert len(set(o.stdout for o in outs)) == 1

@@ -487,12 +487,28 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
         int rc = SCB_OK;
         size_t base = 0;  // challenges already folded into p->g
         if (p->num_vars > 2) pc.next_challenge();
+        // SCB_PAIR_RESIDENT=0: every pass is an ordinary launch (k_pair_pass_sp) -- the same pass bodies, visible to
+        // ncu, which cannot run the resident kernel (it serialises kernel and host)
+        static const bool resident = !(getenv("SCB_PAIR_RESIDENT") && atoi(getenv("SCB_PAIR_RESIDENT")) == 0);
         while (pc.msgs < p->num_vars && rc == SCB_OK) {
             base = pc.used.size() - 2;
             const uint64_t* pair = &pc.used[base];
             uint32_t live = 0, max_passes = 0;
-            RC_TRY(maybe_consolidate(p));
+            RC_TRY(maybe_consolidate(p, !resident));
             RC_TRY(scb_poly_num_vars(p->g, &live));
+            if (!resident) {
+                if (live < 4) {  // too small for a grid pass: the per-round path below finishes the proof
+                    rc = SCB_ETAIL;
+                    break;
+                }
+                uint64_t w[32], next_pair[2];
+                scb_poly* next = nullptr;
+                RC_TRY(scb_poly_pair_pass(p->g, pair, pair + 1, &next, w));
+                scb_poly_free(p->g);
+                p->g = next;
+                RC_TRY(pair_pass_cb(&pc, 0, p->np * p->np, w, next_pair));
+                continue;
+            }
             if (p->sharded) {
                 // sharded passes stop at the consolidation point and always leave two local variables for the grid
                 for (uint32_t mm = live; mm > p->consolidate_at && mm >= 4; mm -= 2) ++max_passes;
@@ -518,7 +534,7 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
         if (rc == SCB_ETAIL) {
             // lock-step lost (e.g. a profiler serialises kernel and host): keep the messages that are out, fold the
             // tables by the challenges they were derived with and carry on with one launch per round
-            g_tail_disabled = true;
+            if (resident) g_tail_disabled = true;
             scb_poly* refolded = nullptr;
             RC_TRY(scb_poly_fix_variables(p->g, pc.used.data() + base, (uint32_t)(j - 1 - base), &refolded));
             scb_poly_free(p->g);
