@@ -208,6 +208,10 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly one JSON line: libraries that print banners to fd 1 (NCCL's version line) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world
@@ -450,7 +454,8 @@ def run_ours(args):
                "single_thread_value": v1, "seconds": tN}
 
     if rank == 0:
-        print(json.dumps({
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name(v, n_gpus, p), "tables": K, "vars_per_gpu": v, "total_vars": v + (world.bit_length() - 1),
@@ -459,7 +464,7 @@ def run_ours(args):
                        "parallelism": f"tables sharded by top variables over {n_gpus} GPU(s)"
                                       + ("" if world == 1 else f"; per-round exchange: {exchange}")},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        }))
+        }) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
