@@ -157,3 +157,67 @@ def test_wide_circuit_verifies(p, width_bits, depth):
     rng = np.random.default_rng(6)
     inp = F.to_mont([int(x) % p for x in rng.integers(0, 2**62, size=1 << width_bits)])
     assert run_gkr(F, c, inp, None, PyRng(OF, 7))
+
+
+class ReplayRng:
+    """Hands out pre-drawn challenges in order (public coins: the verifier's draws do not depend on the messages)."""
+
+    def __init__(self, values):
+        self.values, self.pos = list(values), 0
+
+    def draw(self):
+        v = self.values[self.pos]
+        self.pos += 1
+        return v
+
+
+def run_gkr_batched(F, circuit, inp, rng):
+    """Same protocol with prove_layer: the 2k challenges of a layer are drawn first, the prover produces the whole
+    layer proof in one call, and the reference's verifier logic replays the messages against those challenges."""
+    prover = GkrProver(circuit, inp)
+    verifier = GkrVerifier(circuit)
+    kind, r_i = verifier.receive_prover_msg(prover.start_protocol(), rng)
+    transcripts = []
+    for i in range(circuit.layers_len()):
+        k = circuit.num_vars_at(i + 1)
+        ch = [rng.draw() for _ in range(2 * k)]
+        start, raw = prover.prove_layer(i, r_i, ch)
+        msgs = prover.layer_messages(raw)
+        transcripts.append((start, msgs))
+        replay = ReplayRng(ch)
+        verifier.receive_prover_msg(start, replay)
+        for m in msgs[:-1]:
+            verifier.receive_prover_msg(m, replay)
+        verifier.final_random_point(replay)
+        assert replay.pos == 2 * k
+        kind, r_i = verifier.receive_prover_msg(msgs[-1], rng)  # draws the line point with the live rng
+        assert kind == "R"
+    return verifier.check_input(inp), transcripts
+
+
+@pytest.mark.parametrize("p,width_bits,depth", [(389, 3, 3), (1572869, 9, 4), (O.BLS12_381_FR.p, 6, 2)])
+def test_batched_layer_proof_equals_round_by_round(p, width_bits, depth):
+    OF, F = O.Field(p), T.Field(p)
+    c = big_circuit(F, width_bits, depth, 11)
+    rng = np.random.default_rng(12)
+    inp = F.to_mont([int(x) % p for x in rng.integers(0, 2**62, size=1 << width_bits)])
+    ok, batched = run_gkr_batched(F, c, inp, PyRng(OF, 13))
+    assert ok
+    # round by round with the same challenge stream: every message must be the same polynomial
+    prover, verifier, live = GkrProver(c, inp), GkrVerifier(c), PyRng(OF, 13)
+    kind, r_i = verifier.receive_prover_msg(prover.start_protocol(), live)
+    for i in range(c.layers_len()):
+        k = c.num_vars_at(i + 1)
+        ch = [live.draw() for _ in range(2 * k)]
+        replay = ReplayRng(ch)
+        start = prover.start_round(i, r_i)
+        assert start == batched[i][0]
+        verifier.receive_prover_msg(start, replay)
+        for j in range(2 * k - 1):
+            m = prover.round_msg(j)
+            assert m[1] == batched[i][1][j][1], (i, j)
+            prover.receive_verifier_msg(verifier.receive_prover_msg(m, replay))
+        prover.receive_verifier_msg(verifier.final_random_point(replay))
+        m = prover.round_msg(2 * k - 1)
+        assert m[1] == batched[i][1][-1][1] and m[2] == batched[i][1][-1][2]
+        kind, r_i = verifier.receive_prover_msg(m, live)

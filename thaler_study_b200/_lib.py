@@ -106,6 +106,7 @@ SIGNATURES = {
     "scb_gkr_prover_start_round": (C.c_int, [vp, C.c_uint32, u64p, u64p, u32p]),
     "scb_gkr_prover_round_evals": (C.c_int, [vp, C.c_uint32, u64p, u64p]),
     "scb_gkr_prover_restrict_evals": (C.c_int, [vp, u64p, u64p, C.c_uint32, u32p]),
+    "scb_gkr_prover_prove_layer": (C.c_int, [vp, C.c_uint32, u64p, u64p, C.c_uint32, u64p, u64p, u64p, C.c_uint32, u32p]),
     "scb_peers_create": (C.c_int, [C.c_uint32, C.c_uint32, C.c_size_t, vpp, u8p]),
     "scb_peers_connect": (C.c_int, [vp, u8p]),
     "scb_peers_free": (None, [vp]),

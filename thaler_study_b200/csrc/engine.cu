@@ -70,6 +70,7 @@ struct Ctx {
     uint64_t* partials = nullptr;  // per-block partial sums
     unsigned int* ticket = nullptr;
     uint64_t* h_res = nullptr;     // mapped pinned host memory: kernels write round sums here directly
+    uint64_t* h_msgs = nullptr;    // mapped pinned host memory, 64 KB: message sums of a whole batch of rounds (GKR layer)
     uint64_t* d_scratch = nullptr; // small device scratch (points, results)
     TailMailbox* mailbox = nullptr; // mapped pinned host memory shared with the persistent tail kernel
     PersistCtl* persist_ctl = nullptr; // device memory: barrier state of the grid-wide resident kernel
@@ -103,6 +104,7 @@ static int get_ctx(Ctx** out) {
             CU_TRY(cudaMalloc(&c.ticket, 64));
             CU_TRY(cudaMemset(c.ticket, 0, 64));
             CU_TRY(cudaHostAlloc(&c.h_res, 4096, cudaHostAllocMapped | cudaHostAllocPortable));
+            CU_TRY(cudaHostAlloc(&c.h_msgs, 65536, cudaHostAllocMapped | cudaHostAllocPortable));
             CU_TRY(cudaMalloc(&c.d_scratch, 64 * 1024));
             CU_TRY(cudaHostAlloc(&c.mailbox, sizeof(TailMailbox), cudaHostAllocMapped | cudaHostAllocPortable));
             std::memset((void*)c.mailbox, 0, sizeof(TailMailbox));

@@ -129,6 +129,33 @@ class GkrProver:
             assert kind == "JthRound"
             self.r.append(val)
 
+    def prove_layer(self, i: int, r_i: Sequence[int], challenges: Sequence[int]):
+        """The whole proof of layer i when the verifier's 2k public-coin challenges are known up front: the messages
+        start_round / round_msg(0..2k-1) would produce, from ONE library call (kernels launched back to back, two host
+        waits).  Returns (StartSumCheck message, raw device results); ``layer_messages`` turns the latter into the
+        reference's message sequence."""
+        F = self.F
+        k = self.circuit.num_vars_at(i + 1)
+        assert len(challenges) == 2 * k
+        pt = F.to_mont(list(r_i)) if len(r_i) else np.zeros((1, F.n), dtype=np.uint64)
+        rs = F.to_mont(list(challenges))
+        c1 = np.zeros((1, F.n), dtype=np.uint64)
+        ev = np.zeros((2 * k * 3, F.n), dtype=np.uint64)
+        qe = np.zeros((k + 1, F.n), dtype=np.uint64)
+        nv = C.c_uint32()
+        check(lib.scb_gkr_prover_prove_layer(self._h, i, api._p64(pt), api._p64(rs), 2 * k, api._p64(c1), api._p64(ev), api._p64(qe), k + 1, C.byref(nv)))
+        self.i, self.k, self.r = i, k, list(challenges)
+        self._c_1 = F.from_mont(c1)[0]
+        return ("StartSumCheck", self._c_1, i, nv.value), (ev, qe)
+
+    def layer_messages(self, raw):
+        """Raw sums of ``prove_layer`` -> [SumCheckProverMessage x (2k-1), FinalRoundMessage] (lib.rs:439-456)."""
+        F, k = self.F, self.k
+        ev, qe = raw
+        polys = [api.evals_to_univariate_mont(F, api.KIND_GKR_W, ev[3 * j:3 * j + 3]) for j in range(2 * k)]
+        q = api.evals_to_univariate_mont(F, api.KIND_GKR_W, qe)
+        return [("SumCheckProverMessage", pj) for pj in polys[:-1]] + [("FinalRoundMessage", polys[-1], q)]
+
 
 class GkrVerifier:
     """gkr_protocol::Verifier (gkr-protocol/src/lib.rs:38-218); ``rng.draw()`` stands in for F::rand(rng)."""
