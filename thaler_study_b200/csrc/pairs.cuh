@@ -580,20 +580,35 @@ __global__ void __launch_bounds__(kThreads, (K <= 2 ? 3 : 2))
                     block_reduce<A, NG>(ar, acc, sm);
                 }
             }
-            if (finisher && threadIdx.x == 0) {
-                const uint64_t hi = (uint64_t)(t + 1) << 32;
+            const uint64_t hi = (uint64_t)(t + 1) << 32;
+            if (finisher) {  // CTA-uniform.  The (K+1)^2 final reductions (64-bit modulo + REDC steps) run one per thread
                 const int n_out = grid_out ? NG : NP;
-                uint64_t w[NG][1];
+                if (threadIdx.x == 0) {
 #pragma unroll
-                for (int i = 0; i < NG; ++i) w[i][0] = ar.msg_final(acc[i], grid_out ? GridConsts<K>::msg_k : K);
-                if (peer.world > 1) {  // sharded prover: add the peer GPUs' sums of this pass (NVLink peer windows)
-                    PeerArg pa = peer;
-                    pa.seq += t;
-                    peer_exchange_sum<A, NG>(ar, pa, w);
+                    for (int i = 0; i < NG; ++i) sm[i] = acc[i];
                 }
+                __syncthreads();
+                if (threadIdx.x < NG) {
+                    const uint64_t v = ar.msg_final(sm[threadIdx.x], grid_out ? GridConsts<K>::msg_k : K);
+                    if (peer.world > 1) sm[NG + threadIdx.x] = v;
+                    else if ((int)threadIdx.x < n_out) st_sys(&mb->evals[threadIdx.x], hi | v);
+                }
+                if (peer.world > 1) {  // sharded prover: add the peer GPUs' sums of this pass (NVLink peer windows)
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        uint64_t w[NG][1];
 #pragma unroll
-                for (int i = 0; i < NG; ++i)
-                    if (i < n_out) st_sys(&mb->evals[i], hi | w[i][0]);
+                        for (int i = 0; i < NG; ++i) w[i][0] = sm[NG + i];
+                        PeerArg pa = peer;
+                        pa.seq += t;
+                        peer_exchange_sum<A, NG>(ar, pa, w);
+#pragma unroll
+                        for (int i = 0; i < NG; ++i)
+                            if (i < n_out) st_sys(&mb->evals[i], hi | w[i][0]);
+                    }
+                }
+            }
+            if (finisher && threadIdx.x == 0) {
                 st_sys(&mb->stamp[2 * t], globaltimer_ns());
                 int bad = 0;
                 if (t + 1 < n_passes) {
