@@ -424,14 +424,31 @@ struct PairCtx {
         for (uint32_t x = 0; x < np; ++x) ev[x] = F->add(H[x * np], H[x * np + 1]);
         emit(ev);
     }
+    // g'(Y) = H(r, Y) = sum_a L_a(r) H[a][Y] with the Lagrange basis on the nodes 0..np-1: L_a(r) =
+    // prod_{c != a} (r - c) / prod_{c != a} (a - c).  The np weights are computed once per message (prefix/suffix
+    // products, denominators inverted once per proof), then every column costs np multiplications.
+    std::vector<Fe> den_inv;  // 1 / prod_{c != a} (a - c)
     void emit_second(const std::vector<Fe>& H, const Fe& r) {
-        const InterpConsts& c = interp_consts(*F);
-        std::vector<Fe> ev(np), col(np);
+        if (den_inv.empty()) {
+            den_inv.resize(np);
+            for (uint32_t a = 0; a < np; ++a) {
+                Fe d = F->one();
+                for (uint32_t c = 0; c < np; ++c)
+                    if (c != a) d = F->mul(d, F->sub(F->from_u64(a), F->from_u64(c)));
+                den_inv[a] = F->inverse(d);
+            }
+        }
+        Fe diff[8], pre[9], suf[9], w[8];
+        for (uint32_t c = 0; c < np; ++c) diff[c] = F->sub(r, F->from_u64(c));
+        pre[0] = F->one();
+        for (uint32_t c = 0; c < np; ++c) pre[c + 1] = F->mul(pre[c], diff[c]);
+        suf[np] = F->one();
+        for (uint32_t c = np; c-- > 0;) suf[c] = F->mul(suf[c + 1], diff[c]);
+        for (uint32_t a = 0; a < np; ++a) w[a] = F->mul(F->mul(pre[a], suf[a + 1]), den_inv[a]);
+        std::vector<Fe> ev(np);
         for (uint32_t y = 0; y < np; ++y) {
-            for (uint32_t a = 0; a < np; ++a) col[a] = H[a * np + y];
-            const std::vector<Fe> coef = (np < 10 && !c.basis[np].empty()) ? lagrange_to_coeffs_cached(*F, c, col) : lagrange_to_coeffs(*F, col);
             Fe acc = F->zero();
-            for (size_t i = coef.size(); i-- > 0;) acc = F->add(F->mul(acc, r), coef[i]);
+            for (uint32_t a = 0; a < np; ++a) acc = F->add(acc, F->mul(w[a], H[a * np + y]));
             ev[y] = acc;
         }
         emit(ev);
