@@ -277,8 +277,8 @@ int scb_gkr_prover_round_evals(scb_gkr_prover* p, uint32_t j, const uint64_t* r_
 /* q = restrict_poly(b*, c*, W~_{i+1}) lib.rs:291-321 as its k+1 values at t = 0..k; r_final = the final random point */
 int scb_gkr_prover_restrict_evals(scb_gkr_prover* p, const uint64_t* r_final, uint64_t* out_evals, uint32_t cap, uint32_t* n_out);
 /* One whole layer proof with the verifier's 2k public-coin challenges rs[0..2k) handed over up front: equivalent to
- * start_round + round_evals(j, rs[j-1]) for j = 0..2k-1 + restrict_evals(rs[2k-1]), launched back to back (two host
- * waits per layer instead of one per round).  evals_out: 2k x 3 elements (sums at X = 0,1,2 per round); q_out: k+1. */
+ * start_round + round_evals(j, rs[j-1]) for j = 0..2k-1 + restrict_evals(rs[2k-1]); each phase is one cooperative
+ * launch with the challenges in device memory (one host wait per layer instead of one per round).  evals_out: 2k x 3 elements (sums at X = 0,1,2 per round); q_out: k+1. */
 int scb_gkr_prover_prove_layer(scb_gkr_prover* p, uint32_t i, const uint64_t* r_i, const uint64_t* rs, uint32_t n_rs, uint64_t* c_1_out,
                                uint64_t* evals_out, uint64_t* q_out, uint32_t cap_q, uint32_t* num_vars_out);
 

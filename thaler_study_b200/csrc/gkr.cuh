@@ -19,6 +19,7 @@
 #include <cstdint>
 
 #include "kernels.cuh"
+#include "persist.cuh"
 
 namespace scb {
 
@@ -81,9 +82,12 @@ template <class A>
 __global__ void __launch_bounds__(kThreads) k_gkr_phase2(FieldDesc f, EqPair eq_r, EqPair eq_u, const uint32_t* __restrict__ off1,
                                                          const uint32_t* __restrict__ idx1, const uint8_t* __restrict__ types,
                                                          const uint32_t* __restrict__ in0, ElemArg wu_arg, uint64_t* __restrict__ q,
-                                                         uint64_t* __restrict__ s, uint64_t n_c) {
+                                                         uint64_t* __restrict__ s, uint64_t n_c, const uint64_t* wu_dev = nullptr) {
     const A ar(f);
-    const typename A::El wu = ar.from_words(wu_arg.w);
+    uint64_t wu_w[A::N];  // W~(u): by value, or left in device memory by the previous kernel of a batched layer proof
+#pragma unroll
+    for (int i = 0; i < A::N; ++i) wu_w[i] = wu_dev ? __ldcg(wu_dev + i) : wu_arg.w[i];
+    const typename A::El wu = ar.from_words(wu_w);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_c; c += stride) {
         typename A::El sa = ar.zero(), sm = ar.zero();
@@ -180,6 +184,167 @@ __global__ void __launch_bounds__(kThreads) k_pqs_fold_round(FieldDesc f, const 
         pqs_accumulate(ar, v[0], v[1], v[2], acc);
     }
     grid_reduce_finish<A, 3>(ar, acc, partials, ticket, out);
+}
+
+// ---- all rounds of one P*Q + S sum-check in one cooperative launch, challenges known up front ----
+// Round 0 is the message of the tables as they are; round t >= 1 folds by challenges[t-1] and accumulates the next
+// message (the bodies of k_pqs_round / k_pqs_fold_round).  The CTAs meet at a ticket/flag barrier in device memory
+// between rounds (PersistCtl, persist.cuh); the CTA that takes the last ticket writes the three sums of the round to
+// its slot and releases the next round.  Nothing talks to the host: the launch is fully asynchronous.  Tables written
+// inside the kernel are read back through L2 (ld.global.cg).  final_fold: after the last message, P (two entries by
+// then) is folded by challenges[n_msgs-1] into out_final -- W~(u) for the second phase of a GKR layer.
+template <class A>
+__device__ __forceinline__ typename A::El ld_el_cg(const A& ar, const uint64_t* tab, uint64_t idx) {
+    uint64_t w[A::N];
+    ld_words_cg<A::N>(tab + idx * A::N, w);
+    return ar.from_words(w);
+}
+template <class A>
+constexpr int pqs_persist_blocks() {
+    return A::kLight ? 4 : (A::N == 1 ? 3 : 1);
+}
+template <class A>
+__global__ void __launch_bounds__(kThreads, (pqs_persist_blocks<A>()))
+    k_pqs_persist(FieldDesc f, const uint64_t* P0, const uint64_t* Q0, const uint64_t* S0, uint64_t* buf_a, uint64_t* buf_b,
+                  const uint64_t* challenges, uint32_t m, uint32_t n_msgs, int final_fold, uint64_t* out_slots, uint64_t* out_final, PersistCtl* ctl,
+                  uint64_t* partials) {
+    constexpr int N = A::N, AW = A::AW;
+    const A ar(f);
+    __shared__ uint64_t sm[32 * 3 * AW];
+    __shared__ int flag_sm;
+    const uint64_t cap_a = (m >= 1 ? (1ull << (m - 1)) : 1) * N, cap_b = (m >= 2 ? (1ull << (m - 2)) : 1) * N;  // words per table
+    bool have_release = true;  // round 0 needs no barrier; a CTA running alone needs none either
+    for (uint32_t t = 0; t < n_msgs; ++t) {
+        const uint32_t mt = t == 0 ? m : m - (t - 1);                        // variables of the tables this round reads
+        const uint64_t n_items = t == 0 ? (mt >= 1 ? 1ull << (mt - 1) : 1)  // pairs
+                                        : (mt >= 2 ? 1ull << (mt - 2) : 1); // quads
+        uint64_t active = (n_items + blockDim.x - 1) / blockDim.x;
+        if (active > gridDim.x) active = gridDim.x;
+        const bool solo = active == 1;
+        if (solo && blockIdx.x != 0) return;
+        if (!have_release) {
+            if (threadIdx.x == 0) {
+                const uint64_t t0 = globaltimer_ns();
+                int bad = 0;
+                for (;;) {
+                    uint64_t c;
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(c) : "l"(ctl->challenge) : "memory");
+                    if ((uint32_t)(c >> 32) == t) break;
+                    if (globaltimer_ns() - t0 > 2000000000ull) {  // a CTA died: do not hang the device
+                        bad = 1;
+                        break;
+                    }
+                }
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                flag_sm = bad ? 2 : 0;
+            }
+            __syncthreads();
+            if (flag_sm == 2) return;
+        }
+        typename A::Acc acc[3];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) ar.acc_zero(acc[x]);
+        if (blockIdx.x < active) {
+            const uint64_t start = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = active * blockDim.x;
+            if (t == 0) {
+                for (uint64_t i = start; i < n_items; i += stride) {
+                    const typename A::El p[2] = {ld_el(ar, P0, 2 * i), ld_el(ar, P0, 2 * i + 1)};
+                    const typename A::El q[2] = {ld_el(ar, Q0, 2 * i), ld_el(ar, Q0, 2 * i + 1)};
+                    const typename A::El s[2] = {ld_el(ar, S0, 2 * i), ld_el(ar, S0, 2 * i + 1)};
+                    pqs_accumulate(ar, p, q, s, acc);
+                }
+            } else {
+                uint64_t rw[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) rw[i] = __ldg(challenges + (size_t)(t - 1) * N + i);
+                const typename A::El r = ar.from_words(rw);
+                // t == 1 reads the inputs, then the buffers alternate: round t writes buf_a when t is odd
+                const uint64_t* in[3];
+                uint64_t* outp[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const uint64_t* src0 = k == 0 ? P0 : (k == 1 ? Q0 : S0);
+                    in[k] = t == 1 ? src0 : ((t & 1) ? buf_b + k * cap_b : buf_a + k * cap_a);
+                    outp[k] = (t & 1) ? buf_a + k * cap_a : buf_b + k * cap_b;
+                }
+                for (uint64_t i = start; i < n_items; i += stride) {
+                    typename A::El v[3][2];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            v[k][h] = ar.fold(ld_el_cg(ar, in[k], 4 * i + 2 * h), ld_el_cg(ar, in[k], 4 * i + 2 * h + 1), r);
+                            uint64_t o[N];
+                            ar.to_words(v[k][h], o);
+                            st_words<N>(outp[k] + (2 * i + h) * N, o);
+                        }
+                    }
+                    pqs_accumulate(ar, v[0], v[1], v[2], acc);
+                }
+            }
+            __threadfence();
+            block_reduce<A, 3>(ar, acc, sm);
+            bool finisher = solo;
+            if (!solo) {
+                if (threadIdx.x == 0) {
+#pragma unroll
+                    for (int x = 0; x < 3; ++x) {
+                        uint64_t w[AW];
+                        ar.acc_to_words(acc[x], w);
+#pragma unroll
+                        for (int i = 0; i < AW; ++i) __stcg(&partials[((size_t)blockIdx.x * 3 + x) * AW + i], w[i]);
+                    }
+                    __threadfence();
+                    const unsigned int tk = atomicAdd(&ctl->ticket[t], 1u);
+                    flag_sm = (tk == (unsigned int)active - 1) ? 1 : 0;
+                }
+                __syncthreads();
+                finisher = flag_sm == 1;
+                if (finisher) {
+                    __threadfence();
+#pragma unroll
+                    for (int x = 0; x < 3; ++x) ar.acc_zero(acc[x]);
+                    for (unsigned int b = threadIdx.x; b < (unsigned int)active; b += blockDim.x) {
+#pragma unroll
+                        for (int x = 0; x < 3; ++x) {
+                            uint64_t w[AW];
+#pragma unroll
+                            for (int i = 0; i < AW; ++i) w[i] = __ldcg(&partials[((size_t)b * 3 + x) * AW + i]);
+                            typename A::Acc o;
+                            ar.acc_from_words(o, w);
+                            ar.acc_merge(acc[x], o);
+                        }
+                    }
+                    block_reduce<A, 3>(ar, acc, sm);
+                }
+            }
+            if (finisher && threadIdx.x == 0) {
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    uint64_t w[N];
+                    ar.to_words(ar.acc_final(acc[x]), w);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) out_slots[((size_t)t * 3 + x) * N + i] = w[i];
+                }
+                if (t + 1 < n_msgs) {
+                    if (!solo) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(ctl->challenge), "l"((uint64_t)(t + 1) << 32) : "memory");
+                } else {
+                    if (final_fold) {  // the tables have one variable left: P~ = P[0] + r (P[1] - P[0])
+                        uint64_t rw[N], o[N];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) rw[i] = __ldg(challenges + (size_t)t * N + i);
+                        const uint64_t* pl = t == 0 ? P0 : ((t & 1) ? buf_a : buf_b);
+                        ar.to_words(ar.fold(ld_el_cg(ar, pl, 0), ld_el_cg(ar, pl, 1), ar.from_words(rw)), o);
+#pragma unroll
+                        for (int i = 0; i < N; ++i) out_final[i] = o[i];
+                    }
+                    __threadfence_system();
+                }
+            }
+            if (solo) __syncthreads();  // this CTA's stores are ordered before its next loads
+        }
+        have_release = solo;
+    }
 }
 
 }  // namespace scb
