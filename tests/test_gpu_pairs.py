@@ -99,6 +99,16 @@ def test_pair_kernel_matches_one_round_per_pass():
         "    print(b''.join(T.generate_transcript(T.Prover(g))).hex())\n"
         "    a = T.DenseMultilinearExtension.synthetic(F, v, 7); b = T.DenseMultilinearExtension.synthetic(F, v, 8)\n"
         "    print(b''.join(T.generate_transcript(T.Prover(T.MatMulG.from_tables(a, b)))).hex())\n"
+        # accumulator head-room: the largest p below 2^28, > 16 thread-iterations per pass (so the periodic fold runs)
+        # and the stored-word pattern [0, 0, p-1, p-1] that maximises every lazy grid value (5p-3 for K = 3)
+        "import numpy as np, hashlib\n"
+        "p = 268435399; F = T.Field(p)\n"
+        "for v, K in ((24, 3), (23, 4), (23, 2), (22, 1)):\n"
+        "    pat = np.tile(np.array([0, 0, p - 1, p - 1], dtype=np.uint64), (1 << v) // 4)\n"
+        "    g = T.ProductMLE.new([T.DenseMultilinearExtension.from_evaluations_vec(F, v, pat) for _ in range(K)])\n"
+        "    print(hashlib.sha256(b''.join(T.generate_transcript(T.Prover(g)))).hexdigest())\n"
+        "    g = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, 30 + k) for k in range(K)])\n"
+        "    print(hashlib.sha256(b''.join(T.generate_transcript(T.Prover(g)))).hexdigest())\n"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
     outs = []
     for env_add in ({"SCB_PAIRS": "0", "SCB_TAIL_VARS": "0"}, {"SCB_PAIRS": "0"}, {}, {"SCB_PAIR_BPS": "1"}, {"SCB_PAIR_RESIDENT": "0"},
@@ -107,5 +117,5 @@ def test_pair_kernel_matches_one_round_per_pass():
         outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600))
     for o in outs:
         assert o.returncode == 0, o.stderr[-2000:]
-    assert len(outs[0].stdout.split()) == 18
+    assert len(outs[0].stdout.split()) == 26
     assert len(set(o.stdout for o in outs)) == 1
