@@ -6,6 +6,7 @@
 // transcript bytes (interpolation, zero-term handling, serialization, SHA-256 hash-to-field) is host code
 // here, exactly where the reference keeps it.  In a Rust build this file is replaced by the reference's own
 // crates; it exists so that the path is complete and testable without a Rust toolchain.
+#include <atomic>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -378,7 +379,27 @@ struct TailCtx {
     uint32_t np;  // sums per round
     std::vector<uint64_t> used;  // challenges consumed by the tail's folds, in order (n limbs each)
 };
-static bool g_tail_disabled = false;
+// A resident kernel that loses lock-step with the host (a profiler that serialises kernel and host, or a host thread
+// that was descheduled for longer than the kernel's 250 ms patience) costs a quarter of a second before the per-round
+// fallback takes over.  After such a failure the resident kernels are skipped for a number of proofs that doubles with
+// every consecutive failure (8, 16, ... 4096): a profiler pays the stall a handful of times per run, a one-off hiccup
+// costs eight slower proofs.  Sharded provers must take the same path on every rank, so they disable for good.
+static std::atomic<uint32_t> g_resident_skip{0}, g_resident_backoff{8};
+static bool g_resident_off = false;
+static bool resident_allowed(bool begin_proof) {
+    if (g_resident_off) return false;
+    uint32_t s = g_resident_skip.load();
+    if (s == 0) return true;
+    if (begin_proof) g_resident_skip.store(s - 1);
+    return false;
+}
+static void resident_failed(bool sharded) {
+    if (sharded) g_resident_off = true;
+    const uint32_t b = g_resident_backoff.load();
+    g_resident_skip.store(b);
+    g_resident_backoff.store(b < 4096 ? b * 2 : b);
+}
+static void resident_succeeded() { g_resident_backoff.store(8); }
 // one tail round on the host: sums -> message polynomial -> bytes -> hash chain -> next challenge
 static int tail_round_cb(void* user, uint32_t t, const uint64_t* evals, uint64_t* next_r) {
     TailCtx* tc = (TailCtx*)user;
@@ -493,7 +514,8 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
     offsets[1] = hash_input.size();
     const bool product = p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G;
     uint32_t j = 1;
-    if (p->have_grid && !g_tail_disabled && p->num_vars >= 2 && pair_passes_ok(p->g)) {
+    const bool resident_ok = resident_allowed(true);  // one decision per proof
+    if (p->have_grid && resident_ok && p->num_vars >= 2 && pair_passes_ok(p->g)) {
         // two rounds per pass: g_2 comes from Prover::new's grid, then every pass of the resident kernel folds two
         // variables and returns the grid for the next two messages.  Invariant at the top of the loop: p->g is folded
         // by used[0 .. size-2), the last two challenges are the pair the next pass folds by, and the messages for
@@ -547,11 +569,12 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
             }
         }
         if (rc != SCB_OK && rc != SCB_ETAIL) return rc;
+        if (rc == SCB_OK && resident) resident_succeeded();
         j = pc.msgs;
         if (rc == SCB_ETAIL) {
             // lock-step lost (e.g. a profiler serialises kernel and host): keep the messages that are out, fold the
             // tables by the challenges they were derived with and carry on with one launch per round
-            if (resident) g_tail_disabled = true;
+            if (resident) resident_failed(p->peers != nullptr);
             scb_poly* refolded = nullptr;
             RC_TRY(scb_poly_fix_variables(p->g, pc.used.data() + base, (uint32_t)(j - 1 - base), &refolded));
             scb_poly_free(p->g);
@@ -563,7 +586,7 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
         RC_TRY(maybe_consolidate(p));
         uint32_t live = 0;  // variables of the table about to be folded
         RC_TRY(scb_poly_num_vars(p->g, &live));
-        if (product && !g_tail_disabled && live >= 2 && resident_rounds_ok(p->g, p->sharded)) {
+        if (product && resident_ok && resident_allowed(false) && live >= 2 && resident_rounds_ok(p->g, p->sharded)) {
             // all remaining rounds (sharded: all rounds up to the consolidation point, with the per-round exchange
             // inside the kernel) in one resident kernel, challenges through a mailbox
             TailCtx tc{&F, p->kind, &hash_input, &chain, offsets, j, p->np, {}};
@@ -580,6 +603,7 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
                 rc = scb_poly_resident_rounds(p->g, rw, p->np, max_rounds, tail_round_cb, &tc, &done, was_sharded ? &folded : nullptr);
             }
             if (rc == SCB_OK) {
+                resident_succeeded();
                 if (!was_sharded) break;
                 scb_poly_free(p->g);  // carry on from the slab the kernel left behind: consolidation comes next
                 p->g = folded;
@@ -589,7 +613,7 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
             if (rc != SCB_ETAIL) return rc;
             // lock-step lost (e.g. a profiler serialises kernel and host): keep what was done, fold the tables by the
             // challenges already consumed and carry on with one launch per round
-            g_tail_disabled = true;
+            resident_failed(p->peers != nullptr);
             if (done > 0) {
                 scb_poly* refolded = nullptr;
                 RC_TRY(scb_poly_fix_variables(p->g, tc.used.data(), done, &refolded));
