@@ -1452,12 +1452,12 @@ extern "C" int scb_poly_grid_evals(const scb_poly* p, uint64_t* out_elems) {
                 auto kern = k_grid_sp_tma<K, true>;
                 const size_t smem = tma_ring_bytes<K, 2>();
                 RC_TRY(allow_smem(kern, smem));
-                kern<<<c->sms * 2, kThreads + 32, smem, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
+                kern<<<c->sms * 3, kThreads + 32, smem, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
             } else {
                 auto kern = k_grid_sp_tma<K, false>;
                 const size_t smem = tma_ring_bytes<K, 4>();
                 RC_TRY(allow_smem(kern, smem));
-                kern<<<c->sms * 2, kThreads + 32, smem, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
+                kern<<<c->sms * 3, kThreads + 32, smem, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
             }
         } else if (pair_staging()) {
             if (in32) {

@@ -340,7 +340,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  : "memory");
 }
 
-constexpr int kTmaStages = 4;
+constexpr int kTmaStages = 3;
 template <int K, int WPT>
 constexpr size_t tma_ring_bytes() {
     return (size_t)kTmaStages * K * kThreads * WPT * 8;
@@ -348,7 +348,7 @@ constexpr size_t tma_ring_bytes() {
 
 // K6a'  grid of a table as it is, TMA-staged.  blockDim = kThreads compute threads + one producer warp.
 template <int K, bool IN32>
-__global__ void __launch_bounds__(kThreads + 32, 2)
+__global__ void __launch_bounds__(kThreads + 32, 3)
     k_grid_sp_tma(FieldDesc f, TabsIn<K> in, uint64_t n_groups, uint64_t* partials, unsigned int* ticket, uint64_t* out, PeerArg peer) {
     constexpr int NG = (K + 1) * (K + 1), WPT = IN32 ? 2 : 4, S = kTmaStages;
     constexpr uint32_t TILE_B = kThreads * WPT * 8;  // bytes per table and stage
