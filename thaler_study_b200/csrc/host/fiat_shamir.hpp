@@ -15,7 +15,61 @@
 
 #include "hostfield.hpp"
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <cpuid.h>
+#include <immintrin.h>
+#define SCB_SHA_NI 1
+#endif
+
 namespace scb {
+
+#ifdef SCB_SHA_NI
+// SHA-256 compression with the x86 SHA extensions (same function as Sha256::compress_scalar; chosen at run time).
+// The challenge derivation sits on the prover's critical path once the tables are small: two hash-to-field
+// evaluations per turn-around of the resident kernels.
+inline bool sha_ni_available() {
+    static const bool ok = [] {
+        unsigned a = 0, b = 0, c = 0, d = 0;
+        if (!__get_cpuid_count(7, 0, &a, &b, &c, &d)) return false;
+        const bool sha = (b >> 29) & 1;
+        if (!__get_cpuid(1, &a, &b, &c, &d)) return false;
+        const bool ssse3 = (c >> 9) & 1, sse41 = (c >> 19) & 1;
+        return sha && ssse3 && sse41;
+    }();
+    return ok;
+}
+__attribute__((target("sha,sse4.1,ssse3"))) inline void sha256_compress_ni(uint32_t state[8], const uint8_t* blk, const uint32_t* k) {
+    const __m128i mask = _mm_set_epi64x(0x0c0d0e0f08090a0bULL, 0x0405060700010203ULL);
+    __m128i tmp = _mm_loadu_si128((const __m128i*)&state[0]);  // d c b a
+    __m128i st1 = _mm_loadu_si128((const __m128i*)&state[4]);  // h g f e
+    tmp = _mm_shuffle_epi32(tmp, 0xB1);                        // c d a b
+    st1 = _mm_shuffle_epi32(st1, 0x1B);                        // e f g h
+    __m128i st0 = _mm_alignr_epi8(tmp, st1, 8);                // a b e f
+    st1 = _mm_blend_epi16(st1, tmp, 0xF0);                     // c d g h
+    const __m128i save0 = st0, save1 = st1;
+    __m128i m[4];
+    for (int g = 0; g < 16; ++g) {
+        if (g < 4) {
+            m[g] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(blk + 16 * g)), mask);
+        } else {  // W[4g..4g+3] from the previous sixteen words
+            const __m128i x0 = m[g & 3], x1 = m[(g + 1) & 3], x2 = m[(g + 2) & 3], x3 = m[(g + 3) & 3];
+            m[g & 3] = _mm_sha256msg2_epu32(_mm_add_epi32(_mm_sha256msg1_epu32(x0, x1), _mm_alignr_epi8(x3, x2, 4)), x3);
+        }
+        __m128i msg = _mm_add_epi32(m[g & 3], _mm_loadu_si128((const __m128i*)(k + 4 * g)));
+        st1 = _mm_sha256rnds2_epu32(st1, st0, msg);
+        msg = _mm_shuffle_epi32(msg, 0x0E);
+        st0 = _mm_sha256rnds2_epu32(st0, st1, msg);
+    }
+    st0 = _mm_add_epi32(st0, save0);
+    st1 = _mm_add_epi32(st1, save1);
+    tmp = _mm_shuffle_epi32(st0, 0x1B);         // f e b a
+    st1 = _mm_shuffle_epi32(st1, 0xB1);         // d c h g
+    st0 = _mm_blend_epi16(tmp, st1, 0xF0);      // d c b a
+    st1 = _mm_alignr_epi8(st1, tmp, 8);         // h g f e
+    _mm_storeu_si128((__m128i*)&state[0], st0);
+    _mm_storeu_si128((__m128i*)&state[4], st1);
+}
+#endif
 
 class Sha256 {
    public:
@@ -42,14 +96,17 @@ class Sha256 {
         }
     }
     void finalize(uint8_t out[32]) {
-        uint64_t bitlen = len_ * 8;
-        uint8_t pad = 0x80;
-        update(&pad, 1);
-        uint8_t z = 0;
-        while (fill_ != 56) update(&z, 1);
-        uint8_t lb[8];
-        for (int i = 0; i < 8; ++i) lb[i] = (uint8_t)(bitlen >> (56 - 8 * i));
-        update(lb, 8);
+        const uint64_t bitlen = len_ * 8;
+        buf_[fill_++] = 0x80;
+        if (fill_ > 56) {
+            std::memset(buf_ + fill_, 0, 64 - fill_);
+            compress(buf_);
+            fill_ = 0;
+        }
+        std::memset(buf_ + fill_, 0, 56 - fill_);
+        for (int i = 0; i < 8; ++i) buf_[56 + i] = (uint8_t)(bitlen >> (56 - 8 * i));
+        compress(buf_);
+        fill_ = 0;
         for (int i = 0; i < 8; ++i) {
             out[4 * i] = (uint8_t)(h_[i] >> 24);
             out[4 * i + 1] = (uint8_t)(h_[i] >> 16);
@@ -61,7 +118,7 @@ class Sha256 {
    private:
     static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
     void compress(const uint8_t* blk) {
-        static const uint32_t k[64] = {
+        alignas(16) static const uint32_t k[64] = {
             0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
             0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
             0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147,
@@ -69,6 +126,12 @@ class Sha256 {
             0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08,
             0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
             0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+#ifdef SCB_SHA_NI
+        if (use_ni_) {
+            sha256_compress_ni(h_, blk, k);
+            return;
+        }
+#endif
         uint32_t w[64];
         for (int i = 0; i < 16; ++i)
             w[i] = ((uint32_t)blk[4 * i] << 24) | ((uint32_t)blk[4 * i + 1] << 16) | ((uint32_t)blk[4 * i + 2] << 8) | blk[4 * i + 3];
@@ -93,6 +156,12 @@ class Sha256 {
     uint64_t len_;
     uint8_t buf_[64];
     size_t fill_;
+#ifdef SCB_SHA_NI
+    bool use_ni_ = sha_ni_available();
+
+   public:
+    void force_scalar(bool on) { use_ni_ = !on && sha_ni_available(); }  // tests: both code paths must agree
+#endif
 };
 
 // [ARK] ExpanderXmd::expand (block_size = Z_pad length)

@@ -489,7 +489,7 @@ static int pair_pass_cb(void* user, uint32_t, uint32_t n_vals, const uint64_t* v
     const Fe ra = pc->next_challenge();
     pc->emit_second(v, ra);
     const Fe rb = pc->next_challenge();
-    uint64_t w[kHostMaxLimbs];
+    uint64_t w[kHostMaxLimbs] = {0};
     F.store(ra, w);
     next_pair[0] = w[0];
     F.store(rb, w);
