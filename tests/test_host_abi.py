@@ -105,3 +105,37 @@ def test_domain4_interpolation_equals_lagrange_on_0_1_2():
             dom = O.interpolate_domain4(OF, [f(e) for e in O.domain4_elements(OF)])
             lag = O.lagrange_to_coeffs(OF, [f(0), f(1), f(2)])
             assert dom == lag
+
+
+def test_sha256_scalar_and_sha_extension_paths_agree():
+    """host/fiat_shamir.hpp picks the x86 SHA-extension compression at run time; SCB_SHA_SCALAR=1 forces the portable
+    one.  Both must give the same hash_to_field values (and the in-process values are pinned to the oracle above)."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import ctypes as C, numpy as np\n"
+        "import thaler_study_b200 as T\n"
+        "from thaler_study_b200._lib import lib\n"
+        "for p in (5, 389, 1572869, 0xFFFFFFFF00000001, %d):\n"
+        "    F = T.Field(p)\n"
+        "    for n in (0, 1, 19, 55, 56, 63, 64, 65, 119, 120, 300, 1000):\n"
+        "        msg = bytes((i * 31 + n) & 255 for i in range(n))\n"
+        "        print(F.hash_to_field(msg))\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), O.BLS12_381_FR.p)
+    outs = [subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SCB_SHA_SCALAR=v), capture_output=True, text=True, timeout=300)
+            for v in ("0", "1")]
+    for o in outs:
+        assert o.returncode == 0, o.stderr[-2000:]
+    assert outs[0].stdout == outs[1].stdout and len(outs[0].stdout.split()) == 60
+    # and against the oracle (hashlib)
+    vals = outs[0].stdout.split()
+    i = 0
+    for p in (5, 389, 1572869, 0xFFFFFFFF00000001, O.BLS12_381_FR.p):
+        OF = O.Field(p)
+        for n in (0, 1, 19, 55, 56, 63, 64, 65, 119, 120, 300, 1000):
+            msg = bytes((j * 31 + n) & 255 for j in range(n))
+            assert int(vals[i]) == O.hash_to_field(OF, msg), (p, n)
+            i += 1

@@ -10,6 +10,7 @@
 // oracle restates the same published algorithm on top of hashlib and must agree byte for byte.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -29,6 +30,8 @@ namespace scb {
 // evaluations per turn-around of the resident kernels.
 inline bool sha_ni_available() {
     static const bool ok = [] {
+        const char* off = std::getenv("SCB_SHA_SCALAR");  // tests: force the portable compression function
+        if (off && off[0] == '1') return false;
         unsigned a = 0, b = 0, c = 0, d = 0;
         if (!__get_cpuid_count(7, 0, &a, &b, &c, &d)) return false;
         const bool sha = (b >> 29) & 1;
