@@ -119,3 +119,98 @@ def test_pair_kernel_matches_one_round_per_pass():
         assert o.returncode == 0, o.stderr[-2000:]
     assert len(outs[0].stdout.split()) == 26
     assert len(set(o.stdout for o in outs)) == 1
+
+
+# ----------------------------------------------------------------------------- the resident-kernel entry points, directly
+def _mont1(F, x):
+    return int(F.to_mont([x])[0, 0])
+
+
+@pytest.mark.parametrize("OF,v,K,max_rounds", [(O.FP1572869, 16, 3, 0), (O.FP1572869, 17, 2, 5), (O.Field(0xFFFFFFFF00000001), 15, 3, 0),
+                                               (O.FP389, 9, 4, 0), (O.BLS12_381_FR, 15, 2, 7)], ids=lambda x: str(getattr(x, "bits", x)))
+def test_resident_rounds_callback_api(OF, v, K, max_rounds):
+    """scb_poly_resident_rounds with a caller-supplied challenge callback (what a Rust generate_transcript with its own
+    hashing would do): the sums handed to the callback and the folded polynomial it returns equal the ones
+    scb_poly_fix_and_round_evals produces round by round with the same challenges."""
+    import ctypes as C
+
+    import numpy as np
+
+    from thaler_study_b200 import _lib
+    from thaler_study_b200._lib import check, lib
+
+    F = T.Field(OF.p)
+    rnd = random.Random(v * 131 + K)
+    g = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, 400 + k) for k in range(K)])
+    n_rounds = v - 1 if max_rounds == 0 else max_rounds
+    ch = [rnd.randrange(OF.p) for _ in range(n_rounds + 1)]
+    want, cur = [], g
+    for j in range(n_rounds):
+        cur, ev = cur.fix_and_round_evals(ch[j])
+        want.append(ev)
+    got = []
+    N, npts = F.n, K + 1
+
+    def cb(user, rnd_idx, evals, next_out):
+        arr = np.ctypeslib.as_array(evals, shape=(npts * N,)).copy().reshape(npts, N)
+        got.append(F.from_mont(arr))
+        nxt = F.elem(ch[rnd_idx + 1])
+        for i in range(N):
+            next_out[i] = int(nxt.reshape(-1)[i])
+        return 0
+
+    done = C.c_uint32()
+    folded = C.c_void_p()
+    check(lib.scb_poly_resident_rounds(g._h, T.api._p64(F.elem(ch[0])), npts, max_rounds, _lib.ROUND_CB(cb), None, C.byref(done), C.byref(folded)))
+    assert done.value == n_rounds and got == want
+    out = type(g)(F, folded)
+    assert out.num_vars() == v - n_rounds
+    assert [out.table(k).to_evaluations() for k in range(K)] == [cur.table(k).to_evaluations() for k in range(K)]
+
+
+@pytest.mark.parametrize("OF,v,K,max_passes", [(O.FP1572869, 16, 3, 0), (O.FP1572869, 15, 2, 3), (O.Field(268435399), 12, 4, 0), (O.FP5, 7, 1, 0)],
+                         ids=lambda x: str(getattr(x, "bits", x)))
+def test_resident_pairs_callback_api(OF, v, K, max_passes):
+    """scb_poly_resident_pairs with a caller-supplied callback: every grid equals scb_poly_pair_pass's (and the
+    oracle's definition through it), the line of an odd tail equals the ordinary round sums."""
+    import ctypes as C
+
+    import numpy as np
+
+    from thaler_study_b200 import _lib
+    from thaler_study_b200._lib import check, lib
+
+    F = T.Field(OF.p)
+    rnd = random.Random(v * 17 + K)
+    g = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, 500 + k) for k in range(K)])
+    all_passes = (v - 1) // 2
+    n_passes = all_passes if max_passes == 0 else max_passes
+    pairs = [(rnd.randrange(OF.p), rnd.randrange(OF.p)) for _ in range(n_passes + 1)]
+    want, cur = [], g
+    for t in range(n_passes):
+        if cur.num_vars() >= 4:
+            cur, H = cur.pair_pass(*pairs[t])
+            want.append([x for row in H for x in row])
+        else:  # three variables: fold two, one left -> its line sums
+            cur = cur.fix_variables(list(pairs[t]))
+            want.append(cur.round_evals())
+    got = []
+    npts = K + 1
+
+    def cb(user, pass_idx, n_vals, vals, next_pair):
+        arr = np.ctypeslib.as_array(vals, shape=(n_vals,)).copy().reshape(n_vals, 1)
+        got.append(F.from_mont(arr))
+        a, b = pairs[pass_idx + 1]
+        next_pair[0] = _mont1(F, a)
+        next_pair[1] = _mont1(F, b)
+        return 0
+
+    done = C.c_uint32()
+    folded = C.c_void_p()
+    check(lib.scb_poly_resident_pairs(g._h, T.api._p64(F.elem(pairs[0][0])), T.api._p64(F.elem(pairs[0][1])), max_passes, _lib.PAIR_CB(cb), None,
+                                      C.byref(done), C.byref(folded)))
+    assert done.value == n_passes and got == want
+    out = type(g)(F, folded)
+    assert out.num_vars() == v - 2 * n_passes
+    if out.num_vars() >= 1:
+        assert [out.table(k).to_evaluations() for k in range(K)] == [cur.table(k).to_evaluations() for k in range(K)]

@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, (K <= 2 ? 3 : 2))
                 else if (use_stage) pair_pass_sp_staged<K>(ar, stage_smem, ra, rb, src, dst, n_groups, start, stride, acc);
                 else if (t == 0) pair_pass_sp<K, true, true, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);
                 else pair_pass_sp<K, true, false, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);
-            } else if (start == 0) {  // 8 entries per table -> 2 -> line sums; nothing reads the folded pair again
+            } else if (start == 0) {  // 8 entries per table -> 2 -> line sums
                 uint32_t prod[NP];
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
@@ -551,6 +551,7 @@ __global__ void __launch_bounds__(kThreads, (K <= 2 ? 3 : 2))
                     }
                     const uint32_t u0 = ar.fold_c(ar.fold_c(e[0], e[1], ra), ar.fold_c(e[2], e[3], ra), rb);
                     const uint32_t u1 = ar.fold_c(ar.fold_c(e[4], e[5], ra), ar.fold_c(e[6], e[7], ra), rb);
+                    __stcg(dst[k], (uint64_t)u0 | ((uint64_t)u1 << 32));  // the folded pair, for out_folded
                     pair_into_prod<A, NP>(ar, k == 0, u0, u1, prod);
                 }
 #pragma unroll
