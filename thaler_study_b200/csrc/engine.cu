@@ -1165,535 +1165,8 @@ extern "C" int scb_poly_to_evaluations(const scb_poly* p, uint64_t* out, size_t 
     return SCB_OK;
 }
 
-// ------------------------------------------------------------------------------------------ persistent tail
-// Runs ALL remaining rounds of a product polynomial (m = num_vars >= 2 -> m-1 rounds) in one resident kernel
-// (tail.cuh).  For round t the callback receives the n_points sums and returns the next challenge.
-// Resident-kernel thresholds (variables of the table about to be folded):
-//   m <= SCB_TAIL_VARS (14)               single-CTA tail (tail.cuh); 0 disables both resident kernels
-//   SCB_PERSIST_VARS (15) <= m <= limit   grid-wide resident kernel (persist.cuh); 0 disables it.  The limit is 32 for
-//                                         the small-prime policy (HBM-bound: saves launch + ramp per round) and
-//                                         SCB_PERSIST_MAX_GENERIC (22) for the integer-bound policies, whose big
-//                                         rounds run faster in the leaner per-round kernels.
-static uint32_t env_u32(const char* name, uint32_t dflt) { return getenv(name) ? (uint32_t)atoi(getenv(name)) : dflt; }
-static uint32_t tail_max_vars() {
-    static const uint32_t v = env_u32("SCB_TAIL_VARS", 14);
-    return v > 24 ? 24 : v;
-}
-static uint32_t persist_min_vars() {
-    static const uint32_t v = env_u32("SCB_PERSIST_VARS", 15);
-    return v == 0 ? 1000 : (v < 4 ? 4 : v);
-}
-static uint32_t persist_max_vars(uint32_t policy) {
-    static const uint32_t g = env_u32("SCB_PERSIST_MAX_GENERIC", 22);
-    return policy == POL_SP ? 32 : (g > kTailMaxRounds + 1 ? kTailMaxRounds + 1 : g);
-}
-bool scb::resident_rounds_ok(const scb_poly* p, bool need_grid) {
-    if (!p || !(p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) || p->t.empty()) return false;
-    const uint32_t m = p->t[0].nv, tv = tail_max_vars();
-    if (tv < 2 || m < 2) return false;
-    if (m <= tv && m < persist_min_vars()) return !need_grid;
-    Ctx* c;
-    if (get_ctx(&c) != SCB_OK || !c->coop) return false;
-    return m >= persist_min_vars() && m <= persist_max_vars(p->f->policy);
-}
-// Measurements of the resident kernels since the last reset: CUDA-event time of every launch (on the launching
-// stream) and, for the last grid-wide launch, the per-round device stamps (%globaltimer).
-struct ResidentStats {
-    uint64_t launches = 0;
-    double total_ms = 0.0;
-    uint32_t last_rounds = 0;
-    double work_us[kTailMaxRounds + 1] = {0}, turn_us[kTailMaxRounds + 1] = {0};
-};
-static ResidentStats g_res_stats;
-static std::mutex g_res_mu;
-extern "C" int scb_resident_stats(uint64_t* launches, double* total_kernel_ms, uint32_t* last_rounds, double* last_work_us,
-                                  double* last_turn_us, uint32_t cap) {
-    std::lock_guard<std::mutex> lk(g_res_mu);
-    if (launches) *launches = g_res_stats.launches;
-    if (total_kernel_ms) *total_kernel_ms = g_res_stats.total_ms;
-    if (last_rounds) *last_rounds = g_res_stats.last_rounds;
-    for (uint32_t t = 0; t < cap && t < g_res_stats.last_rounds; ++t) {
-        if (last_work_us) last_work_us[t] = g_res_stats.work_us[t];
-        if (last_turn_us) last_turn_us[t] = g_res_stats.turn_us[t];
-    }
-    return SCB_OK;
-}
-extern "C" void scb_resident_stats_reset(void) {
-    std::lock_guard<std::mutex> lk(g_res_mu);
-    g_res_stats = ResidentStats();
-}
-extern "C" int scb_poly_tail_rounds(const scb_poly* p, const uint64_t* r_first, uint32_t n_points, scb_round_cb cb, void* user,
-                                    uint32_t* rounds_done) {
-    return scb_poly_resident_rounds(p, r_first, n_points, 0, cb, user, rounds_done, nullptr);
-}
-extern "C" int scb_poly_resident_rounds(const scb_poly* p, const uint64_t* r_first, uint32_t n_points, uint32_t max_rounds, scb_round_cb cb,
-                                        void* user, uint32_t* rounds_done, scb_poly** out_folded) {
-    ARG_TRY(p && r_first && cb && rounds_done, "null argument");
-    *rounds_done = 0;
-    if (out_folded) *out_folded = nullptr;
-    ARG_TRY(p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G, "the persistent tail handles product polynomials only");
-    ARG_TRY(n_points == poly_n_points(p), "n_points must be the full message size");
-    const uint32_t m = p->t[0].nv;
-    ARG_TRY(m >= 2 && m <= kTailMaxRounds + 1, "resident rounds need 2..33 variables");
-    Ctx* c;
-    RC_TRY(get_ctx(&c));
-    const FieldImpl& f = *p->f;
-    const uint32_t N = f.d.n, n_rounds = (max_rounds == 0 || max_rounds > m - 1) ? m - 1 : max_rounds;
-    ARG_TRY(f.policy != POL_SP || m <= 32, "table too large for the small-prime path");
-    ARG_TRY(elem_canonical(f, r_first), "challenge is not a canonical field element");
-    // tables above 2^persist_min_vars() entries use the grid-wide kernel (persist.cuh), smaller ones a single CTA
-    const bool grid_wide = m >= persist_min_vars() && c->coop != 0;
-    if (!grid_wide && m > 24) {
-        set_error("the single-CTA tail takes at most 24 variables");
-        return SCB_ETAIL;  // caller falls back to one launch per round
-    }
-    const bool exchanging = g_cur_peers && g_cur_peers->world > 1;
-    ARG_TRY(grid_wide || !exchanging, "sharded rounds need the grid-wide resident kernel");
-    const size_t esz = f.policy == POL_SP ? 4 : (size_t)8 * N;  // internal ping-pong buffers (packed for small primes)
-    std::vector<BufRef> ba(p->t.size()), bb(p->t.size());
-    for (size_t k = 0; k < p->t.size(); ++k) {
-        RC_TRY(alloc_buf(std::max<size_t>(esz << (m - 1), 32), &ba[k]));
-        RC_TRY(alloc_buf(std::max<size_t>(esz << (m >= 3 ? m - 2 : 1), 32), &bb[k]));
-    }
-    TailMailbox* mb = c->mailbox;
-    std::memset((void*)mb, 0, sizeof(TailMailbox));
-    std::atomic_thread_fence(std::memory_order_seq_cst);
-    const ElemArg ra = elem_arg(f, r_first);
-    uint64_t timeout_ns = 250ull * 1000 * 1000;  // normal host turn-around is microseconds
-    const int in_w32 = p->t[0].p32 ? 1 : 0;
-    if (grid_wide) CU_TRY(cudaMemsetAsync(c->persist_ctl, 0, sizeof(PersistCtl), g_stream));
-    CU_TRY(cudaEventRecord(c->ev0, g_stream));
-    if (grid_wide) {
-        cudaError_t le = cudaSuccess;
-        DISPATCH_POLICY(f.policy, DISPATCH_K(p->t.size(), {
-            TabsIn<K> in;
-            TabsOut<K> oa, ob;
-            for (int k = 0; k < K; ++k) {
-                in.p[k] = p->t[k].buf->ptr;
-                oa.p[k] = ba[k]->ptr;
-                ob.p[k] = bb[k]->ptr;
-            }
-            auto kern = k_persist_rounds<A, K>;
-            int nb = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, 0) != cudaSuccess || nb < 1) nb = 1;
-            if (nb > persist_blocks<A, K>()) nb = persist_blocks<A, K>();
-            int grid = c->sms * nb;
-            if (grid > kMaxGrid) grid = kMaxGrid;
-            FieldDesc fd = f.d;
-            ElemArg rr = ra;
-            uint32_t mm = m, nr = n_rounds;
-            int w32 = in_w32;
-            PersistCtl* ctl = c->persist_ctl;
-            uint64_t* parts = c->partials;
-            PeerArg pa = peer_arg(c);  // exchange numbers pa.seq .. pa.seq + n_rounds - 1, one per round
-            if (exchanging) g_cur_peers->seq += n_rounds - 1;
-            void* args[] = {&fd, &in, &oa, &ob, &rr, &mm, &nr, &w32, &mb, &ctl, &parts, &timeout_ns, &pa};
-            le = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), args, 0, g_stream);
-        }));
-        if (le != cudaSuccess) {
-            cudaGetLastError();
-            set_error("cooperative launch failed: %s", cudaGetErrorString(le));
-            return SCB_ECUDA;
-        }
-    } else {
-        DISPATCH_POLICY(f.policy, DISPATCH_K(p->t.size(), {
-            TabsIn<K> in;
-            TabsOut<K> oa, ob;
-            for (int k = 0; k < K; ++k) {
-                in.p[k] = p->t[k].buf->ptr;
-                oa.p[k] = ba[k]->ptr;
-                ob.p[k] = bb[k]->ptr;
-            }
-            k_tail_rounds<A, K><<<1, tail_threads<A>(), 0, g_stream>>>(f.d, in, oa, ob, ra, m, n_rounds, mb, timeout_ns, in_w32);
-        }));
-    }
-    LAUNCH_CHECK();
-    CU_TRY(cudaEventRecord(c->ev1, g_stream));
-    int rc = SCB_OK;
-    uint64_t evals[kMaxPts * kMaxLimbs], next_r[kMaxLimbs];
-    // mailbox words are self-validating: (tag << 32) | 32-bit payload, one word per limb for the small-prime policy
-    // (values < 2^32), two otherwise (tail.cuh)
-    const uint32_t H = f.policy == POL_SP ? 1 : 2, n_words = n_points * N;
-    for (uint32_t t = 0; t < n_rounds && rc == SCB_OK; ++t) {
-        const uint64_t tag = (uint64_t)t + 1;
-        uint64_t spins = 0;
-        for (;;) {
-            bool ready = true;
-            for (uint32_t i = 0; i < n_words * H; ++i) {
-                if ((mb->evals[i] >> 32) != tag) {
-                    ready = false;
-                    break;
-                }
-            }
-            if (ready) break;
-            if (mb->dev_status == 2) {
-                set_error("the resident kernel lost lock-step with the host (serialising profiler?)");
-                rc = SCB_ETAIL;
-                break;
-            }
-            if ((++spins & 0xFFFFF) == 0) {  // every ~1M polls make sure the kernel is still alive
-                cudaError_t q = cudaStreamQuery(g_stream);
-                if (q != cudaErrorNotReady) {
-                    set_error("resident kernel ended early: %s", cudaGetErrorString(q));
-                    rc = q == cudaSuccess ? SCB_ETAIL : SCB_ECUDA;
-                    break;
-                }
-            }
-        }
-        if (rc != SCB_OK) break;
-        for (uint32_t i = 0; i < n_words; ++i) {
-            if (H == 1) evals[i] = (uint32_t)mb->evals[i];
-            else evals[i] = (uint64_t)(uint32_t)mb->evals[2 * i] | (mb->evals[2 * i + 1] << 32);
-        }
-        rc = cb(user, t, evals, next_r);
-        if (rc != SCB_OK) break;
-        *rounds_done = t + 1;
-        if (t + 1 < n_rounds) {
-            if (!elem_canonical(f, next_r)) {
-                set_error("challenge is not a canonical field element");
-                rc = SCB_EINVAL;
-                break;
-            }
-            for (uint32_t i = 0; i < N; ++i) {
-                if (H == 1) {
-                    mb->challenge[i] = (tag << 32) | (uint32_t)next_r[i];
-                } else {
-                    mb->challenge[2 * i] = (tag << 32) | (uint32_t)next_r[i];
-                    mb->challenge[2 * i + 1] = (tag << 32) | (next_r[i] >> 32);
-                }
-            }
-        }
-    }
-    if (rc != SCB_OK) {
-        mb->challenge[0] = (uint64_t)kMbAbortTag << 32;
-        std::atomic_thread_fence(std::memory_order_seq_cst);
-    }
-    cudaError_t e = cudaStreamSynchronize(g_stream);
-    if (e == cudaSuccess && rc == SCB_OK) {
-        float ms = 0.f;
-        std::lock_guard<std::mutex> lk(g_res_mu);
-        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) {
-            g_res_stats.launches += 1;
-            g_res_stats.total_ms += ms;
-        }
-        if (grid_wide) {  // per-round device time up to "sums posted" and host turn-around, microseconds
-            g_res_stats.last_rounds = n_rounds;
-            for (uint32_t t = 0; t < n_rounds; ++t) {
-                g_res_stats.work_us[t] = (double)(mb->stamp[2 * t] - (t == 0 ? mb->stamp[2 * kTailMaxRounds + 1] : mb->stamp[2 * t - 1])) * 1e-3;
-                g_res_stats.turn_us[t] = t + 1 < n_rounds ? (double)(mb->stamp[2 * t + 1] - mb->stamp[2 * t]) * 1e-3 : 0.0;
-            }
-        }
-    }
-    static const bool trace = getenv("SCB_PERSIST_TRACE") && atoi(getenv("SCB_PERSIST_TRACE")) != 0;
-    if (trace && grid_wide && rc == SCB_OK) {
-        fprintf(stderr, "[persist m=%u]", m);
-        for (uint32_t t = 0; t < n_rounds; ++t) fprintf(stderr, " %.1f/%.1f", g_res_stats.work_us[t], g_res_stats.turn_us[t]);
-        fprintf(stderr, "\n");
-    }
-    if (e != cudaSuccess && rc == SCB_OK) {
-        set_error("tail kernel failed: %s", cudaGetErrorString(e));
-        rc = SCB_ECUDA;
-    }
-    if (rc == SCB_OK && exchanging) rc = peers_check(c);
-    if (rc == SCB_OK && out_folded) {  // the tables after n_rounds folds: what the last round wrote
-        auto q = std::make_unique<scb_poly>(*p);
-        const bool in_b = ((n_rounds - 1) & 1) != 0;
-        for (size_t k = 0; k < p->t.size(); ++k) {
-            Table tk;
-            tk.nv = m - n_rounds;
-            tk.buf = in_b ? bb[k] : ba[k];
-            tk.p32 = f.policy == POL_SP;
-            if (tk.p32 && !p->allow_packed) RC_TRY(unpack_table(c, f, tk, &q->t[k]));
-            else q->t[k] = tk;
-        }
-        *out_folded = q.release();
-    }
-    return rc;
-}
-
-// ------------------------------------------------------------------------------------------ two rounds per pass
-// pairs.cuh: small-prime policy, product polynomials.  SCB_PAIRS=0 switches the scheme off.
-// SCB_PAIR_STAGE=1: the pair kernels prefetch the next iteration's tiles into shared memory with cp.async
-// (measured slower than plain 256-bit loads on B200 for these integer-bound passes, profiles/r01_pairs.md)
-static bool pair_staging() {
-    static const bool on = env_u32("SCB_PAIR_STAGE", 0) != 0;
-    return on;
-}
-bool scb::pair_passes_ok(const scb_poly* p) {
-    static const bool on = env_u32("SCB_PAIRS", 1) != 0;
-    if (!on || !p || !(p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) || p->t.empty()) return false;
-    if (p->f->policy != POL_SP || p->t[0].nv < 2 || p->t[0].nv > 32) return false;
-    if (tail_max_vars() < 2 || persist_min_vars() > 64) return false;  // resident kernels disabled
-    Ctx* c;
-    return get_ctx(&c) == SCB_OK && c->coop != 0;
-}
-// (K+1)^2 sums H[a][b] = sum_x'' prod_k f_k(a, b, x''), a-major, over the two lowest variables
-extern "C" int scb_poly_grid_evals(const scb_poly* p, uint64_t* out_elems) {
-    ARG_TRY(p && out_elems, "null argument");
-    ARG_TRY(p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G, "grid sums are defined for product polynomials");
-    ARG_TRY(p->f->policy == POL_SP, "grid sums are implemented for the small-prime policy");
-    ARG_TRY(p->t[0].nv >= 2 && p->t[0].nv <= 32, "need 2..32 variables");
-    Ctx* c;
-    RC_TRY(get_ctx(&c));
-    const FieldImpl& f = *p->f;
-    const uint64_t n_groups = p->t[0].len() / 4;
-    const bool in32 = p->t[0].p32;
-    const uint32_t NP = (uint32_t)p->t.size() + 1;
-    const PeerArg pa = peer_arg(c);  // sharded prover: the finishing thread adds the peer GPUs' grid sums
-    DISPATCH_K(p->t.size(), {
-        TabsIn<K> in;
-        for (int k = 0; k < K; ++k) {
-            ARG_TRY(p->t[k].p32 == in32, "tables of one polynomial must share a layout");
-            in.p[k] = p->t[k].buf->ptr;
-        }
-        static const bool use_tma = env_u32("SCB_GRID_TMA", 0) != 0;
-        if (use_tma) {
-            if (in32) {
-                auto kern = k_grid_sp_tma<K, true>;
-                const size_t smem = tma_ring_bytes<K, 2>();
-                RC_TRY(allow_smem(kern, smem));
-                kern<<<c->sms * 3, kThreads + 32, smem, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
-            } else {
-                auto kern = k_grid_sp_tma<K, false>;
-                const size_t smem = tma_ring_bytes<K, 4>();
-                RC_TRY(allow_smem(kern, smem));
-                kern<<<c->sms * 3, kThreads + 32, smem, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
-            }
-        } else if (pair_staging()) {
-            if (in32) {
-                auto kern = k_grid_sp<K, true, true>;
-                const size_t smem = Stager<K, 2>::bytes(kThreads);
-                RC_TRY(allow_smem(kern, smem));
-                kern<<<occ_grid(c, kern, n_groups, smem), kThreads, smem, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
-            } else {
-                auto kern = k_grid_sp<K, false, true>;
-                const size_t smem = Stager<K, 4>::bytes(kThreads);
-                RC_TRY(allow_smem(kern, smem));
-                kern<<<occ_grid(c, kern, n_groups, smem), kThreads, smem, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
-            }
-        } else if (in32) {
-            auto kern = k_grid_sp<K, true, false>;
-            kern<<<occ_grid(c, kern, n_groups), kThreads, 0, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
-        } else {
-            auto kern = k_grid_sp<K, false, false>;
-            kern<<<occ_grid(c, kern, n_groups), kThreads, 0, g_stream>>>(f.d, in, n_groups, c->partials, c->ticket, c->h_res, pa);
-        }
-    });
-    LAUNCH_CHECK();
-    CU_TRY(cudaStreamSynchronize(g_stream));
-    RC_TRY(peers_check(c));
-    std::memcpy(out_elems, c->h_res, (size_t)8 * NP * NP);
-    return SCB_OK;
-}
-// one pair pass as its own launch: fold the two lowest variables by (ra, rb), grid sums of the folded table
-extern "C" int scb_poly_pair_pass(const scb_poly* p, const uint64_t* ra, const uint64_t* rb, scb_poly** out, uint64_t* out_elems) {
-    ARG_TRY(p && ra && rb && out && out_elems, "null argument");
-    ARG_TRY(p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G, "pair passes are defined for product polynomials");
-    ARG_TRY(p->f->policy == POL_SP, "pair passes are implemented for the small-prime policy");
-    ARG_TRY(p->t[0].nv >= 4 && p->t[0].nv <= 32, "need 4..32 variables");
-    Ctx* c;
-    RC_TRY(get_ctx(&c));
-    const FieldImpl& f = *p->f;
-    ARG_TRY(elem_canonical(f, ra) && elem_canonical(f, rb), "challenge is not a canonical field element");
-    const uint64_t n_groups = p->t[0].len() / 16;
-    const bool in32 = p->t[0].p32;
-    const uint32_t NP = (uint32_t)p->t.size() + 1;
-    auto q = std::make_unique<scb_poly>(*p);
-    q->allow_packed = true;  // the folded tables are packed uint32; other entry points unpack on entry
-    for (size_t k = 0; k < p->t.size(); ++k) {
-        ARG_TRY(p->t[k].p32 == in32, "tables of one polynomial must share a layout");
-        q->t[k].nv = p->t[k].nv - 2;
-        q->t[k].buf.reset();
-        q->t[k].p32 = true;
-        RC_TRY(alloc_buf((size_t)4 << q->t[k].nv, &q->t[k].buf));
-    }
-    const ElemArg a = elem_arg(f, ra), b = elem_arg(f, rb);
-    DISPATCH_K(p->t.size(), {
-        TabsIn<K> in;
-        TabsOut<K> o;
-        for (int k = 0; k < K; ++k) {
-            in.p[k] = p->t[k].buf->ptr;
-            o.p[k] = q->t[k].buf->ptr;
-        }
-        if (in32 && pair_staging()) {
-            auto kern = k_pair_pass_sp<K, true, true>;
-            const size_t smem = pair_stage_bytes<K>();
-            RC_TRY(allow_smem(kern, smem));
-            kern<<<occ_grid(c, kern, n_groups, smem), kThreads, smem, g_stream>>>(f.d, in, o, a, b, n_groups, c->partials, c->ticket, c->h_res);
-        } else if (in32) {
-            auto kern = k_pair_pass_sp<K, true, false>;
-            kern<<<occ_grid(c, kern, n_groups), kThreads, 0, g_stream>>>(f.d, in, o, a, b, n_groups, c->partials, c->ticket, c->h_res);
-        } else {
-            auto kern = k_pair_pass_sp<K, false, false>;
-            kern<<<occ_grid(c, kern, n_groups), kThreads, 0, g_stream>>>(f.d, in, o, a, b, n_groups, c->partials, c->ticket, c->h_res);
-        }
-    });
-    LAUNCH_CHECK();
-    CU_TRY(cudaStreamSynchronize(g_stream));
-    std::memcpy(out_elems, c->h_res, (size_t)8 * NP * NP);
-    *out = q.release();
-    return SCB_OK;
-}
-// All pair passes of a proof in one resident kernel (k_persist_pairs_sp).  `p` has m >= 3 variables; pass t folds two
-// variables by challenge pair t ((ra, rb) first, then what the callback returned) and hands the callback the grid
-// ((K+1)^2 values, folded table still has >= 2 variables) or the line ((K+1) values, exactly one variable left).
-extern "C" int scb_poly_resident_pairs(const scb_poly* p, const uint64_t* ra, const uint64_t* rb, uint32_t max_passes, scb_pair_cb cb,
-                                       void* user, uint32_t* passes_done, scb_poly** out_folded) {
-    ARG_TRY(p && ra && rb && cb && passes_done, "null argument");
-    *passes_done = 0;
-    if (out_folded) *out_folded = nullptr;
-    ARG_TRY(p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G, "pair passes are defined for product polynomials");
-    ARG_TRY(p->f->policy == POL_SP, "pair passes are implemented for the small-prime policy");
-    const uint32_t m = p->t[0].nv;
-    ARG_TRY(m >= 3 && m <= 32, "need 3..32 variables");
-    Ctx* c;
-    RC_TRY(get_ctx(&c));
-    const FieldImpl& f = *p->f;
-    ARG_TRY(elem_canonical(f, ra) && elem_canonical(f, rb), "challenge is not a canonical field element");
-    if (!c->coop) {
-        set_error("cooperative launches are not supported on this device");
-        return SCB_ETAIL;
-    }
-    const uint32_t all_passes = (m - 2 + 1) / 2, NP = (uint32_t)p->t.size() + 1;
-    const uint32_t n_passes = (max_passes == 0 || max_passes > all_passes) ? all_passes : max_passes;
-    const bool exchanging = g_cur_peers && g_cur_peers->world > 1;
-    ARG_TRY(!exchanging || m >= 2 * n_passes + 2, "sharded pair passes must leave two local variables (grid sums)");
-    std::vector<BufRef> ba(p->t.size()), bb(p->t.size());
-    for (size_t k = 0; k < p->t.size(); ++k) {
-        ARG_TRY(p->t[k].p32 == p->t[0].p32, "tables of one polynomial must share a layout");
-        RC_TRY(alloc_buf(std::max<size_t>((size_t)4 << (m - 2), 32), &ba[k]));
-        RC_TRY(alloc_buf(std::max<size_t>((size_t)4 << (m >= 4 ? m - 4 : 0), 32), &bb[k]));
-    }
-    TailMailbox* mb = c->mailbox;
-    std::memset((void*)mb, 0, sizeof(TailMailbox));
-    std::atomic_thread_fence(std::memory_order_seq_cst);
-    uint64_t timeout_ns = 250ull * 1000 * 1000;
-    CU_TRY(cudaMemsetAsync(c->persist_ctl, 0, sizeof(PersistCtl), g_stream));
-    CU_TRY(cudaEventRecord(c->ev0, g_stream));
-    cudaError_t le = cudaSuccess;
-    DISPATCH_K(p->t.size(), {
-        TabsIn<K> in;
-        TabsOut<K> oa, ob;
-        for (int k = 0; k < K; ++k) {
-            in.p[k] = p->t[k].buf->ptr;
-            oa.p[k] = ba[k]->ptr;
-            ob.p[k] = bb[k]->ptr;
-        }
-        auto kern = k_persist_pairs_sp<K>;
-        int use_stage = pair_staging() ? 1 : 0;
-        const size_t smem = use_stage ? pair_stage_bytes<K>() : 0;
-        RC_TRY(allow_smem(kern, smem));
-        int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
-        static const int bps_env = (int)env_u32("SCB_PAIR_BPS", 0);
-        if (bps_env > 0 && bps_env < nb) nb = bps_env;
-        int grid = c->sms * nb;
-        if (grid > kMaxGrid) grid = kMaxGrid;
-        FieldDesc fd = f.d;
-        ElemArg a = elem_arg(f, ra), b = elem_arg(f, rb);
-        uint32_t mm = m, np_ = n_passes;
-        int w32 = p->t[0].p32 ? 1 : 0;
-        PersistCtl* ctl = c->persist_ctl;
-        uint64_t* parts = c->partials;
-        PeerArg pa = peer_arg(c);  // exchange numbers pa.seq .. pa.seq + n_passes - 1, one per pass
-        if (exchanging) g_cur_peers->seq += n_passes - 1;
-        void* args[] = {&fd, &in, &oa, &ob, &a, &b, &mm, &np_, &w32, &mb, &ctl, &parts, &timeout_ns, &use_stage, &pa};
-        le = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), args, smem, g_stream);
-    });
-    if (le != cudaSuccess) {
-        cudaGetLastError();
-        set_error("cooperative launch failed: %s", cudaGetErrorString(le));
-        return SCB_ETAIL;  // caller falls back to one launch per round
-    }
-    LAUNCH_CHECK();
-    CU_TRY(cudaEventRecord(c->ev1, g_stream));
-    int rc = SCB_OK;
-    uint64_t vals[kMaxGridPts], next_pair[2];
-    uint32_t mt = m;
-    for (uint32_t t = 0; t < n_passes && rc == SCB_OK; ++t, mt -= 2) {
-        const uint64_t tag = (uint64_t)t + 1;
-        const uint32_t n_vals = mt >= 4 ? NP * NP : NP;
-        uint64_t spins = 0;
-        for (;;) {
-            bool ready = true;
-            for (uint32_t i = 0; i < n_vals; ++i) {
-                if ((mb->evals[i] >> 32) != tag) {
-                    ready = false;
-                    break;
-                }
-            }
-            if (ready) break;
-            if (mb->dev_status == 2) {
-                set_error("the resident kernel lost lock-step with the host (serialising profiler?)");
-                rc = SCB_ETAIL;
-                break;
-            }
-            if ((++spins & 0xFFFFF) == 0) {
-                cudaError_t q = cudaStreamQuery(g_stream);
-                if (q != cudaErrorNotReady) {
-                    set_error("resident kernel ended early: %s", cudaGetErrorString(q));
-                    rc = q == cudaSuccess ? SCB_ETAIL : SCB_ECUDA;
-                    break;
-                }
-            }
-        }
-        if (rc != SCB_OK) break;
-        for (uint32_t i = 0; i < n_vals; ++i) vals[i] = (uint32_t)mb->evals[i];
-        rc = cb(user, t, n_vals, vals, next_pair);
-        if (rc != SCB_OK) break;
-        *passes_done = t + 1;
-        if (t + 1 < n_passes) {
-            if (!elem_canonical(f, next_pair) || !elem_canonical(f, next_pair + 1)) {
-                set_error("challenge is not a canonical field element");
-                rc = SCB_EINVAL;
-                break;
-            }
-            mb->challenge[0] = (tag << 32) | (uint32_t)next_pair[0];
-            mb->challenge[1] = (tag << 32) | (uint32_t)next_pair[1];
-        }
-    }
-    if (rc != SCB_OK) {
-        mb->challenge[0] = (uint64_t)kMbAbortTag << 32;
-        std::atomic_thread_fence(std::memory_order_seq_cst);
-    }
-    cudaError_t e = cudaStreamSynchronize(g_stream);
-    if (e == cudaSuccess && rc == SCB_OK) {
-        float ms = 0.f;
-        std::lock_guard<std::mutex> lk(g_res_mu);
-        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) {
-            g_res_stats.launches += 1;
-            g_res_stats.total_ms += ms;
-        }
-        g_res_stats.last_rounds = n_passes;
-        for (uint32_t t = 0; t < n_passes; ++t) {
-            g_res_stats.work_us[t] = (double)(mb->stamp[2 * t] - (t == 0 ? mb->stamp[2 * kTailMaxRounds + 1] : mb->stamp[2 * t - 1])) * 1e-3;
-            g_res_stats.turn_us[t] = t + 1 < n_passes ? (double)(mb->stamp[2 * t + 1] - mb->stamp[2 * t]) * 1e-3 : 0.0;
-        }
-        static const bool trace = getenv("SCB_PERSIST_TRACE") && atoi(getenv("SCB_PERSIST_TRACE")) != 0;
-        if (trace) {
-            fprintf(stderr, "[pairs m=%u]", m);
-            for (uint32_t t = 0; t < n_passes; ++t) fprintf(stderr, " %.1f/%.1f", g_res_stats.work_us[t], g_res_stats.turn_us[t]);
-            fprintf(stderr, "\n");
-        }
-    }
-    if (e != cudaSuccess && rc == SCB_OK) {
-        set_error("resident kernel failed: %s", cudaGetErrorString(e));
-        rc = SCB_ECUDA;
-    }
-    if (rc == SCB_OK && exchanging) rc = peers_check(c);
-    if (rc == SCB_OK && out_folded) {  // the tables after n_passes two-variable folds: what the last pass wrote
-        auto q = std::make_unique<scb_poly>(*p);
-        q->allow_packed = true;
-        const bool in_b = ((n_passes - 1) & 1) != 0;
-        for (size_t k = 0; k < p->t.size(); ++k) {
-            q->t[k].nv = m - 2 * n_passes;
-            q->t[k].buf = in_b ? bb[k] : ba[k];
-            q->t[k].p32 = true;
-        }
-        *out_folded = q.release();
-    }
-    return rc;
-}
+// ------------------------------------------------------------------------------------------ resident kernels, pair passes
+#include "resident_engine.inc"
 
 // ------------------------------------------------------------------------------------------ peers API
 __global__ void __launch_bounds__(kThreads) k_peer_publish(PeerArg pa, const uint4* __restrict__ src, uint64_t n16, uint64_t dst_byte_off) {
