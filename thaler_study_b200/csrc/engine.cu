@@ -595,6 +595,48 @@ static int eval_table(Ctx* c, const FieldImpl& f, const Table& t, const uint64_t
     return SCB_OK;
 }
 
+// T evaluations of one table, points in host memory as pts[t][j][limb] (coordinate j bound to index bit j): one
+// kernel builds all eq tables, then one pass over the table per chunk of TC points.  d_out (device or mapped host
+// memory) receives T elements; nothing waits.  Falls back to T single evaluations for shapes the staged tables do not fit.
+static int eval_table_multi(Ctx* c, const FieldImpl& f, const Table& t, const uint64_t* pts, uint32_t T, uint64_t* d_out) {
+    const uint32_t v = t.nv, N = f.d.n;
+    const uint32_t cap_bits = N == 1 ? 12 : 10;
+    const uint32_t TC = N == 1 ? 8 : 2;
+    uint32_t lb = v / 2;
+    while (lb > 0 && ((size_t)TC * 8 * N << lb) > 64 * 1024) --lb;  // TC low tables in 64 KB of shared memory
+    if (v < 2 || lb < 1 || v - lb > cap_bits || t.p32) {
+        for (uint32_t i = 0; i < T; ++i) RC_TRY(eval_table(c, f, t, pts + (size_t)i * v * N, nullptr, d_out + (size_t)i * N));
+        return SCB_OK;
+    }
+    for (size_t i = 0; i < (size_t)T * v; ++i) ARG_TRY(elem_canonical(f, pts + i * N), "point coordinate is not canonical");
+    BufRef d_pts, lo, hi;
+    RC_TRY(alloc_buf((size_t)T * v * N * 8, &d_pts));
+    RC_TRY(alloc_buf(((size_t)T * 8 * N) << lb, &lo));
+    RC_TRY(alloc_buf(((size_t)T * 8 * N) << (v - lb), &hi));
+    CU_TRY(cudaMemcpyAsync(d_pts->ptr, pts, (size_t)T * v * N * 8, cudaMemcpyHostToDevice, g_stream));
+    const size_t eq_smem = (size_t)8 * N << cap_bits;
+    DISPATCH_POLICY(f.policy, {
+        auto kern = k_eq_tables_multi<A>;
+        RC_TRY(allow_smem(kern, eq_smem));
+        kern<<<2 * T, 1024, eq_smem, g_stream>>>(f.d, d_pts->ptr, lb, v, lo->ptr, hi->ptr);
+    });
+    LAUNCH_CHECK();
+    const uint64_t n = t.len();
+    for (uint32_t t0 = 0; t0 < T; t0 += TC) {
+        const uint32_t np = T - t0 < TC ? T - t0 : TC;
+        const size_t smem = ((size_t)np * 8 * N) << lb;
+        DISPATCH_POLICY(f.policy, {
+            constexpr int KTC = A::N == 1 ? 8 : 2;
+            auto kern = k_mle_dot_multi<A, KTC>;
+            RC_TRY(allow_smem(kern, ((size_t)KTC * 8 * N) << lb));
+            kern<<<grid_for(c, n), kThreads, smem, g_stream>>>(f.d, t.buf->ptr, lo->ptr + (((size_t)t0 << lb) * N), hi->ptr + (((size_t)t0 << (v - lb)) * N),
+                                                              lb, v, np, n, c->partials, c->ticket, d_out + (size_t)t0 * N);
+        });
+        LAUNCH_CHECK();
+    }
+    return SCB_OK;
+}
+
 extern "C" int scb_mle_evaluate(const scb_mle* m, const uint64_t* point, uint32_t n_point, uint64_t* out_elem) {
     ARG_TRY(m && out_elem && (point || n_point == 0), "null argument");
     ARG_TRY(n_point == m->t.nv, "point dimension does not match num_vars");

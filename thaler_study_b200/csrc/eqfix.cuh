@@ -64,6 +64,80 @@ __global__ void __launch_bounds__(1024) k_eq_tables(FieldDesc f, PointArg pt, ui
     }
 }
 
+// Same for T points at once (coordinates in device memory, pts[t][j] bound to index bit j): block 2t builds point t's
+// low table, block 2t+1 its high table; both must fit shared memory (lb, v - lb <= cap_bits).  Tables are stored
+// point-major: lo_all[t << lb ...], hi_all[t << (v - lb) ...].
+template <class A>
+__global__ void __launch_bounds__(1024) k_eq_tables_multi(FieldDesc f, const uint64_t* __restrict__ pts, uint32_t lb, uint32_t v, uint64_t* lo_all,
+                                                          uint64_t* hi_all) {
+    constexpr int N = A::N;
+    extern __shared__ uint64_t eq_sm[];
+    const A ar(f);
+    const uint32_t t = blockIdx.x >> 1, half_id = blockIdx.x & 1;
+    const uint32_t first = half_id == 0 ? 0 : lb;
+    const uint32_t nb = half_id == 0 ? lb : v - lb;
+    uint64_t* out = half_id == 0 ? lo_all + ((size_t)t << lb) * N : hi_all + ((size_t)t << (v - lb)) * N;
+    const uint64_t* coords = pts + (size_t)t * v * N;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) eq_sm[i] = f.one[i];
+    }
+    __syncthreads();
+    for (uint32_t l = 0; l < nb; ++l) {
+        uint64_t cw[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) cw[i] = __ldg(coords + (size_t)(first + l) * N + i);
+        const typename A::El c = ar.from_words(cw);
+        const uint32_t half = 1u << l;
+        for (uint32_t i = threadIdx.x; i < half; i += blockDim.x) {
+            typename A::El cur = ar.from_words(eq_sm + (size_t)i * N);
+            typename A::El hi = ar.mul(cur, c);
+            ar.to_words(hi, eq_sm + (size_t)(i + half) * N);
+            ar.to_words(ar.sub(cur, hi), eq_sm + (size_t)i * N);
+        }
+        __syncthreads();
+    }
+    const uint64_t words = ((uint64_t)N) << nb;
+    for (uint64_t i = threadIdx.x; i < words; i += blockDim.x) out[i] = eq_sm[i];
+}
+
+// TC evaluations of ONE table in one pass: out[t] = sum_i evals[i] * lo_t[i & (2^lb - 1)] * hi_t[i >> lb].  The TC low
+// tables are staged in shared memory; every entry of the table is loaded once and used TC times (restrict_poly needs
+// k + 1 evaluations of the same W along a line, gkr-protocol/src/lib.rs:291-321).
+template <class A, int TC>
+__global__ void __launch_bounds__(kThreads) k_mle_dot_multi(FieldDesc f, const uint64_t* __restrict__ evals, const uint64_t* __restrict__ lo_all,
+                                                            const uint64_t* __restrict__ hi_all, uint32_t lb, uint32_t v, uint32_t n_pts, uint64_t n,
+                                                            uint64_t* partials, unsigned int* ticket, uint64_t* out) {
+    constexpr int N = A::N;
+    extern __shared__ uint64_t lo_sm[];
+    const A ar(f);
+    const uint64_t lo_words = ((uint64_t)n_pts << lb) * N;
+    for (uint64_t i = threadIdx.x; i < lo_words; i += blockDim.x) lo_sm[i] = lo_all[i];
+    __syncthreads();
+    typename A::Acc acc[TC];
+#pragma unroll
+    for (int t = 0; t < TC; ++t) ar.acc_zero(acc[t]);
+    const uint64_t mask = (1ull << lb) - 1;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t w[N];
+        ld_words<N>(evals + i * N, w);
+        const typename A::Lz e = ar.lz(ar.from_words(w));
+        const uint64_t il = i & mask, ih = i >> lb;
+#pragma unroll
+        for (int t = 0; t < TC; ++t) {
+            if (t < (int)n_pts) {
+                uint64_t hw[N];
+#pragma unroll
+                for (int q = 0; q < N; ++q) hw[q] = __ldg(hi_all + (((size_t)t << (v - lb)) + ih) * N + q);
+                const typename A::Lz m = ar.lz_mul(e, ar.lz(ar.from_words(lo_sm + (((size_t)t << lb) + il) * N)));
+                ar.acc_add(acc[t], ar.lz_mul(m, ar.lz(ar.from_words(hw))));
+            }
+        }
+    }
+    grid_reduce_finish<A, TC>(ar, acc, partials, ticket, out);
+}
+
 // out[j] = sum_{i < 2^m} eq[i] * t[j * 2^m + i]      (the LOW m variables fixed); one warp per output
 template <class A>
 __global__ void __launch_bounds__(kThreads) k_fix_low_eq(FieldDesc f, const uint64_t* __restrict__ tab, const uint64_t* __restrict__ eq,
