@@ -283,7 +283,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel
     # Small-prime fields (the default workload): two rounds per pass (csrc/pairs.cuh).  A proof is two launches:
-    # k_grid_sp (Prover::new: the (K+1)^2 grid sums that yield c_1, g_1 and g_2) and the resident k_persist_pairs_sp
+    # k_grid_sp_pf (Prover::new: the (K+1)^2 grid sums that yield c_1, g_1 and g_2) and the resident k_persist_pairs_sp
     # (every later round; pass t folds two variables and accumulates the next grid).  The resident kernel is the
     # dominant one; it is timed with CUDA events around its launch, on its stream, inside the timed region above,
     # and its first pass (the one that streams the full tables) with %globaltimer stamps inside the kernel.
@@ -326,7 +326,7 @@ def run_ours(args):
                                 "bytes": pbytes[0], "source": "%globaltimer stamps inside the kernel, last launch"},
                 "pass0_alone_traffic": 7.241953e9 if std else None,
                 "latency_us": {"host_turnaround_total": sum(res_stats["turn_us"]), "passes_after_0_total": sum(res_stats["work_us"][1:])},
-                "grid_kernel_alone": {"kernel": "k_grid_sp<3,in=u64> (Prover::new), 2^%d-entry tables" % v, "kernel_ms": gms,
+                "grid_kernel_alone": {"kernel": "k_grid_sp_pf<3> (Prover::new; u64 input, register double buffer), 2^%d-entry tables" % v, "kernel_ms": gms,
                                       "achieved": grid_bytes / (gms * 1e-3) / 1e9, "frac": grid_bytes / (gms * 1e-3) / 1e9 / peak,
                                       "algorithmic_bytes_per_launch": grid_bytes, "traffic": 6.457139e9 if std else None,
                                       "share_of_step": gms / ms},
