@@ -112,7 +112,7 @@ def test_pair_kernel_matches_one_round_per_pass():
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
     outs = []
     for env_add in ({"SCB_PAIRS": "0", "SCB_TAIL_VARS": "0"}, {"SCB_PAIRS": "0"}, {}, {"SCB_PAIR_BPS": "1"}, {"SCB_PAIR_RESIDENT": "0"},
-                    {"SCB_PAIR_STAGE": "1"}, {"SCB_GRID_TMA": "1"}, {"SCB_GRID_PF": "0"}):
+                    {"SCB_PAIR_STAGE": "1"}, {"SCB_GRID_TMA": "1"}, {"SCB_GRID_PF": "0"}, {"SCB_PAIR_PIPE": "0"}):
         env = dict(os.environ, **env_add)
         outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600))
     for o in outs:

@@ -164,6 +164,57 @@ __device__ __forceinline__ void pair_pass_sp(const PolSP& ar, const PolSP::FoldC
     grid_canon<K>(ar, c32, acc);
 }
 
+// Pair pass over 8-byte tables with the loads software-pipelined across tables: while table k's 16 entries are folded,
+// the 128 bytes of the next table (or of table 0 of the next thread-iteration) are already in flight.  Two raw
+// buffers alternate; PAR says which one holds table 0 (it flips every iteration when K is odd), so all register-array
+// indices are compile-time.
+template <int K, int PAR>
+__device__ __forceinline__ void pair_pipe_step(const PolSP& ar, const PolSP::FoldC ra, const PolSP::FoldC rb, const uint64_t* const (&src)[K],
+                                               uint64_t* const (&dst)[K], uint64_t g, uint64_t g_next, bool has_next, uint64_t (&w)[2][16],
+                                               uint64_t (&acc)[(K + 1) * (K + 1)]) {
+    uint32_t c[K][4];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int cur = (k + PAR) & 1, nxt = cur ^ 1;
+        if (k + 1 < K) ld_words<16>(src[k + 1 < K ? k + 1 : 0] + g * 16, w[nxt]);
+        else if (has_next) ld_words<16>(src[0] + g_next * 16, w[nxt]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t lo = ar.fold_c((uint32_t)w[cur][4 * q], (uint32_t)w[cur][4 * q + 1], ra);
+            const uint32_t hi = ar.fold_c((uint32_t)w[cur][4 * q + 2], (uint32_t)w[cur][4 * q + 3], ra);
+            c[k][q] = ar.fold_c(lo, hi, rb);
+        }
+        uint64_t o[2] = {(uint64_t)c[k][0] | ((uint64_t)c[k][1] << 32), (uint64_t)c[k][2] | ((uint64_t)c[k][3] << 32)};
+        st_words<2>(dst[k] + g * 2, o);
+    }
+    grid_accumulate<K>(ar, c, acc);
+}
+template <int K>
+__device__ __forceinline__ void pair_pass_sp_pipe(const PolSP& ar, const PolSP::FoldC ra, const PolSP::FoldC rb, const uint64_t* const (&src)[K],
+                                                  uint64_t* const (&dst)[K], uint64_t n_groups, uint64_t start, uint64_t stride,
+                                                  uint64_t (&acc)[(K + 1) * (K + 1)]) {
+    const uint32_t c32 = (uint32_t)((1ull << 32) % ar.p);
+    uint32_t it = 0;
+    uint64_t w[2][16];
+    uint64_t g = start;
+    if (g < n_groups) ld_words<16>(src[0] + g * 16, w[0]);
+    while (g < n_groups) {
+        if ((++it % (GridConsts<K>::fold_every / 2)) == 0) grid_fold(c32, acc);
+        uint64_t gn = g + stride;
+        pair_pipe_step<K, 0>(ar, ra, rb, src, dst, g, gn, gn < n_groups, w, acc);
+        g = gn;
+        if constexpr (K & 1) {  // table 0 of this iteration sits in the other buffer
+            if (g >= n_groups) break;
+            gn = g + stride;
+            pair_pipe_step<K, 1>(ar, ra, rb, src, dst, g, gn, gn < n_groups, w, acc);
+            g = gn;
+        }
+    }
+    grid_canon<K>(ar, c32, acc);
+}
+
 // ------------------------------------------------------------------------------------------ staged loads
 // The grid passes spend ~300 issue cycles per thread-iteration at 2-3 CTAs per SM, so loads issued at the top of an
 // iteration leave HBM idle while the warp computes (ncu: long_scoreboard dominates, issue active 54 %).  cp.async
@@ -570,8 +621,9 @@ __global__ void __launch_bounds__(kThreads, (K <= 2 ? 3 : 2))
         if (blockIdx.x < active) {
             const uint64_t start = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = active * blockDim.x;
             if (m >= 4) {
-                if (!src_w32) pair_pass_sp<K, false, true, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);  // only the caller's tables
-                else if (use_stage) pair_pass_sp_staged<K>(ar, stage_smem, ra, rb, src, dst, n_groups, start, stride, acc);
+                if (!src_w32 && (use_stage & 2)) pair_pass_sp_pipe<K>(ar, ra, rb, src, dst, n_groups, start, stride, acc);
+                else if (!src_w32) pair_pass_sp<K, false, true, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);  // only the caller's tables
+                else if (use_stage & 1) pair_pass_sp_staged<K>(ar, stage_smem, ra, rb, src, dst, n_groups, start, stride, acc);
                 else if (t == 0) pair_pass_sp<K, true, true, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);
                 else pair_pass_sp<K, true, false, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);
             } else if (start == 0) {  // 8 entries per table -> 2 -> line sums
