@@ -137,6 +137,14 @@ def resident_stats(T):
             "work_us": list(work)[: rounds.value], "turn_us": list(turn)[: rounds.value]}
 
 
+def pair_pass_stats(T):
+    import ctypes as C
+
+    n, ms = C.c_uint64(), C.c_double()
+    T.lib.scb_pair_pass_stats(C.byref(n), C.byref(ms))
+    return {"launches": n.value, "total_ms": ms.value}
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -289,16 +297,18 @@ def run_ours(args):
     # and its first pass (the one that streams the full tables) with %globaltimer stamps inside the kernel.
     # Other fields: one round per pass; the dominant launch is the fused fold + message kernel of round 1, timed alone.
     roof = None
+    pass_stats = pair_pass_stats(T)
+    first_alone = pass_stats["launches"] == args.steps  # the pass over the 8-byte tables ran as its own launch
+    n_res_passes = (v - 1) // 2 - (1 if first_alone else 0)
     if rank == 0 and F.policy == 0 and world == 1 and os.environ.get("SCB_PAIRS", "1") != "0" \
-            and res_stats["launches"] == args.steps and res_stats["last_rounds"] == (v - 1) // 2:
+            and res_stats["launches"] == args.steps and res_stats["last_rounds"] == n_res_passes:
         peak, peak_src = hbm_peak()
         pbytes, m, in_b = [], v, E
         while m >= 3:  # pass: read K tables of 2^m entries, write 2^(m-2) packed entries (nothing after the last fold)
             pbytes.append(K * ((1 << m) * in_b + ((1 << (m - 2)) * 4 if m >= 4 else 0)))
             m, in_b = m - 2, 4
         res_ms = res_stats["total_ms"] / res_stats["launches"]
-        res_achieved = sum(pbytes) / (res_ms * 1e-3) / 1e9
-        w0 = res_stats["work_us"][0]
+        res_bytes = sum(pbytes[1:]) if first_alone else sum(pbytes)
         times = []
         for i in range(3 + max(args.steps, 5)):  # Prover::new's grid kernel, timed alone (call includes one sync + 128 B D2H)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -312,27 +322,40 @@ def run_ours(args):
         grid_bytes = K * (1 << v) * E
         std = v == 28 and K == 3 and p == MODULUS
         proof_bytes = grid_bytes + sum(pbytes)
-        roof = {"bound": "hbm",
-                "kernel": "k_persist_pairs_sp<3> (rounds 3..%d of the proof: %d passes, each folds two variables and accumulates the "
-                          "16 grid sums of the next two messages; one cooperative launch)" % (v, len(pbytes)),
-                "achieved": res_achieved, "peak": peak, "unit": "GB/s", "frac": res_achieved / peak, "traffic": None,
-                "traffic_note": "ncu serialises kernel and host, so the resident kernel cannot run under it; the same pass bodies "
-                                "as stand-alone launches (k_pair_pass_sp, k_grid_sp) are captured in profiles/: DRAM traffic == "
-                                "algorithmic bytes (pass0_alone_traffic, grid_kernel_alone.traffic)",
-                "kernel_ms": res_ms, "algorithmic_bytes_per_launch": sum(pbytes), "peak_source": peak_src,
-                "timing": "CUDA events around the launch on its stream, all %d launches of the timed region" % res_stats["launches"],
-                "share_of_step": res_ms / ms,
-                "pass0_phase": {"us": w0, "achieved": pbytes[0] / (w0 * 1e-6) / 1e9, "frac": pbytes[0] / (w0 * 1e-6) / 1e9 / peak,
-                                "bytes": pbytes[0], "source": "%globaltimer stamps inside the kernel, last launch"},
-                "pass0_alone_traffic": 7.241953e9 if std else None,
-                "latency_us": {"host_turnaround_total": sum(res_stats["turn_us"]), "passes_after_0_total": sum(res_stats["work_us"][1:])},
-                "grid_kernel_alone": {"kernel": "k_grid_sp_pf<3> (Prover::new; u64 input, register double buffer), 2^%d-entry tables" % v, "kernel_ms": gms,
-                                      "achieved": grid_bytes / (gms * 1e-3) / 1e9, "frac": grid_bytes / (gms * 1e-3) / 1e9 / peak,
-                                      "algorithmic_bytes_per_launch": grid_bytes, "traffic": 6.457139e9 if std else None,
-                                      "share_of_step": gms / ms},
-                "proof_bytes_moved": proof_bytes, "proof_frac_of_hbm_roofline": (proof_bytes / (ms * 1e-3) / 1e9) / peak,
-                "proof_survey_bytes": 4.0 * K * (1 << v) * E,
-                "proof_frac_vs_survey_bytes": (4.0 * K * (1 << v) * E / (ms * 1e-3) / 1e9) / peak}
+        grid = {"kernel": "k_grid_sp_pf<3> (Prover::new; u64 input, register double buffer), 2^%d-entry tables" % v, "kernel_ms": gms,
+                "achieved": grid_bytes / (gms * 1e-3) / 1e9, "frac": grid_bytes / (gms * 1e-3) / 1e9 / peak,
+                "algorithmic_bytes_per_launch": grid_bytes, "traffic": 6.457139e9 if std else None, "share_of_step": gms / ms,
+                "timing": "CUDA events around the call, timed alone after the timed region (call includes one sync + 128 B D2H)"}
+        resident = {"kernel": "k_persist_pairs_sp<3> (%d resident pair passes: the remaining rounds, one cooperative launch)" % n_res_passes,
+                    "kernel_ms": res_ms, "algorithmic_bytes_per_launch": res_bytes, "achieved": res_bytes / (res_ms * 1e-3) / 1e9,
+                    "frac": res_bytes / (res_ms * 1e-3) / 1e9 / peak, "share_of_step": res_ms / ms,
+                    "latency_us": {"host_turnaround_total": sum(res_stats["turn_us"]), "device_passes_total": sum(res_stats["work_us"])},
+                    "traffic": None, "traffic_note": "ncu serialises kernel and host, so a resident kernel cannot run under it"}
+        proof = {"proof_bytes_moved": proof_bytes, "proof_frac_of_hbm_roofline": (proof_bytes / (ms * 1e-3) / 1e9) / peak,
+                 "proof_survey_bytes": 4.0 * K * (1 << v) * E,
+                 "proof_frac_vs_survey_bytes": (4.0 * K * (1 << v) * E / (ms * 1e-3) / 1e9) / peak}
+        if first_alone:
+            # dominant kernel of the step: the pair pass over the caller's 8-byte tables, an ordinary launch timed with CUDA
+            # events around it on its stream, every launch of the timed region (scb_pair_pass_stats)
+            pms = pass_stats["total_ms"] / pass_stats["launches"]
+            roof = {"bound": "hbm",
+                    "kernel": "k_pair_pass_sp<3,in=u64,out=u32> (rounds 3-4 of the proof: folds two variables of the 2^%d-entry tables and "
+                              "accumulates the 16 grid sums of the next two messages)" % v,
+                    "achieved": pbytes[0] / (pms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": pbytes[0] / (pms * 1e-3) / 1e9 / peak,
+                    "traffic": 7.241953e9 if std else None, "kernel_ms": pms, "algorithmic_bytes_per_launch": pbytes[0], "peak_source": peak_src,
+                    "timing": "CUDA events around the launch on its stream, all %d launches of the timed region" % pass_stats["launches"],
+                    "share_of_step": pms / ms, "grid_kernel_alone": grid, "resident_kernel": resident}
+        else:
+            w0 = res_stats["work_us"][0]
+            roof = {"bound": "hbm", "kernel": resident["kernel"], "achieved": resident["achieved"], "peak": peak, "unit": "GB/s",
+                    "frac": resident["frac"], "traffic": None, "traffic_note": resident["traffic_note"], "kernel_ms": res_ms,
+                    "algorithmic_bytes_per_launch": res_bytes, "peak_source": peak_src,
+                    "timing": "CUDA events around the launch on its stream, all %d launches of the timed region" % res_stats["launches"],
+                    "share_of_step": res_ms / ms,
+                    "pass0_phase": {"us": w0, "achieved": pbytes[0] / (w0 * 1e-6) / 1e9, "frac": pbytes[0] / (w0 * 1e-6) / 1e9 / peak,
+                                    "bytes": pbytes[0], "source": "%globaltimer stamps inside the kernel, last launch"},
+                    "pass0_alone_traffic": 7.241953e9 if std else None, "latency_us": resident["latency_us"], "grid_kernel_alone": grid}
+        roof.update(proof)
     elif rank == 0:
         # Timed alone, on the same kernel variant the proof runs in round 1: with the small-prime policy the prover's
         # folded tables are packed uint32 (packed.cuh), so the launch reads 2^v ark elements (E bytes) per table and

@@ -193,6 +193,8 @@ int scb_poly_resident_pairs(const scb_poly* p, const uint64_t* ra, const uint64_
  * turn-around (posted -> next challenge seen by the kernel), microseconds, from %globaltimer stamps. */
 int scb_resident_stats(uint64_t* launches, double* total_kernel_ms, uint32_t* last_rounds, double* last_work_us,
                        double* last_turn_us, uint32_t cap);
+/* launches and summed CUDA-event kernel time of the stand-alone pair passes (scb_poly_pair_pass) since the last reset */
+int scb_pair_pass_stats(uint64_t* launches, double* total_kernel_ms);
 void scb_resident_stats_reset(void);
 
 /* ------------------------------------------------------------------ round-message algebra (host) */

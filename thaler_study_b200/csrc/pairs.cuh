@@ -168,47 +168,56 @@ __device__ __forceinline__ void pair_pass_sp(const PolSP& ar, const PolSP::FoldC
 // the 128 bytes of the next table (or of table 0 of the next thread-iteration) are already in flight.  Two raw
 // buffers alternate; PAR says which one holds table 0 (it flips every iteration when K is odd), so all register-array
 // indices are compile-time.
-template <int K, int PAR>
-__device__ __forceinline__ void pair_pipe_step(const PolSP& ar, const PolSP::FoldC ra, const PolSP::FoldC rb, const uint64_t* const (&src)[K],
-                                               uint64_t* const (&dst)[K], uint64_t g, uint64_t g_next, bool has_next, uint64_t (&w)[2][16],
-                                               uint64_t (&acc)[(K + 1) * (K + 1)]) {
-    uint32_t c[K][4];
+template <int K, int k, int CUR, bool IN32, bool NC>
+__device__ __forceinline__ void pair_pipe_table(const PolSP& ar, const PolSP::FoldC ra, const PolSP::FoldC rb, const uint64_t* const (&src)[K],
+                                                uint64_t* const (&dst)[K], uint64_t g, uint64_t g_next, bool has_next,
+                                                uint64_t (&wa)[IN32 ? 8 : 16], uint64_t (&wb)[IN32 ? 8 : 16], uint32_t (&c)[K][4]) {
+    constexpr int WPT = IN32 ? 8 : 16;
+    uint64_t(&cur)[WPT] = CUR ? wb : wa;
+    uint64_t(&nxt)[WPT] = CUR ? wa : wb;
+    if constexpr (k + 1 < K) ld_words_sel<WPT, NC>(src[k + 1 < K ? k + 1 : 0] + g * WPT, nxt);
+    else if (has_next) ld_words_sel<WPT, NC>(src[0] + g_next * WPT, nxt);
+    uint32_t t[16];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        constexpr int dummy = 0;
-        (void)dummy;
-        const int cur = (k + PAR) & 1, nxt = cur ^ 1;
-        if (k + 1 < K) ld_words<16>(src[k + 1 < K ? k + 1 : 0] + g * 16, w[nxt]);
-        else if (has_next) ld_words<16>(src[0] + g_next * 16, w[nxt]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t lo = ar.fold_c((uint32_t)w[cur][4 * q], (uint32_t)w[cur][4 * q + 1], ra);
-            const uint32_t hi = ar.fold_c((uint32_t)w[cur][4 * q + 2], (uint32_t)w[cur][4 * q + 3], ra);
-            c[k][q] = ar.fold_c(lo, hi, rb);
-        }
-        uint64_t o[2] = {(uint64_t)c[k][0] | ((uint64_t)c[k][1] << 32), (uint64_t)c[k][2] | ((uint64_t)c[k][3] << 32)};
-        st_words<2>(dst[k] + g * 2, o);
+    for (int q = 0; q < 16; ++q) {
+        if constexpr (IN32) t[q] = (q & 1) ? (uint32_t)(cur[q / 2] >> 32) : (uint32_t)cur[q / 2];
+        else t[q] = (uint32_t)cur[q];
     }
-    grid_accumulate<K>(ar, c, acc);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t lo = ar.fold_c(t[4 * q], t[4 * q + 1], ra), hi = ar.fold_c(t[4 * q + 2], t[4 * q + 3], ra);
+        c[k][q] = ar.fold_c(lo, hi, rb);
+    }
+    uint64_t o[2] = {(uint64_t)c[k][0] | ((uint64_t)c[k][1] << 32), (uint64_t)c[k][2] | ((uint64_t)c[k][3] << 32)};
+    st_words<2>(dst[k] + g * 2, o);
+    if constexpr (k + 1 < K) pair_pipe_table<K, k + 1, CUR ^ 1, IN32, NC>(ar, ra, rb, src, dst, g, g_next, has_next, wa, wb, c);
 }
-template <int K>
+// IN32: packed uint32 input (64 bytes per table and thread-iteration) instead of the caller's 8-byte entries (128)
+template <int K, bool IN32, bool NC>
 __device__ __forceinline__ void pair_pass_sp_pipe(const PolSP& ar, const PolSP::FoldC ra, const PolSP::FoldC rb, const uint64_t* const (&src)[K],
                                                   uint64_t* const (&dst)[K], uint64_t n_groups, uint64_t start, uint64_t stride,
                                                   uint64_t (&acc)[(K + 1) * (K + 1)]) {
+    constexpr int WPT = IN32 ? 8 : 16;
     const uint32_t c32 = (uint32_t)((1ull << 32) % ar.p);
     uint32_t it = 0;
-    uint64_t w[2][16];
+    uint64_t wa[WPT], wb[WPT];
     uint64_t g = start;
-    if (g < n_groups) ld_words<16>(src[0] + g * 16, w[0]);
+    if (g < n_groups) ld_words_sel<WPT, NC>(src[0] + g * WPT, wa);
     while (g < n_groups) {
         if ((++it % (GridConsts<K>::fold_every / 2)) == 0) grid_fold(c32, acc);
         uint64_t gn = g + stride;
-        pair_pipe_step<K, 0>(ar, ra, rb, src, dst, g, gn, gn < n_groups, w, acc);
+        {
+            uint32_t c[K][4];
+            pair_pipe_table<K, 0, 0, IN32, NC>(ar, ra, rb, src, dst, g, gn, gn < n_groups, wa, wb, c);
+            grid_accumulate<K>(ar, c, acc);
+        }
         g = gn;
         if constexpr (K & 1) {  // table 0 of this iteration sits in the other buffer
             if (g >= n_groups) break;
             gn = g + stride;
-            pair_pipe_step<K, 1>(ar, ra, rb, src, dst, g, gn, gn < n_groups, w, acc);
+            uint32_t c[K][4];
+            pair_pipe_table<K, 0, 1, IN32, NC>(ar, ra, rb, src, dst, g, gn, gn < n_groups, wa, wb, c);
+            grid_accumulate<K>(ar, c, acc);
             g = gn;
         }
     }
@@ -559,7 +568,9 @@ __global__ void __launch_bounds__(kThreads, 3)
 // entries-bits (m >= 3) by the challenge pair number t and posts: the (K+1)^2 grid of the folded table when it still
 // has >= 2 variables, its (K+1) line sums when it has exactly one.  n_passes = ceil((m - 2) / 2).  Barrier, mailbox
 // and solo-CTA endgame as in k_persist_rounds.
-template <int K>
+// U64IN: the first pass may read the caller's 8-byte tables.  The packed-only instantiation (what a proof runs after
+// its first pass was a launch of its own) has the registers to pipeline the packed loads across tables as well.
+template <int K, bool U64IN>
 __global__ void __launch_bounds__(kThreads, (K <= 2 ? 3 : 2))
     k_persist_pairs_sp(FieldDesc f, TabsIn<K> in0, TabsOut<K> buf_a, TabsOut<K> buf_b, ElemArg ra0, ElemArg rb0, uint32_t m, uint32_t n_passes,
                        int in0_w32, TailMailbox* mb, PersistCtl* ctl, uint64_t* partials, uint64_t timeout_ns, int use_stage, PeerArg peer) {
@@ -621,11 +632,15 @@ __global__ void __launch_bounds__(kThreads, (K <= 2 ? 3 : 2))
         if (blockIdx.x < active) {
             const uint64_t start = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = active * blockDim.x;
             if (m >= 4) {
-                if (!src_w32 && (use_stage & 2)) pair_pass_sp_pipe<K>(ar, ra, rb, src, dst, n_groups, start, stride, acc);
-                else if (!src_w32) pair_pass_sp<K, false, true, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);  // only the caller's tables
-                else if (use_stage & 1) pair_pass_sp_staged<K>(ar, stage_smem, ra, rb, src, dst, n_groups, start, stride, acc);
-                else if (t == 0) pair_pass_sp<K, true, true, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);
-                else pair_pass_sp<K, true, false, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);
+                if constexpr (U64IN) {
+                    if (!src_w32 && (use_stage & 2)) pair_pass_sp_pipe<K, false, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);
+                    else if (!src_w32) pair_pass_sp<K, false, true, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);  // only the caller's tables
+                    else if (use_stage & 1) pair_pass_sp_staged<K>(ar, stage_smem, ra, rb, src, dst, n_groups, start, stride, acc);
+                    else if (t == 0) pair_pass_sp<K, true, true, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);
+                    else pair_pass_sp<K, true, false, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);
+                } else {
+                    pair_pass_sp_pipe<K, true, false>(ar, ra, rb, src, dst, n_groups, start, stride, acc);  // L2-coherent loads throughout
+                }
             } else if (start == 0) {  // 8 entries per table -> 2 -> line sums
                 uint32_t prod[NP];
 #pragma unroll

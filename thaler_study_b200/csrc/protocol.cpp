@@ -535,7 +535,14 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
             uint32_t live = 0, max_passes = 0;
             RC_TRY(maybe_consolidate(p, !resident));
             RC_TRY(scb_poly_num_vars(p->g, &live));
-            if (!resident) {
+            // The pass over the caller's 8-byte tables runs as its own launch when the tables are large (>= 2^26
+            // entries): the stand-alone kernel fits 3 CTAs per SM (80 registers), the resident one 2; without the
+            // 8-byte path the resident kernel has the registers to pipeline its packed loads across tables; and the
+            // extra launch + wait costs less than the two gains (SCB_PAIR_FIRST_ALONE=0: everything in the resident
+            // kernel; =n: threshold 2^n).
+            static const uint32_t first_alone = getenv("SCB_PAIR_FIRST_ALONE") ? (uint32_t)atoi(getenv("SCB_PAIR_FIRST_ALONE")) : 26;
+            const bool alone_now = resident && first_alone != 0 && !p->sharded && live >= first_alone && !poly_is_packed(p->g);
+            if (!resident || alone_now) {
                 if (live < 4) {  // too small for a grid pass: the per-round path below finishes the proof
                     rc = SCB_ETAIL;
                     break;
