@@ -290,11 +290,12 @@ def run_ours(args):
     value = total_entries / (ms * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel
-    # Small-prime fields (the default workload): two rounds per pass (csrc/pairs.cuh).  A proof is two launches:
-    # k_grid_sp_pf (Prover::new: the (K+1)^2 grid sums that yield c_1, g_1 and g_2) and the resident k_persist_pairs_sp
-    # (every later round; pass t folds two variables and accumulates the next grid).  The resident kernel is the
-    # dominant one; it is timed with CUDA events around its launch, on its stream, inside the timed region above,
-    # and its first pass (the one that streams the full tables) with %globaltimer stamps inside the kernel.
+    # Small-prime fields (the default workload): two rounds per pass (csrc/pairs.cuh).  A proof of 2^28-entry tables is
+    # three launches: k_grid_sp_pf (Prover::new: the (K+1)^2 grid sums that yield c_1, g_1 and g_2), k_pair_pass_sp (the
+    # pair pass over the caller's 8-byte tables: folds two variables, accumulates the next grid) and the resident
+    # k_persist_pairs_sp (the 12 remaining passes over packed tables).  The pair pass over the full tables is the
+    # dominant kernel; the library times it with CUDA events around the launch, on its stream, for every launch inside
+    # the timed region above (scb_pair_pass_stats); likewise the resident kernel (scb_resident_stats).
     # Other fields: one round per pass; the dominant launch is the fused fold + message kernel of round 1, timed alone.
     roof = None
     pass_stats = pair_pass_stats(T)
