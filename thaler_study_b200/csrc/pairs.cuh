@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 template <int K, bool IN32, bool STAGED>
 __global__ void __launch_bounds__(kThreads, 3)
     k_pair_pass_sp(FieldDesc f, TabsIn<K> in, TabsOut<K> outp, ElemArg ra_arg, ElemArg rb_arg, uint64_t n_groups, uint64_t* partials,
-                   unsigned int* ticket, uint64_t* out) {
+                   unsigned int* ticket, uint64_t* out, PeerArg peer) {
     constexpr int NG = (K + 1) * (K + 1);
     const PolSP ar(f);
     const PolSP::FoldC ra = ar.fold_const(ar.from_words(ra_arg.w)), rb = ar.fold_const(ar.from_words(rb_arg.w));
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(kThreads, 3)
     const uint64_t start = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
     if constexpr (IN32 && STAGED) pair_pass_sp_staged<K>(ar, stage_smem, ra, rb, src, dst, n_groups, start, stride, acc);
     else pair_pass_sp<K, IN32, true, true>(ar, ra, rb, src, dst, n_groups, start, stride, acc);
-    grid_reduce_finish<PolSP, NG>(ar, acc, partials, ticket, out, GridConsts<K>::msg_k, nullptr);
+    grid_reduce_finish<PolSP, NG>(ar, acc, partials, ticket, out, GridConsts<K>::msg_k, &peer);
 }
 
 // ------------------------------------------------------------------------------------------ resident kernel

@@ -541,7 +541,8 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
             // extra launch + wait costs less than the two gains (SCB_PAIR_FIRST_ALONE=0: everything in the resident
             // kernel; =n: threshold 2^n).
             static const uint32_t first_alone = getenv("SCB_PAIR_FIRST_ALONE") ? (uint32_t)atoi(getenv("SCB_PAIR_FIRST_ALONE")) : 26;
-            const bool alone_now = resident && first_alone != 0 && !p->sharded && live >= first_alone && !poly_is_packed(p->g);
+            const bool alone_now = resident && first_alone != 0 && live >= first_alone && !poly_is_packed(p->g) &&
+                                   (!p->sharded || (live > p->consolidate_at && live >= 4));  // sharded: two local variables stay
             if (!resident || alone_now) {
                 if (live < 4) {  // too small for a grid pass: the per-round path below finishes the proof
                     rc = SCB_ETAIL;
@@ -549,7 +550,10 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
                 }
                 uint64_t w[32], next_pair[2];
                 scb_poly* next = nullptr;
-                RC_TRY(scb_poly_pair_pass(p->g, pair, pair + 1, &next, w));
+                {
+                    PeersScope scope(p->sharded ? p->peers : nullptr);  // sharded: exchange inside the kernel's finish
+                    RC_TRY(scb_poly_pair_pass(p->g, pair, pair + 1, &next, w));
+                }
                 scb_poly_free(p->g);
                 p->g = next;
                 RC_TRY(pair_pass_cb(&pc, 0, p->np * p->np, w, next_pair));
