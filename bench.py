@@ -438,9 +438,17 @@ def run_ours(args):
             host.append(ht.numpy().view(np.uint64))
         torch.cuda.synchronize()
 
+        # One GPU: scb_poly_product_from_host -- for the small-prime field the tables cross PCIe as packed uint32 where
+        # the host cores keep up and as 8-byte entries where not (narrowed on the device).  Sharded runs keep one plain
+        # cudaMemcpy per table: the ranks of a box share its host cores.
+        one_call = world == 1 and os.environ.get("SCB_BENCH_E2E_PLAIN", "0") == "0"
+
         def e2e_step():
-            hs = [T.DenseMultilinearExtension.from_evaluations_vec(F, v, h) for h in host]  # cudaMemcpy H2D
-            gg = T.ProductMLE.new(hs)
+            if one_call:
+                gg = T.ProductMLE.from_host_tables(F, v, host)
+            else:
+                hs = [T.DenseMultilinearExtension.from_evaluations_vec(F, v, h) for h in host]  # cudaMemcpy H2D
+                gg = T.ProductMLE.new(hs)
             return prove(gg)  # messages come back device -> host every round
 
         e2e_step()
@@ -459,9 +467,24 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
         rounds = v + (world.bit_length() - 1)
+        h2d = K * (1 << v) * E * n_gpus
+        note = "scb_mle_from_host x%d (pinned host tables, H2D) + Prover::new + all rounds + Fiat-Shamir, per step" % K
+        upload = None
+        if one_call:
+            import ctypes
+
+            pc, rc_ = ctypes.c_uint64(), ctypes.c_uint64()
+            T._lib.check(T.lib.scb_host_pack_stats(ctypes.byref(pc), ctypes.byref(rc_)))
+            note = "scb_poly_product_from_host (pinned host tables, H2D) + Prover::new + all rounds + Fiat-Shamir, per step"
+            if F.policy == 0 and pc.value + rc_.value > 0 and os.environ.get("SCB_HOST_PACK", "1") != "0":
+                chunk = K * (1 << v) // (pc.value + rc_.value)
+                h2d = (4 * pc.value + 8 * rc_.value) * chunk  # bytes of the copies the last step queued
+                upload = {"chunk_entries": chunk, "chunks_packed_on_host_4B": pc.value, "chunks_packed_on_device_8B": rc_.value,
+                          "host_pack_threads": min(32, int(os.environ.get("SCB_HOST_PACK_THREADS", os.cpu_count() or 1)))}
         e2e = {"value": total_entries / (ems * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ems,
-               "h2d_bytes_per_step": K * (1 << v) * E * n_gpus, "d2h_bytes_per_step": rounds * (K + 1) * E * n_gpus,
-               "note": "scb_mle_from_host x3 (pinned host tables, H2D) + Prover::new + all rounds + Fiat-Shamir, per step"}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": rounds * (K + 1) * E * n_gpus, "note": note}
+        if upload:
+            e2e["upload"] = upload
         del host
 
     cpu = None

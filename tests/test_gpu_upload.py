@@ -1,0 +1,115 @@
+"""GPU tests of scb_poly_product_from_host (upload_engine.inc): ProductMLE<K> built straight from host tables.  For the
+reference's small-prime fields the tables cross PCIe as packed uint32 (host threads narrow chunks into pinned staging;
+a second lane copies chunks as they are and narrows them on the device).  Whatever the lane, the handle must hold the
+same field elements and prove to the same transcript bytes as the plain 8-byte upload and the oracle."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from oracle.coracle import CField
+
+import thaler_study_b200 as T
+from thaler_study_b200 import _lib
+from thaler_study_b200._lib import check, lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _stats():
+    a, b = C.c_uint64(), C.c_uint64()
+    check(lib.scb_host_pack_stats(C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def _small(monkeypatch, threads=3, raw=1, chunk_log2=6):
+    monkeypatch.setenv("SCB_HOST_PACK_MIN_VARS", "6")
+    monkeypatch.setenv("SCB_HOST_PACK_CHUNK_LOG2", str(chunk_log2))
+    monkeypatch.setenv("SCB_HOST_PACK_THREADS", str(threads))
+    monkeypatch.setenv("SCB_HOST_PACK_RAW", str(raw))
+
+
+@pytest.mark.parametrize("p", [5, 389, 1572869])
+@pytest.mark.parametrize("K", [1, 2, 3, 4])
+def test_packed_upload_matches_oracle_transcript(p, K, monkeypatch):
+    if K >= p:
+        pytest.skip("degree >= characteristic")
+    OF, F = O.Field(p), T.Field(p)
+    rnd = random.Random(1000 * K + p)
+    for v, threads, raw in ((6, 1, 1), (7, 2, 0), (9, 3, 1), (12, 4, 1)):
+        _small(monkeypatch, threads, raw)
+        vals = [[rnd.randrange(p) for _ in range(1 << v)] for _ in range(K)]
+        g = T.ProductMLE.from_host_tables(F, v, vals)
+        packed_chunks, raw_chunks = _stats()
+        assert packed_chunks + raw_chunks == K * (1 << (v - 6)) and (raw or raw_chunks == 0)
+        assert g.num_vars() == v
+        for k in range(K):
+            assert g.table(k).to_evaluations() == vals[k]
+        og = O.ProductMLE(OF, [O.DenseMLE(OF, v, t) for t in vals])
+        assert g.sum() == O.Prover(og).c_1()
+        want = O.generate_transcript(OF, O.Prover(og))
+        assert T.generate_transcript(T.Prover(g)) == want
+        plain = T.ProductMLE.new([T.DenseMultilinearExtension.from_evaluations_vec(F, v, t) for t in vals])
+        assert T.generate_transcript(T.Prover(plain)) == want
+        assert T.verify_transcript(want, T.Verifier(v, g))
+        # interactive rounds on the packed handle
+        pr, r = T.Prover(g), 1
+        opr = O.Prover(og)
+        for j in range(v):
+            assert list(pr.round(r, j).coeffs) == [(int(d), int(c)) for d, c in opr.round(r, j).coeffs]
+            r = rnd.randrange(p)
+
+
+def test_packed_upload_rejects_non_canonical_entries(monkeypatch):
+    _small(monkeypatch)
+    F = T.Field(1572869)
+    v = 10
+    for lane_raw in (0, 1):
+        monkeypatch.setenv("SCB_HOST_PACK_RAW", str(lane_raw))
+        for where in (0, 517, (1 << v) - 1):
+            t = np.zeros([1 << v, 1], dtype=np.uint64)
+            t[where, 0] = 1 << 21  # >= 2^bits(p)
+            with pytest.raises(T.ScbError) as ei:
+                T.ProductMLE.from_host_tables(F, v, [t, np.ones([1 << v, 1], dtype=np.uint64)])
+            assert ei.value.code == _lib.SCB_EINVAL
+
+
+@pytest.mark.parametrize("p", [(1 << 61) - 1, O.BLS12_381_FR.p], ids=["p61", "bls12_381_fr"])
+def test_other_fields_take_the_plain_copy(p, monkeypatch):
+    _small(monkeypatch)
+    OF, F = O.Field(p), T.Field(p)
+    rnd = random.Random(9)
+    v, K = 8, 2
+    vals = [[rnd.randrange(p) for _ in range(1 << v)] for _ in range(K)]
+    g = T.ProductMLE.from_host_tables(F, v, vals)
+    for k in range(K):
+        assert g.table(k).to_evaluations() == vals[k]
+    want = O.generate_transcript(OF, O.Prover(O.ProductMLE(OF, [O.DenseMLE(OF, v, t) for t in vals])))
+    assert T.generate_transcript(T.Prover(g)) == want
+
+
+@pytest.mark.parametrize("switch", ["default", "no_raw_lane", "off"])
+def test_large_tables_default_switches(switch, monkeypatch):
+    """2^24-entry tables with the default chunking (2^20 entries): both lanes run; the proof equals the plain upload's,
+    which the C oracle anchors through the round sums of the first rounds."""
+    if switch == "no_raw_lane":
+        monkeypatch.setenv("SCB_HOST_PACK_RAW", "0")
+    if switch == "off":
+        monkeypatch.setenv("SCB_HOST_PACK", "0")
+    p, v, K = 1572869, 24, 3
+    F, cf = T.Field(p), CField(p)
+    tabs = [cf.synth(500 + k, 0, 1 << v) for k in range(K)]  # Montgomery words, ark's layout
+    g = T.ProductMLE.from_host_tables(F, v, tabs)
+    if switch != "off":
+        packed_chunks, raw_chunks = _stats()
+        assert packed_chunks + raw_chunks == K * (1 << (v - 20))
+        assert switch == "default" or raw_chunks == 0
+    assert g.round_evals() == cf.from_mont(cf.product_round_evals(tabs, K + 1))
+    for k in range(K):
+        assert np.array_equal(g.table(k).to_evaluations_mont().reshape(-1), np.asarray(tabs[k]).reshape(-1))
+    plain = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, 500 + k) for k in range(K)])
+    got = T.generate_transcript(T.Prover(g))
+    assert got == T.generate_transcript(T.Prover(plain))
+    assert T.verify_transcript(got, T.Verifier(v, plain))

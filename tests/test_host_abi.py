@@ -26,6 +26,15 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in _lib.lib.scb_version()
 
 
+@pytest.mark.parametrize("k,nv,chunk_log2,workers,raw_lane", [(1, 6, 6, 1, 0), (3, 12, 6, 4, 1), (4, 14, 8, 7, 1), (2, 16, 10, 3, 0),
+                                                              (3, 20, 16, 8, 1), (1, 10, 10, 2, 1)])
+def test_packed_upload_scheduler_on_a_memcpy_backend(k, nv, chunk_log2, workers, raw_lane):
+    """host/hostpack.hpp: pack workers take chunks from the front, the raw lane from the back; every entry must arrive
+    narrowed at its place exactly once (no device involved: the back end copies into host memory)."""
+    for seed in (1, 2, 3):
+        _lib.check(_lib.lib.scb_host_pack_selftest(k, nv, chunk_log2, workers, raw_lane, seed))
+
+
 def test_no_cpu_fallback_without_device():
     if T.device_count() > 0:
         pytest.skip("a device is present")

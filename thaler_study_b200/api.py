@@ -403,6 +403,19 @@ class ProductMLE(SumCheckPolynomial):
         check(lib.scb_poly_product(arr, len(tables), C.byref(h)))
         return ProductMLE(tables[0].F, h)
 
+    @staticmethod
+    def from_host_tables(F: Field, num_vars: int, tables: Sequence[Table]) -> "ProductMLE":
+        """K host tables (ark's in-memory format when given as uint64 arrays) -> one handle, in one call: the upload
+        packs small-prime tables to 32 bits on the way (scb_poly_product_from_host)."""
+        ms = [_as_mont(F, t) for t in tables]
+        for m in ms:
+            if m.shape[0] != 1 << num_vars:
+                raise ValueError("The size of evaluations should be 2^num_vars.")
+        arr = (u64p * len(ms))(*[_p64(m) for m in ms])
+        h = C.c_void_p()
+        check(lib.scb_poly_product_from_host(F._h, len(ms), num_vars, arr, C.byref(h)))
+        return ProductMLE(F, h)
+
 
 class MatMulG(SumCheckPolynomial):
     """matrix_multiplication::G (matrix-multiplication/src/lib.rs:12-15,62-147)."""

@@ -1353,5 +1353,8 @@ extern "C" int scb_poly_field_impl(const scb_poly* p, const FieldImpl** out) {
     return SCB_OK;
 }
 
+// ------------------------------------------------------------------------------------------ packed upload of host tables
+#include "upload_engine.inc"
+
 // ------------------------------------------------------------------------------------------ GKR (sparse wiring)
 #include "gkr_engine.inc"
