@@ -473,13 +473,15 @@ def run_ours(args):
         if one_call:
             import ctypes
 
-            pc, rc_ = ctypes.c_uint64(), ctypes.c_uint64()
-            T._lib.check(T.lib.scb_host_pack_stats(ctypes.byref(pc), ctypes.byref(rc_)))
+            pc, rc_, hb = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+            T._lib.check(T.lib.scb_host_pack_stats(ctypes.byref(pc), ctypes.byref(rc_), ctypes.byref(hb)))
             note = "scb_poly_product_from_host (pinned host tables, H2D) + Prover::new + all rounds + Fiat-Shamir, per step"
             if F.policy == 0 and pc.value + rc_.value > 0 and os.environ.get("SCB_HOST_PACK", "1") != "0":
-                chunk = K * (1 << v) // (pc.value + rc_.value)
-                h2d = (4 * pc.value + 8 * rc_.value) * chunk  # bytes of the copies the last step queued
-                upload = {"chunk_entries": chunk, "chunks_packed_on_host_4B": pc.value, "chunks_packed_on_device_8B": rc_.value,
+                h2d = hb.value  # bytes of the copies the last step queued, counted by the library as it queued them
+                wire21 = p < (1 << 21) and os.environ.get("SCB_HOST_PACK_WIRE", "21") == "21"
+                upload = {"chunk_entries": K * (1 << v) // (pc.value + rc_.value), "chunks_narrowed_on_host": pc.value,
+                          "chunks_narrowed_on_device": rc_.value,
+                          "host_lane_wire_format": "three 21-bit entries per 64-bit word" if wire21 else "uint32",
                           "host_pack_threads": min(32, int(os.environ.get("SCB_HOST_PACK_THREADS", os.cpu_count() or 1)))}
         e2e = {"value": total_entries / (ems * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ems,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": rounds * (K + 1) * E * n_gpus, "note": note}

@@ -117,14 +117,15 @@ int scb_poly_matmul_g(const scb_mle* f_a, const scb_mle* f_b, scb_poly** out);
 /* ProductMLE<K> straight from K caller-owned host tables of 2^num_vars elements each, in ark's in-memory format
  * (SURVEY 8b scb_poly_create; what a Rust shim calls with `evaluations.as_ptr()` of each DenseMultilinearExtension,
  * sum-check-protocol/src/lib.rs:88-97 being the consumer).  The host tables may be reused on return.
- * Small-prime fields (one limb, p < 2^28) and num_vars >= 22: the tables cross PCIe as packed uint32 where the host
- * cores keep up (pinned staging, several threads) and as they are where not, narrowed on the device -- the handle then
- * holds the packed layout the prover's own folded tables use (scb_poly_allow_packed).  SCB_EINVAL if an entry is not
- * below 2^bits(p).  Switches: SCB_HOST_PACK=0 (plain copies), SCB_HOST_PACK_THREADS, SCB_HOST_PACK_MIN_VARS,
- * SCB_HOST_PACK_CHUNK_LOG2, SCB_HOST_PACK_RAW=0 (no device-side lane). */
+ * Small-prime fields (one limb, p < 2^28) and num_vars >= 22: the tables cross PCIe narrowed where the host cores keep
+ * up (several threads, pinned staging; three 21-bit entries per 64-bit word when p < 2^21, uint32 otherwise) and as
+ * they are where not, narrowed on the device -- the handle then holds the packed uint32 layout the prover's own folded
+ * tables use (scb_poly_allow_packed).  SCB_EINVAL if an entry is not below 2^bits(p).  Switches: SCB_HOST_PACK=0
+ * (plain copies), SCB_HOST_PACK_THREADS, SCB_HOST_PACK_MIN_VARS, SCB_HOST_PACK_CHUNK_LOG2, SCB_HOST_PACK_RAW=0 (no
+ * device-side lane), SCB_HOST_PACK_WIRE=32 (uint32 on the wire), SCB_HOST_PACK_NT=1 (streaming stores into the staging buffers). */
 int scb_poly_product_from_host(const scb_field* f, uint32_t k, uint32_t num_vars, const uint64_t* const* host_tables, scb_poly** out);
-/* chunks of the last packed upload that crossed as uint32 (host lane) and as 8-byte entries (device lane) */
-int scb_host_pack_stats(uint64_t* packed_chunks, uint64_t* raw_chunks);
+/* the last packed upload: chunks narrowed by the host lane and by the device lane, bytes of all its H2D copies */
+int scb_host_pack_stats(uint64_t* packed_chunks, uint64_t* raw_chunks, uint64_t* h2d_bytes);
 /* the upload's host-side scheduler run against a memcpy back end on k random tables (no device needed): SCB_OK if
  * every entry arrives, narrowed, where it belongs */
 int scb_host_pack_selftest(uint32_t k, uint32_t num_vars, uint32_t chunk_log2, uint32_t workers, uint32_t raw_lane, uint64_t seed);

@@ -19,13 +19,16 @@ pytestmark = pytest.mark.gpu
 
 
 def _stats():
-    a, b = C.c_uint64(), C.c_uint64()
-    check(lib.scb_host_pack_stats(C.byref(a), C.byref(b)))
+    a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    check(lib.scb_host_pack_stats(C.byref(a), C.byref(b), C.byref(c)))
+    _stats.h2d_bytes = c.value
     return a.value, b.value
 
 
-def _small(monkeypatch, threads=3, raw=1, chunk_log2=6):
+def _small(monkeypatch, threads=3, raw=1, chunk_log2=6, wire=21, nt=1):
     monkeypatch.setenv("SCB_HOST_PACK_MIN_VARS", "6")
+    monkeypatch.setenv("SCB_HOST_PACK_WIRE", str(wire))  # 21: three entries per word when p < 2^21; 32: uint32
+    monkeypatch.setenv("SCB_HOST_PACK_NT", str(nt))
     monkeypatch.setenv("SCB_HOST_PACK_CHUNK_LOG2", str(chunk_log2))
     monkeypatch.setenv("SCB_HOST_PACK_THREADS", str(threads))
     monkeypatch.setenv("SCB_HOST_PACK_RAW", str(raw))
@@ -38,12 +41,14 @@ def test_packed_upload_matches_oracle_transcript(p, K, monkeypatch):
         pytest.skip("degree >= characteristic")
     OF, F = O.Field(p), T.Field(p)
     rnd = random.Random(1000 * K + p)
-    for v, threads, raw in ((6, 1, 1), (7, 2, 0), (9, 3, 1), (12, 4, 1)):
-        _small(monkeypatch, threads, raw)
+    for v, threads, raw, wire, nt in ((6, 1, 1, 21, 1), (7, 2, 0, 21, 0), (7, 2, 0, 32, 1), (9, 3, 1, 32, 0), (12, 4, 1, 21, 1), (12, 4, 0, 21, 1)):
+        _small(monkeypatch, threads, raw, wire=wire, nt=nt)
         vals = [[rnd.randrange(p) for _ in range(1 << v)] for _ in range(K)]
         g = T.ProductMLE.from_host_tables(F, v, vals)
         packed_chunks, raw_chunks = _stats()
         assert packed_chunks + raw_chunks == K * (1 << (v - 6)) and (raw or raw_chunks == 0)
+        per_chunk = 22 * 8 if wire == 21 else 64 * 4  # ceil(64 / 3) words, or 64 uint32
+        assert _stats.h2d_bytes == packed_chunks * per_chunk + raw_chunks * 64 * 8
         assert g.num_vars() == v
         for k in range(K):
             assert g.table(k).to_evaluations() == vals[k]
@@ -66,8 +71,9 @@ def test_packed_upload_rejects_non_canonical_entries(monkeypatch):
     _small(monkeypatch)
     F = T.Field(1572869)
     v = 10
-    for lane_raw in (0, 1):
+    for lane_raw, wire in ((0, 21), (1, 21), (0, 32), (1, 32)):
         monkeypatch.setenv("SCB_HOST_PACK_RAW", str(lane_raw))
+        monkeypatch.setenv("SCB_HOST_PACK_WIRE", str(wire))
         for where in (0, 517, (1 << v) - 1):
             t = np.zeros([1 << v, 1], dtype=np.uint64)
             t[where, 0] = 1 << 21  # >= 2^bits(p)
@@ -90,12 +96,14 @@ def test_other_fields_take_the_plain_copy(p, monkeypatch):
     assert T.generate_transcript(T.Prover(g)) == want
 
 
-@pytest.mark.parametrize("switch", ["default", "no_raw_lane", "off"])
+@pytest.mark.parametrize("switch", ["default", "no_raw_lane", "wire32", "off"])
 def test_large_tables_default_switches(switch, monkeypatch):
     """2^24-entry tables with the default chunking (2^20 entries): both lanes run; the proof equals the plain upload's,
     which the C oracle anchors through the round sums of the first rounds."""
     if switch == "no_raw_lane":
         monkeypatch.setenv("SCB_HOST_PACK_RAW", "0")
+    if switch == "wire32":
+        monkeypatch.setenv("SCB_HOST_PACK_WIRE", "32")
     if switch == "off":
         monkeypatch.setenv("SCB_HOST_PACK", "0")
     p, v, K = 1572869, 24, 3
@@ -105,7 +113,7 @@ def test_large_tables_default_switches(switch, monkeypatch):
     if switch != "off":
         packed_chunks, raw_chunks = _stats()
         assert packed_chunks + raw_chunks == K * (1 << (v - 20))
-        assert switch == "default" or raw_chunks == 0
+        assert switch != "no_raw_lane" or raw_chunks == 0
     assert g.round_evals() == cf.from_mont(cf.product_round_evals(tabs, K + 1))
     for k in range(K):
         assert np.array_equal(g.table(k).to_evaluations_mont().reshape(-1), np.asarray(tabs[k]).reshape(-1))

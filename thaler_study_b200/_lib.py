@@ -55,7 +55,7 @@ SIGNATURES = {
     "scb_poly_product": (C.c_int, [vpp, C.c_uint32, vpp]),
     "scb_poly_matmul_g": (C.c_int, [vp, vp, vpp]),
     "scb_poly_product_from_host": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.POINTER(u64p), vpp]),
-    "scb_host_pack_stats": (C.c_int, [u64p, u64p]),
+    "scb_host_pack_stats": (C.c_int, [u64p, u64p, u64p]),
     "scb_host_pack_selftest": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]),
     "scb_poly_matmul_g_new": (C.c_int, [vp, C.c_uint32, u64p, u64p, u64p, vpp]),
     "scb_poly_triangle_g_new": (C.c_int, [vp, C.c_uint32, u8p, vpp]),

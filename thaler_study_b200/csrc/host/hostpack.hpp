@@ -32,6 +32,65 @@ static inline uint64_t pack32_host(const uint64_t* __restrict__ src, uint32_t* _
     return acc;
 }
 
+#if defined(__SSE2__)
+}  // namespace scb
+#include <emmintrin.h>
+namespace scb {
+// the same with streaming stores: the staging buffer is written past the caches (no read-for-ownership of its lines)
+static inline uint64_t pack32_host_nt(const uint64_t* __restrict__ src, uint32_t* __restrict__ dst, uint64_t n) {
+    __m128i acc = _mm_setzero_si128();
+    uint64_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const __m128i a = _mm_loadu_si128((const __m128i*)(src + i)), b = _mm_loadu_si128((const __m128i*)(src + i + 2));
+        acc = _mm_or_si128(acc, _mm_or_si128(a, b));
+        const __m128i lo = _mm_castps_si128(_mm_shuffle_ps(_mm_castsi128_ps(a), _mm_castsi128_ps(b), _MM_SHUFFLE(2, 0, 2, 0)));
+        _mm_stream_si128((__m128i*)(dst + i), lo);  // staging buffers are 16-byte aligned, chunks are multiples of 4
+    }
+    uint64_t w[2];
+    _mm_storeu_si128((__m128i*)w, acc);
+    uint64_t r = w[0] | w[1];
+    for (; i < n; ++i) {
+        r |= src[i];
+        dst[i] = (uint32_t)src[i];
+    }
+    _mm_sfence();
+    return r;
+}
+#else
+static inline uint64_t pack32_host_nt(const uint64_t* src, uint32_t* dst, uint64_t n) { return pack32_host(src, dst, n); }
+#endif
+
+// Three entries below 2^21 per 64-bit word (entry i of a chunk in bits 21*(i%3) .. of word i/3; a last partial word is
+// zero-filled): the wire format for fields of at most 21 bits, such as the reference's F_1572869.  ceil(n/3) words.
+static inline uint64_t pack21_words(uint64_t n) { return (n + 2) / 3; }
+template <bool NT>
+static inline uint64_t pack21_host(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, uint64_t n) {
+    uint64_t acc = 0, i = 0, j = 0;
+    for (; i + 3 <= n; i += 3, ++j) {
+        const uint64_t a = src[i], b = src[i + 1], c = src[i + 2];
+        acc |= a | b | c;
+        const uint64_t w = a | (b << 21) | (c << 42);
+#if defined(__SSE2__) && defined(__x86_64__)
+        if (NT) _mm_stream_si64((long long*)(dst + j), (long long)w);
+        else dst[j] = w;
+#else
+        dst[j] = w;
+#endif
+    }
+    if (i < n) {
+        const uint64_t a = src[i], b = i + 1 < n ? src[i + 1] : 0;
+        acc |= a | b;
+        dst[j] = a | (b << 21);
+    }
+#if defined(__SSE2__) && defined(__x86_64__)
+    if (NT) _mm_sfence();
+#endif
+    return acc;
+}
+static inline void unpack21_host(const uint64_t* src, uint32_t* dst, uint64_t n) {
+    for (uint64_t i = 0; i < n; ++i) dst[i] = (uint32_t)((src[i / 3] >> (21 * (i % 3))) & 0x1fffffu);
+}
+
 struct PackUnits {  // chunks of all tables as one list: unit u = (table u / per_table, offset (u % per_table) * chunk)
     uint64_t per_table = 0, chunk = 0, total = 0;
     std::mutex mu;
@@ -57,7 +116,8 @@ struct PackStats {
 
 // Back end B:
 //   int  thread_enter();                                        per-thread set-up (device selection); 0 = ok
-//   uint32_t* stage(int worker, int slot);                      pinned staging buffer (chunk entries)
+//   uint32_t* stage(int worker, int slot);                      pinned staging buffer (4 bytes per chunk entry, 8-byte aligned);
+//                                                               holds uint32 entries or, with wire21, ceil(chunk/3) words
 //   int  stage_wait(int worker, int slot);                      the copy queued from that buffer has completed
 //   int  submit_packed(int worker, int slot, uint32_t table, uint64_t off, uint64_t n);
 //   int  raw_wait(int slot);                                    the device buffer of that slot is free again
@@ -65,7 +125,7 @@ struct PackStats {
 // Every call returns 0 or an error code, which stops all lanes and becomes the return value.
 template <class B>
 int run_pack_upload(B& be, const uint64_t* const* tables, uint32_t k, uint64_t len, uint64_t chunk, int workers, int raw_slots,
-                    uint64_t* or_acc, PackStats* stats) {
+                    uint64_t* or_acc, PackStats* stats, bool streaming_stores = false, bool wire21 = false) {
     PackUnits units(k, len, chunk);
     std::atomic<int> err{0};
     std::atomic<uint64_t> acc{0}, n_packed{0}, n_raw{0};
@@ -78,7 +138,9 @@ int run_pack_upload(B& be, const uint64_t* const* tables, uint32_t k, uint64_t l
             const uint64_t off = (u % units.per_table) * chunk;
             rc = be.stage_wait(w, slot);
             if (rc != 0) break;
-            a |= pack32_host(tables[t] + off, be.stage(w, slot), chunk);
+            const uint64_t* src = tables[t] + off;
+            if (wire21) a |= streaming_stores ? pack21_host<true>(src, (uint64_t*)be.stage(w, slot), chunk) : pack21_host<false>(src, (uint64_t*)be.stage(w, slot), chunk);
+            else a |= streaming_stores ? pack32_host_nt(src, be.stage(w, slot), chunk) : pack32_host(src, be.stage(w, slot), chunk);
             rc = be.submit_packed(w, slot, t, off, chunk);
             slot ^= 1;
             ++cnt;
@@ -122,15 +184,20 @@ struct MemcpyPackBackend {
     std::vector<std::vector<uint32_t>> staging;  // [worker * 2 + slot]
     std::vector<std::vector<uint32_t>>* dst;     // [table]
     std::atomic<uint64_t> raw_or{0};
+    bool wire21 = false;
     MemcpyPackBackend(uint64_t chunk_, int workers, std::vector<std::vector<uint32_t>>* dst_) : chunk(chunk_), dst(dst_) {
         staging.resize((size_t)workers * 2);
-        for (auto& s : staging) s.resize(chunk_);
+        for (auto& s : staging) s.resize(chunk_ + 4);
     }
     int thread_enter() { return 0; }
-    uint32_t* stage(int w, int slot) { return staging[(size_t)w * 2 + slot].data(); }
+    uint32_t* stage(int w, int slot) {  // 16-byte aligned inside the vector's allocation
+        uint32_t* p = staging[(size_t)w * 2 + slot].data();
+        return (uint32_t*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+    }
     int stage_wait(int, int) { return 0; }
     int submit_packed(int w, int slot, uint32_t t, uint64_t off, uint64_t n) {
-        std::copy(stage(w, slot), stage(w, slot) + n, (*dst)[t].begin() + off);
+        if (wire21) unpack21_host((const uint64_t*)stage(w, slot), (*dst)[t].data() + off, n);
+        else std::copy(stage(w, slot), stage(w, slot) + n, (*dst)[t].begin() + off);
         return 0;
     }
     int raw_wait(int) { return 0; }
