@@ -158,6 +158,17 @@ static int occ_grid(const Ctx* c, KernelT kernel, uint64_t items, size_t dyn_sme
     if (want < 1) want = 1;
     return (int)(want < cap ? want : cap);
 }
+// the same for kernels whose dynamic shared memory varies from call to call (no cache)
+template <class KernelT>
+static int occ_grid_smem(const Ctx* c, KernelT kernel, uint64_t items, size_t dyn_smem) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kThreads, dyn_smem) != cudaSuccess || nb < 1) nb = 1;
+    uint64_t want = (items + kThreads - 1) / kThreads;
+    uint64_t cap = (uint64_t)c->sms * nb;
+    if (cap > (uint64_t)kMaxGrid) cap = kMaxGrid;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
 // opt in to more than 48 KB of dynamic shared memory (once per kernel)
 template <class KernelT>
 static int allow_smem(KernelT kernel, size_t bytes) {
@@ -573,7 +584,11 @@ static int eval_table(Ctx* c, const FieldImpl& f, const Table& t, const uint64_t
     const uint32_t v = t.nv, N = f.d.n;
     ARG_TRY(v <= 34, "table too large for MLE evaluation");
     for (uint32_t j = 0; j < v; ++j) ARG_TRY(elem_canonical(f, bitpt + (size_t)j * N), "point coordinate is not canonical");
-    const uint32_t lb_max = N == 1 ? 12 : 10;
+    // low table (shared memory, copied by every CTA) over lb index bits, high table (L2) over the rest
+    static const uint32_t lb_env = getenv("SCB_MLE_LB") ? (uint32_t)atoi(getenv("SCB_MLE_LB")) : 0;
+    static const int u_env = getenv("SCB_MLE_U") ? atoi(getenv("SCB_MLE_U")) : 0;
+    uint32_t lb_max = N == 1 ? 12 : 10;
+    if (lb_env >= 2 && lb_env < lb_max) lb_max = lb_env;
     const uint32_t lb = v < lb_max ? v : lb_max;
     BufRef lo, hi;
     RC_TRY(build_eq_tables(c, f, bitpt, lb, v, &lo, &hi));
@@ -581,10 +596,17 @@ static int eval_table(Ctx* c, const FieldImpl& f, const Table& t, const uint64_t
     DISPATCH_POLICY(f.policy, {
         const size_t smem = (size_t)8 * N << lb;
         const uint64_t n = t.len();
-        if (A::N == 1 && lb >= 2) {
-            k_mle_dot<A, (A::N == 1 ? 4 : 1)><<<grid_for(c, n / 4), kThreads, smem, g_stream>>>(f.d, t.buf->ptr, lo->ptr, hi->ptr, lb, n / 4, c->partials, c->ticket, res);
+        if (lb >= 2) {  // four entries of a row per group: 1.25 multiplications per entry
+            if (A::N == 1 && u_env != 1) {
+                auto kern = k_mle_dot<A, 4, (A::N == 1 ? 4 : 1)>;  // four 256-bit loads in flight per thread
+                kern<<<occ_grid_smem(c, kern, (n / 4 + 3) / 4, smem), kThreads, smem, g_stream>>>(f.d, t.buf->ptr, lo->ptr, hi->ptr, lb, n / 4, c->partials, c->ticket, res);
+            } else {
+                auto kern = k_mle_dot<A, 4, 1>;
+                kern<<<occ_grid_smem(c, kern, n / 4, smem), kThreads, smem, g_stream>>>(f.d, t.buf->ptr, lo->ptr, hi->ptr, lb, n / 4, c->partials, c->ticket, res);
+            }
         } else {
-            k_mle_dot<A, 1><<<grid_for(c, n), kThreads, smem, g_stream>>>(f.d, t.buf->ptr, lo->ptr, hi->ptr, lb, n, c->partials, c->ticket, res);
+            auto kern = k_mle_dot<A, 1, 1>;
+            kern<<<occ_grid_smem(c, kern, n, smem), kThreads, smem, g_stream>>>(f.d, t.buf->ptr, lo->ptr, hi->ptr, lb, n, c->partials, c->ticket, res);
         }
     });
     LAUNCH_CHECK();

@@ -452,8 +452,10 @@ __global__ void __launch_bounds__(kThreads) k_product_table(FieldDesc f, TabsIn<
 // The two tables are built by k_eq_tables (eqfix.cuh).
 // ------------------------------------------------------------------------------------------
 // k_mle_dot: sum_i evals[i] * lo[i & (2^lb-1)] * hi[i >> lb].  VEC consecutive entries (same row)
-// per thread-iteration; lo table staged in shared memory.
-template <class A, int VEC>
+// per group: the VEC products with the low table are added up before the one multiplication by the row's high-table
+// entry (1 + 1/VEC multiplications per entry).  U groups per thread-iteration with all their loads issued first;
+// lo table staged in shared memory.
+template <class A, int VEC, int U>
 __global__ void __launch_bounds__(kThreads) k_mle_dot(FieldDesc f, const uint64_t* __restrict__ evals,
                                                       const uint64_t* __restrict__ lo_tab, const uint64_t* __restrict__ hi_tab,
                                                       uint32_t lb, uint64_t n_groups, uint64_t* partials, unsigned int* ticket,
@@ -469,21 +471,31 @@ __global__ void __launch_bounds__(kThreads) k_mle_dot(FieldDesc f, const uint64_
     const uint64_t groups_per_row_mask = ((1ull << lb) / VEC) - 1;
     const uint32_t row_shift = lb - (VEC == 4 ? 2 : (VEC == 2 ? 1 : 0));
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
-        uint64_t w[VEC * N];
-        ld_words<VEC * N>(evals + g * VEC * N, w);
-        const uint64_t il = (g & groups_per_row_mask) * VEC;
-        const uint64_t ih = g >> row_shift;
-        typename A::Lz s;
+    for (uint64_t g0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g0 < n_groups; g0 += stride * U) {
+        uint64_t w[U][VEC * N];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            typename A::Lz m = ar.lz_mul(ar.lz(ar.from_words(w + e * N)), ar.lz(ar.from_words(lo_sm + (il + e) * N)));
-            s = e == 0 ? m : ar.lz_add(s, m);
+        for (int u = 0; u < U; ++u) {
+            const uint64_t g = g0 + (uint64_t)u * stride;
+            if (u == 0 || g < n_groups) ld_words<VEC * N>(evals + g * VEC * N, w[u]);
         }
-        uint64_t hw[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) hw[i] = __ldg(hi_tab + ih * N + i);
-        ar.acc_add(acc[0], ar.lz_mul(s, ar.lz(ar.from_words(hw))));
+        for (int u = 0; u < U; ++u) {
+            const uint64_t g = g0 + (uint64_t)u * stride;
+            if (u == 0 || g < n_groups) {
+                const uint64_t il = (g & groups_per_row_mask) * VEC;
+                const uint64_t ih = g >> row_shift;
+                typename A::Lz s;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    typename A::Lz m = ar.lz_mul(ar.lz(ar.from_words(w[u] + e * N)), ar.lz(ar.from_words(lo_sm + (il + e) * N)));
+                    s = e == 0 ? m : ar.lz_add(s, m);
+                }
+                uint64_t hw[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) hw[i] = __ldg(hi_tab + ih * N + i);
+                ar.acc_add(acc[0], ar.lz_mul(s, ar.lz(ar.from_words(hw))));
+            }
+        }
     }
     grid_reduce_finish<A, 1>(ar, acc, partials, ticket, out);
 }
