@@ -573,7 +573,18 @@ static int build_eq_tables(Ctx* c, const FieldImpl& f, const uint64_t* bitpt, ui
     if (v) std::memcpy(pa.w, bitpt, (size_t)8 * N * v);
     const uint32_t cap_bits = N == 1 ? 12 : 10;
     const size_t smem = (size_t)8 * N << cap_bits;
-    DISPATCH_POLICY(f.policy, { k_eq_tables<A><<<2, 1024, smem, g_stream>>>(f.d, pa, lb, v, (*lo)->ptr, (*hi)->ptr, cap_bits); });
+    static const bool split = !(getenv("SCB_EQ_SPLIT") && atoi(getenv("SCB_EQ_SPLIT")) == 0);
+    const uint32_t hb = v - lb;
+    if (split && lb <= 18 && hb <= 18 && v >= 2) {
+        // sub-tables of at most 2^9 entries in shared memory, the last level spread over the grid (eqfix.cuh)
+        const uint32_t blocks_lo = lb <= 10 ? 1 : std::min(32u, 1u << (lb - 10)), blocks_hi = hb <= 10 ? 1 : std::min(64u, 1u << (hb - 10));
+        const size_t smem2 = (size_t)8 * N * ((1u << (lb / 2)) + (1u << (lb - lb / 2)) > (1u << (hb / 2)) + (1u << (hb - hb / 2))
+                                                  ? (1u << (lb / 2)) + (1u << (lb - lb / 2))
+                                                  : (1u << (hb / 2)) + (1u << (hb - hb / 2)));
+        DISPATCH_POLICY(f.policy, { k_eq_tables_split<A><<<blocks_lo + blocks_hi, 1024, smem2, g_stream>>>(f.d, pa, lb, v, (*lo)->ptr, (*hi)->ptr, blocks_lo); });
+    } else {
+        DISPATCH_POLICY(f.policy, { k_eq_tables<A><<<2, 1024, smem, g_stream>>>(f.d, pa, lb, v, (*lo)->ptr, (*hi)->ptr, cap_bits); });
+    }
     LAUNCH_CHECK();
     return SCB_OK;
 }

@@ -64,6 +64,56 @@ __global__ void __launch_bounds__(1024) k_eq_tables(FieldDesc f, PointArg pt, ui
     }
 }
 
+// The same two tables with every level but the last done on sub-tables: a table over nb index bits is the outer product
+// of one over its low nb/2 bits and one over the rest (exact arithmetic: the same field elements as nb doublings), so
+// each block doubles two sub-tables of at most 2^9 entries side by side in shared memory and then writes its slice of
+// the products -- the last, widest doubling step spread over the whole grid instead of one block's loop in global
+// memory.  Blocks [0, blocks_lo) write the low table, the rest the high table.
+template <class A>
+__global__ void __launch_bounds__(1024) k_eq_tables_split(FieldDesc f, PointArg pt, uint32_t lb, uint32_t v, uint64_t* lo_tab, uint64_t* hi_tab,
+                                                          uint32_t blocks_lo) {
+    constexpr int N = A::N;
+    extern __shared__ uint64_t eq_sm[];
+    const A ar(f);
+    const bool is_lo = blockIdx.x < blocks_lo;
+    const uint32_t first = is_lo ? 0 : lb;
+    const uint32_t nb = is_lo ? lb : v - lb;
+    uint64_t* out = is_lo ? lo_tab : hi_tab;
+    const uint32_t blk = is_lo ? blockIdx.x : blockIdx.x - blocks_lo;
+    const uint32_t nblk = is_lo ? blocks_lo : gridDim.x - blocks_lo;
+    const uint32_t h0 = nb / 2, h1 = nb - h0;  // h1 >= h0
+    uint64_t* ta = eq_sm;                      // index bits [0, h0)
+    uint64_t* tb = eq_sm + ((size_t)N << h0);  // index bits [h0, nb)
+    const uint32_t half_threads = blockDim.x / 2;
+    const bool in_a = threadIdx.x < half_threads;
+    const uint32_t tid = in_a ? threadIdx.x : threadIdx.x - half_threads;
+    uint64_t* tab = in_a ? ta : tb;
+    const uint32_t bits = in_a ? h0 : h1, cfirst = first + (in_a ? 0 : h0);
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) tab[i] = f.one[i];
+    }
+    __syncthreads();
+    for (uint32_t l = 0; l < h1; ++l) {
+        if (l < bits) {
+            const typename A::El c = ar.from_words(pt.w + (size_t)(cfirst + l) * N);
+            const uint32_t half = 1u << l;
+            for (uint32_t i = tid; i < half; i += half_threads) {
+                typename A::El cur = ar.from_words(tab + (size_t)i * N);
+                typename A::El hi = ar.mul(cur, c);
+                ar.to_words(hi, tab + (size_t)(i + half) * N);
+                ar.to_words(ar.sub(cur, hi), tab + (size_t)i * N);
+            }
+        }
+        __syncthreads();
+    }
+    const uint64_t n_out = 1ull << nb, mask = (1ull << h0) - 1;
+    for (uint64_t i = (uint64_t)blk * blockDim.x + threadIdx.x; i < n_out; i += (uint64_t)nblk * blockDim.x) {
+        const typename A::El a = ar.from_words(ta + (size_t)(i & mask) * N), b = ar.from_words(tb + (size_t)(i >> h0) * N);
+        ar.to_words(ar.mul(a, b), out + i * N);
+    }
+}
+
 // Same for T points at once (coordinates in device memory, pts[t][j] bound to index bit j): block 2t builds point t's
 // low table, block 2t+1 its high table; both must fit shared memory (lb, v - lb <= cap_bits).  Tables are stored
 // point-major: lo_all[t << lb ...], hi_all[t << (v - lb) ...].
