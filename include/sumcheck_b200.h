@@ -122,8 +122,10 @@ int scb_poly_matmul_g(const scb_mle* f_a, const scb_mle* f_b, scb_poly** out);
  * they are where not, narrowed on the device -- the handle then holds the packed uint32 layout the prover's own folded
  * tables use (scb_poly_allow_packed).  SCB_EINVAL if an entry is not below 2^bits(p).  Switches: SCB_HOST_PACK=0
  * (plain copies), SCB_HOST_PACK_THREADS, SCB_HOST_PACK_MIN_VARS, SCB_HOST_PACK_CHUNK_LOG2, SCB_HOST_PACK_RAW=0 (no
- * device-side lane), SCB_HOST_PACK_WIRE=32 (uint32 on the wire), SCB_HOST_PACK_NT=1 (streaming stores into the staging buffers). */
+ * device-side lane; it is also skipped when a table is not in pinned memory), SCB_HOST_PACK_WIRE=32 (uint32 on the wire), SCB_HOST_PACK_NT=1 (streaming stores into the staging buffers). */
 int scb_poly_product_from_host(const scb_field* f, uint32_t k, uint32_t num_vars, const uint64_t* const* host_tables, scb_poly** out);
+/* scb_mle_from_host and the two *_multilinear_from_evaluations calls take the same narrowing upload for such tables
+ * when the process is the only rank of its box (LOCAL_WORLD_SIZE unset or 1) and widen to 8-byte entries on the device. */
 /* the last packed upload: chunks narrowed by the host lane and by the device lane, bytes of all its H2D copies */
 int scb_host_pack_stats(uint64_t* packed_chunks, uint64_t* raw_chunks, uint64_t* h2d_bytes);
 /* the upload's host-side scheduler run against a memcpy back end on k random tables (no device needed): SCB_OK if

@@ -31,7 +31,7 @@ def _small(monkeypatch, threads=3, raw=1, chunk_log2=6, wire=21, nt=1):
     monkeypatch.setenv("SCB_HOST_PACK_NT", str(nt))
     monkeypatch.setenv("SCB_HOST_PACK_CHUNK_LOG2", str(chunk_log2))
     monkeypatch.setenv("SCB_HOST_PACK_THREADS", str(threads))
-    monkeypatch.setenv("SCB_HOST_PACK_RAW", str(raw))
+    monkeypatch.setenv("SCB_HOST_PACK_RAW", "2" if raw else "0")  # 2: device lane even from pageable (numpy) memory
 
 
 @pytest.mark.parametrize("p", [5, 389, 1572869])
@@ -72,7 +72,7 @@ def test_packed_upload_rejects_non_canonical_entries(monkeypatch):
     F = T.Field(1572869)
     v = 10
     for lane_raw, wire in ((0, 21), (1, 21), (0, 32), (1, 32)):
-        monkeypatch.setenv("SCB_HOST_PACK_RAW", str(lane_raw))
+        monkeypatch.setenv("SCB_HOST_PACK_RAW", "2" if lane_raw else "0")
         monkeypatch.setenv("SCB_HOST_PACK_WIRE", str(wire))
         for where in (0, 517, (1 << v) - 1):
             t = np.zeros([1 << v, 1], dtype=np.uint64)
@@ -100,6 +100,7 @@ def test_other_fields_take_the_plain_copy(p, monkeypatch):
 def test_large_tables_default_switches(switch, monkeypatch):
     """2^24-entry tables with the default chunking (2^20 entries): both lanes run; the proof equals the plain upload's,
     which the C oracle anchors through the round sums of the first rounds."""
+    monkeypatch.setenv("SCB_HOST_PACK_RAW", "2")  # numpy tables are pageable: ask for the device lane explicitly
     if switch == "no_raw_lane":
         monkeypatch.setenv("SCB_HOST_PACK_RAW", "0")
     if switch == "wire32":
@@ -121,3 +122,34 @@ def test_large_tables_default_switches(switch, monkeypatch):
     got = T.generate_transcript(T.Prover(g))
     assert got == T.generate_transcript(T.Prover(plain))
     assert T.verify_transcript(got, T.Verifier(v, plain))
+
+
+@pytest.mark.parametrize("p", [389, 1572869])
+def test_mle_from_host_narrows_large_tables_on_the_way(p, monkeypatch):
+    """scb_mle_from_host / vsbw_multilinear_from_evaluations with 2^22-entry host tables (pageable numpy memory: host
+    lane only) take the packed upload and widen on the device: same table, same evaluation as the device-made one."""
+    F, cf = T.Field(p), CField(p)
+    v = 22
+    tab = cf.synth(77, 0, 1 << v)
+    rnd = random.Random(p)
+    r = [rnd.randrange(p) for _ in range(v)]
+    dev = T.DenseMultilinearExtension.synthetic(F, v, 77)
+    want = dev.evaluate_be(r)
+    outs = []
+    for switch in ("1", "0"):
+        monkeypatch.setenv("SCB_HOST_PACK", switch)
+        m = T.DenseMultilinearExtension.from_evaluations_vec(F, v, tab)
+        if switch == "1":
+            packed_chunks, raw_chunks = _stats()
+            assert (packed_chunks, raw_chunks) == (4, 0)  # 2^22 entries in 2^20-entry chunks, nothing through the device lane
+        assert np.array_equal(m.to_evaluations_mont().reshape(-1), np.asarray(tab).reshape(-1))
+        assert m.evaluate_be(r) == want
+        outs.append(T.vsbw_multilinear_from_evaluations(F, tab, r))
+        assert T.cti_multilinear_from_evaluations(F, tab, r) == want
+    assert outs == [want, want]
+    bad = np.array(tab, copy=True)
+    bad[12345] = 1 << 40
+    monkeypatch.setenv("SCB_HOST_PACK", "1")
+    with pytest.raises(T.ScbError) as ei:
+        T.DenseMultilinearExtension.from_evaluations_vec(F, v, bad)
+    assert ei.value.code == _lib.SCB_EINVAL

@@ -408,10 +408,26 @@ static int mle_new(const std::shared_ptr<FieldImpl>& f, uint32_t nv, scb_mle** o
     return SCB_OK;
 }
 
+static int mle_upload_packed(Ctx* c, const FieldImpl& fi, uint32_t num_vars, const uint64_t* evals, Table* out, bool* done);  // upload_engine.inc
 extern "C" int scb_mle_from_host(const scb_field* f, uint32_t num_vars, const uint64_t* evals, scb_mle** out) {
     ARG_TRY(f && evals && out, "null argument");
     Ctx* c;
     RC_TRY(get_ctx(&c));
+    {
+        // large small-prime tables cross PCIe narrowed and are widened on the device (upload_engine.inc)
+        ARG_TRY(num_vars <= 40, "too many variables");
+        Table t;
+        bool done = false;
+        RC_TRY(mle_upload_packed(c, *f->impl, num_vars, evals, &t, &done));
+        if (done) {
+            CU_TRY(cudaStreamSynchronize(g_stream));
+            auto mm = std::make_unique<scb_mle>();
+            mm->f = f->impl;
+            mm->t = t;
+            *out = mm.release();
+            return SCB_OK;
+        }
+    }
     scb_mle* m = nullptr;
     RC_TRY(mle_new(f->impl, num_vars, &m, true));
     cudaError_t e = cudaMemcpyAsync(m->t.buf->ptr, evals, m->t.buf->bytes, cudaMemcpyHostToDevice, g_stream);
