@@ -440,8 +440,10 @@ def run_ours(args):
 
         # One GPU: scb_poly_product_from_host -- for the small-prime field the tables cross PCIe as packed uint32 where
         # the host cores keep up and as 8-byte entries where not (narrowed on the device).  Sharded runs keep one plain
-        # cudaMemcpy per table: the ranks of a box share its host cores.
-        one_call = world == 1 and os.environ.get("SCB_BENCH_E2E_PLAIN", "0") == "0"
+        # cudaMemcpy per table: the ranks of a box share its host memory system, which is what bounds the narrowing
+        # upload (2 GPUs measured with it: 117.8 ms per step against 119.0 plain, profiles/r01_bench_2gpu_packed_upload.json;
+        # SCB_BENCH_E2E_UPLOAD=1 selects it anyway).
+        one_call = (world == 1 or os.environ.get("SCB_BENCH_E2E_UPLOAD", "0") == "1") and os.environ.get("SCB_BENCH_E2E_PLAIN", "0") == "0"
 
         def e2e_step():
             if one_call:
@@ -478,11 +480,15 @@ def run_ours(args):
             note = "scb_poly_product_from_host (pinned host tables, H2D) + Prover::new + all rounds + Fiat-Shamir, per step"
             if F.policy == 0 and pc.value + rc_.value > 0 and os.environ.get("SCB_HOST_PACK", "1") != "0":
                 h2d = hb.value  # bytes of the copies the last step queued, counted by the library as it queued them
+                if world > 1:
+                    tb = torch.tensor([h2d], device="cuda", dtype=torch.int64)
+                    dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+                    h2d = int(tb.item())
                 wire21 = p < (1 << 21) and os.environ.get("SCB_HOST_PACK_WIRE", "21") == "21"
                 upload = {"chunk_entries": K * (1 << v) // (pc.value + rc_.value), "chunks_narrowed_on_host": pc.value,
                           "chunks_narrowed_on_device": rc_.value,
                           "host_lane_wire_format": "three 21-bit entries per 64-bit word" if wire21 else "uint32",
-                          "host_pack_threads": min(32, int(os.environ.get("SCB_HOST_PACK_THREADS", os.cpu_count() or 1)))}
+                          "host_pack_threads_per_rank": min(32, int(os.environ.get("SCB_HOST_PACK_THREADS", max(1, (os.cpu_count() or 1) // world))))}
         e2e = {"value": total_entries / (ems * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ems,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": rounds * (K + 1) * E * n_gpus, "note": note}
         if upload:

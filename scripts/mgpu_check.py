@@ -34,6 +34,26 @@ for p, lv, K, cat in ((1572869, 20, 3, 16), (1572869, 18, 3, 3), (1572869, 17, 4
         good = msgs == want and c_1 == T.Prover(full).c_1() and T.verify_transcript(msgs, T.Verifier(lv + lg, full))
         print(f"p_bits={F.bits} lv={lv} K={K} consolidate_at={cat}: {'ok' if good else 'MISMATCH'}")
         ok = ok and good
+# slabs uploaded from host tables through the narrowing upload (packed uint32 from the start): same transcript
+os.environ["SCB_HOST_PACK_MIN_VARS"] = "8"
+os.environ["SCB_HOST_PACK_CHUNK_LOG2"] = "10"
+os.environ["SCB_HOST_PACK_RAW"] = "2"
+for p, lv, K, cat in ((1572869, 20, 3, 16), (1572869, 17, 4, 16), (1572869, 12, 3, 4), (389, 9, 2, 16)):
+    F = T.Field(p)
+    slabs = [T.DenseMultilinearExtension.synthetic(F, lv, 900 + k, start=rank << lv) for k in range(K)]
+    c_1, msgs = prove_sharded_p2p(T.ProductMLE.new(slabs), peers, consolidate_at=cat)
+    host = [s_.to_evaluations_mont() for s_ in slabs]
+    for rep in range(2):
+        c_1b, msgs_b = prove_sharded_p2p(T.ProductMLE.from_host_tables(F, lv, host), peers, consolidate_at=cat)
+        if msgs_b != msgs or c_1b != c_1:
+            print(f"rank {rank}: transcript from uploaded slabs differs (p_bits={F.bits} lv={lv} rep={rep})")
+            ok = False
+    c_1c, msgs_c = prove_sharded(CudaProductEngine(T.ProductMLE.from_host_tables(F, lv, host)), consolidate_at=cat)
+    if msgs_c != msgs or c_1c != c_1:
+        print(f"rank {rank}: NCCL transcript from uploaded slabs differs (p_bits={F.bits} lv={lv})")
+        ok = False
+    if rank == 0:
+        print(f"uploaded slabs p_bits={F.bits} lv={lv} K={K}: {'ok' if ok else 'MISMATCH'}")
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
