@@ -28,6 +28,7 @@ extern "C" {
     fn scb_mle_from_host(f: *const scb_field, num_vars: u32, evals: *const u64, out: *mut *mut scb_mle) -> c_int;
     fn scb_mle_free(m: *mut scb_mle);
     fn scb_poly_product(tables: *const *const scb_mle, k: u32, out: *mut *mut scb_poly) -> c_int;
+    fn scb_poly_product_from_host(f: *const scb_field, k: u32, num_vars: u32, host_tables: *const *const u64, out: *mut *mut scb_poly) -> c_int;
     fn scb_poly_matmul_g_new(f: *const scb_field, n: u32, a: *const u64, b: *const u64, point: *const u64,
                              out: *mut *mut scb_poly) -> c_int;
     fn scb_poly_clone(p: *const scb_poly, out: *mut *mut scb_poly) -> c_int;
@@ -71,8 +72,20 @@ impl<F: PrimeField> GpuPoly<F> {
         f
     }
 
-    /// Product of K dense multilinear tables over the same variables (`ProductMLE<K>`).
+    /// Product of K dense multilinear tables over the same variables (`ProductMLE<K>`): one call takes all K slices
+    /// as they lie in memory; small-prime tables are narrowed on their way to the device (include/sumcheck_b200.h).
     pub fn product(tables: &[&[F]]) -> Self {
+        let field = Self::field();
+        let nv = tables[0].len().trailing_zeros();
+        assert!(tables.iter().all(|t| t.len() == 1usize << nv), "The size of evaluations should be 2^num_vars.");
+        let ptrs: Vec<*const u64> = tables.iter().map(|t| as_words(t)).collect();
+        let mut poly = ptr::null_mut();
+        check(unsafe { scb_poly_product_from_host(field, ptrs.len() as u32, nv, ptrs.as_ptr(), &mut poly) });
+        Self { field, poly, owns_field: true, _f: PhantomData }
+    }
+
+    /// The same from tables that are already on the device (`scb_mle` handles are built one by one).
+    pub fn product_of_mles(tables: &[&[F]]) -> Self {
         let field = Self::field();
         let nv = tables[0].len().trailing_zeros();
         let mut mles = vec![];

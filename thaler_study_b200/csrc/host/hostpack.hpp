@@ -122,7 +122,8 @@ struct PackStats {
 //   int  submit_packed(int worker, int slot, uint32_t table, uint64_t off, uint64_t n);
 //   int  raw_wait(int slot);                                    the device buffer of that slot is free again
 //   int  submit_raw(int slot, uint32_t table, uint64_t off, uint64_t n, const uint64_t* src);
-// Every call returns 0 or an error code, which stops all lanes and becomes the return value.
+// Every call returns 0 or an error code, which stops all lanes and becomes the return value (-2: no thread could be
+// started).  Nothing is thrown.
 template <class B>
 int run_pack_upload(B& be, const uint64_t* const* tables, uint32_t k, uint64_t len, uint64_t chunk, int workers, int raw_slots,
                     uint64_t* or_acc, PackStats* stats, bool streaming_stores = false, bool wire21 = false) {
@@ -167,8 +168,12 @@ int run_pack_upload(B& be, const uint64_t* const* tables, uint32_t k, uint64_t l
     };
     std::vector<std::thread> th;
     th.reserve((size_t)workers + 1);
-    for (int w = 0; w < workers; ++w) th.emplace_back(pack_lane, w);
-    if (raw_slots > 0) th.emplace_back(raw_lane);
+    try {
+        for (int w = 0; w < workers; ++w) th.emplace_back(pack_lane, w);
+        if (raw_slots > 0) th.emplace_back(raw_lane);
+    } catch (...) {  // no more threads to be had: the lanes that did start finish the list
+        if (th.empty()) err.store(-2);
+    }
     for (auto& t : th) t.join();
     *or_acc = acc.load();
     if (stats) {
