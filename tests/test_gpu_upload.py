@@ -41,14 +41,16 @@ def test_packed_upload_matches_oracle_transcript(p, K, monkeypatch):
         pytest.skip("degree >= characteristic")
     OF, F = O.Field(p), T.Field(p)
     rnd = random.Random(1000 * K + p)
-    for v, threads, raw, wire, nt in ((6, 1, 1, 21, 1), (7, 2, 0, 21, 0), (7, 2, 0, 32, 1), (9, 3, 1, 32, 0), (12, 4, 1, 21, 1), (12, 4, 0, 21, 1)):
-        _small(monkeypatch, threads, raw, wire=wire, nt=nt)
+    # chunk sizes 2^6 and 2^7: a chunk's last 21-bit word holds one entry (64 = 3*21 + 1) or two (128 = 3*42 + 2)
+    for v, threads, raw, wire, nt, cl in ((6, 1, 1, 21, 1, 6), (7, 2, 0, 21, 0, 6), (7, 2, 0, 32, 1, 6), (9, 3, 1, 32, 0, 6), (12, 4, 1, 21, 1, 6),
+                                          (12, 4, 0, 21, 1, 6), (9, 3, 1, 21, 0, 7), (11, 2, 0, 21, 1, 7)):
+        _small(monkeypatch, threads, raw, chunk_log2=cl, wire=wire, nt=nt)
         vals = [[rnd.randrange(p) for _ in range(1 << v)] for _ in range(K)]
         g = T.ProductMLE.from_host_tables(F, v, vals)
         packed_chunks, raw_chunks = _stats()
-        assert packed_chunks + raw_chunks == K * (1 << (v - 6)) and (raw or raw_chunks == 0)
-        per_chunk = 22 * 8 if wire == 21 else 64 * 4  # ceil(64 / 3) words, or 64 uint32
-        assert _stats.h2d_bytes == packed_chunks * per_chunk + raw_chunks * 64 * 8
+        assert packed_chunks + raw_chunks == K * (1 << (v - cl)) and (raw or raw_chunks == 0)
+        per_chunk = -(-(1 << cl) // 3) * 8 if wire == 21 else (1 << cl) * 4  # ceil(chunk / 3) words, or chunk uint32
+        assert _stats.h2d_bytes == packed_chunks * per_chunk + raw_chunks * (1 << cl) * 8
         assert g.num_vars() == v
         for k in range(K):
             assert g.table(k).to_evaluations() == vals[k]

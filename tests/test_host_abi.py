@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 
 @pytest.mark.parametrize("k,nv,chunk_log2,workers,raw_lane", [(1, 6, 6, 1, 0), (3, 12, 6, 4, 1), (4, 14, 8, 7, 1), (2, 16, 10, 3, 0),
-                                                              (3, 20, 16, 8, 1), (1, 10, 10, 2, 1)])
+                                                              (3, 20, 16, 8, 1), (1, 10, 10, 2, 1), (2, 13, 7, 3, 1), (3, 15, 9, 5, 0)])
 def test_packed_upload_scheduler_on_a_memcpy_backend(k, nv, chunk_log2, workers, raw_lane):
     """host/hostpack.hpp: pack workers take chunks from the front, the raw lane from the back; every entry must arrive
     narrowed at its place exactly once (no device involved: the back end copies into host memory)."""
