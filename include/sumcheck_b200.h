@@ -57,6 +57,15 @@ int scb_synchronize(void);
 /* number of kernels this library launched since load / last reset (bench.py's gpu_launches) */
 int scb_launch_count(uint64_t* out, int reset);
 
+/* Tuning / diagnostic switches (thaler_study_b200/csrc/options.hpp lists them with their defaults).  This is the ONLY
+ * way to change them: the library never reads the process environment.  Every switch selects between code paths that
+ * return the same field elements and transcript bytes.  Process-wide; set them before the calls they affect.
+ * SCB_EINVAL for an unknown name.  scb_option_name(i) enumerates the names (NULL past the last). */
+int scb_set_option(const char* name, int64_t value);
+int scb_get_option(const char* name, int64_t* out);
+const char* scb_option_name(uint32_t index);
+void scb_reset_options(void);
+
 /* ------------------------------------------------------------------ field (a11) */
 /* replaces #[derive(MontConfig)] #[modulus = ..] + Fp64<MontBackend<_,1>> (sum-check-protocol/src/lib.rs:349-354);
  * n_limbs in {1, 4}; derives -p^-1 mod 2^64, R, R^2 */
@@ -120,12 +129,14 @@ int scb_poly_matmul_g(const scb_mle* f_a, const scb_mle* f_b, scb_poly** out);
  * Small-prime fields (one limb, p < 2^28) and num_vars >= 22: the tables cross PCIe narrowed where the host cores keep
  * up (several threads, pinned staging; three 21-bit entries per 64-bit word when p < 2^21, uint32 otherwise) and as
  * they are where not, narrowed on the device -- the handle then holds the packed uint32 layout the prover's own folded
- * tables use (scb_poly_allow_packed).  SCB_EINVAL if an entry is not below 2^bits(p).  Switches: SCB_HOST_PACK=0
- * (plain copies), SCB_HOST_PACK_THREADS, SCB_HOST_PACK_MIN_VARS, SCB_HOST_PACK_CHUNK_LOG2, SCB_HOST_PACK_RAW=0 (no
- * device-side lane; it is also skipped when a table is not in pinned memory), SCB_HOST_PACK_WIRE=32 (uint32 on the wire), SCB_HOST_PACK_NT=1 (streaming stores into the staging buffers). */
+ * tables use (scb_poly_allow_packed).  SCB_EINVAL if an entry is not a canonical field element (>= p).  Options
+ * (scb_set_option): host_pack = 0 (plain copies), host_pack_threads, host_pack_min_vars, host_pack_chunk_log2,
+ * host_pack_raw = 0 (no device-side lane; it is also skipped when a table is not in pinned memory), host_pack_wire = 32
+ * (uint32 on the wire), host_pack_nt = 1 (streaming stores into the staging buffers). */
 int scb_poly_product_from_host(const scb_field* f, uint32_t k, uint32_t num_vars, const uint64_t* const* host_tables, scb_poly** out);
 /* scb_mle_from_host and the two *_multilinear_from_evaluations calls take the same narrowing upload for such tables
- * when the process is the only rank of its box (LOCAL_WORLD_SIZE unset or 1) and widen to 8-byte entries on the device. */
+ * when the process is the only rank of its box (option local_ranks = 1, the default; the sharded driver sets it) and
+ * widen to 8-byte entries on the device. */
 /* the last packed upload: chunks narrowed by the host lane and by the device lane, bytes of all its H2D copies */
 int scb_host_pack_stats(uint64_t* packed_chunks, uint64_t* raw_chunks, uint64_t* h2d_bytes);
 /* the upload's host-side scheduler run against a memcpy back end on k random tables (no device needed): SCB_OK if
@@ -243,7 +254,11 @@ void scb_verifier_free(scb_verifier* v);
 int scb_verifier_set_c_1(scb_verifier* v, const uint64_t* c_1);            /* :271-273 */
 /* Verifier::round(g_j, rng) :278-330 with rng.draw() == r_j.  *final_round = 1 and *accepted set on the
  * last round (VerifierRoundResult::FinalRound), else *final_round = 0 (JthRound(r_j)).
- * SCB_EVERIFY = ProverClaimMismatch, SCB_ENOPOLY = NoPolySet. */
+ * SCB_EVERIFY = ProverClaimMismatch, SCB_ENOPOLY = NoPolySet.
+ * Option strict_verifier (default 1): the final round ALSO checks g_n(0) + g_n(1) == g_{n-1}(r_{n-1}), and a
+ * one-variable verifier evaluates its oracle in its only round (FinalRound) -- the reference's :298-310 and
+ * :284-297 skip both, which lets a false c_1 through.  Honest transcripts are unaffected;
+ * strict_verifier = 0 reproduces the reference literally. */
 int scb_verifier_round(scb_verifier* v, const uint64_t* degrees, const uint64_t* coeffs, uint32_t n_terms, const uint64_t* r_j,
                        int* final_round, int* accepted);
 
@@ -252,9 +267,13 @@ int scb_verifier_round(scb_verifier* v, const uint64_t* degrees, const uint64_t*
  * Consumes the prover's rounds.  out = g_1 || g_2 || ...; offsets[i]..offsets[i+1] delimits message i
  * (offsets has num_vars + 1 entries). */
 int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t cap, size_t* out_len, uint64_t* offsets);
-/* verify_transcript(transcript, verifier)  fiat-shamir/src/lib.rs:123-143 */
-int scb_fs_verify_transcript(scb_verifier* v, const uint8_t* transcript, const uint64_t* offsets, uint32_t n_msgs,
-                             int* accepted);
+/* verify_transcript(transcript, verifier)  fiat-shamir/src/lib.rs:123-143.  `transcript` is untrusted input:
+ * offsets[0] == 0 <= offsets[1] <= ... <= offsets[n_msgs] <= transcript_len is enforced (SCB_EINVAL otherwise).
+ * With option strict_verifier (default 1) *accepted = 1 only if the verifier reached and passed its final round
+ * (n_msgs == n): the reference loops over whatever prefix it is given and never reaches the oracle check for a
+ * truncated transcript. */
+int scb_fs_verify_transcript(scb_verifier* v, const uint8_t* transcript, size_t transcript_len, const uint64_t* offsets,
+                             uint32_t n_msgs, int* accepted);
 
 /* The same hash chain as an explicit state machine, for provers whose round sums arrive in pieces (the sharded
  * multi-GPU prover: one row of (d+1) partial sums per rank).  absorb_round adds the n_parts rows mod p, turns the

@@ -35,9 +35,9 @@ for p, lv, K, cat in ((1572869, 20, 3, 16), (1572869, 18, 3, 3), (1572869, 17, 4
         print(f"p_bits={F.bits} lv={lv} K={K} consolidate_at={cat}: {'ok' if good else 'MISMATCH'}")
         ok = ok and good
 # slabs uploaded from host tables through the narrowing upload (packed uint32 from the start): same transcript
-os.environ["SCB_HOST_PACK_MIN_VARS"] = "8"
-os.environ["SCB_HOST_PACK_CHUNK_LOG2"] = "10"
-os.environ["SCB_HOST_PACK_RAW"] = "2"
+T.set_option("host_pack_min_vars", 8)
+T.set_option("host_pack_chunk_log2", 10)
+T.set_option("host_pack_raw", 2)
 for p, lv, K, cat in ((1572869, 20, 3, 16), (1572869, 17, 4, 16), (1572869, 12, 3, 4), (389, 9, 2, 16)):
     F = T.Field(p)
     slabs = [T.DenseMultilinearExtension.synthetic(F, lv, 900 + k, start=rank << lv) for k in range(K)]

@@ -54,7 +54,7 @@ def test_packed_children_equal_plain_children(p, K):
 def test_transcript_independent_of_packing_and_tail():
     code = (
         "import sys; sys.path.insert(0, %r)\n"
-        "import thaler_study_b200 as T\n"
+        "import thaler_study_b200 as T; T.options_from_env()\n"
         "for p, v, K in ((1572869, 19, 3), (389, 16, 2), (5, 15, 4)):\n"
         "    F = T.Field(p)\n"
         "    g = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, 70 + k) for k in range(K)])\n"

@@ -92,7 +92,7 @@ def test_pair_kernel_matches_one_round_per_pass():
     barrier, the packed layouts and the solo endgame all take part."""
     code = (
         "import sys; sys.path.insert(0, %r)\n"
-        "import thaler_study_b200 as T\n"
+        "import thaler_study_b200 as T; T.options_from_env()\n"
         "for p, v, K in ((1572869, 20, 3), (1572869, 19, 3), (1572869, 17, 4), (1572869, 16, 2), (389, 15, 1), (5, 14, 3), (268435399, 18, 3), (1572869, 5, 3), (1572869, 4, 2)):\n"
         "    F = T.Field(p)\n"
         "    g = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, 70 + k) for k in range(K)])\n"

@@ -367,6 +367,57 @@ def test_error_conventions():
             kind, r = v.round(p.round(r, j), rng)
 
 
+@pytest.mark.parametrize("n", [1, 2, 5])
+def test_strict_verifier_rejects_a_false_claim_the_reference_logic_accepts(n):
+    """The reference's last-round branch (sum-check-protocol/src/lib.rs:298-310) never links g_n to g_{n-1}: a prover
+    who claims c_1 + 1, shifts g_1 by 1/2 and then sends the honest messages is accepted.  The default (option
+    strict_verifier = 1) rejects it; honest runs are accepted either way with the same bytes."""
+    OF, F = O.FP1572869, T.Field(1572869)
+    rnd = random.Random(77 + n)
+    t = [rand_table(OF, n, rnd) for _ in range(2)]
+    g = T.ProductMLE.new([T.DenseMultilinearExtension.from_evaluations_vec(F, n, x) for x in t])
+    half = pow(2, -1, OF.p)
+
+    def run(strict, cheat):
+        T.set_option("strict_verifier", 1 if strict else 0)
+        prover = T.Prover(g)
+        ver = T.Verifier(n, g)
+        ver.set_c_1((prover.c_1() + (1 if cheat else 0)) % OF.p)
+        rng, r, out = PyRng(OF, 3), 1, None
+        for j in range(n):
+            g_j = prover.round(r, j)
+            if cheat and j == 0:
+                d = dict(g_j.coeffs)
+                d[0] = (d.get(0, 0) + half) % OF.p
+                g_j = T.SparsePolynomial(F, sorted(d.items()))
+            kind, val = ver.round(g_j, rng)
+            if kind == "JthRound":
+                r = val
+            else:
+                out = val
+        return out
+
+    assert run(True, False) is True and run(False, False) is (True if n > 1 else None)
+    if n == 1:
+        assert run(True, True) is False          # the only round evaluates the oracle: g_1'(r) != g(r)
+        assert run(False, True) is None          # reference: the first-round branch returns before any oracle check
+    else:
+        with pytest.raises(T.ProverClaimMismatch):
+            run(True, True)
+        assert run(False, True) is True          # the reference's literal logic accepts the false claim
+
+
+def test_truncated_transcript_is_not_accepted():
+    OF, F = O.FP389, T.Field(389)
+    rnd = random.Random(5)
+    g = T.ProductMLE.new([T.DenseMultilinearExtension.from_evaluations_vec(F, 4, rand_table(OF, 4, rnd)) for _ in range(2)])
+    tr = T.generate_transcript(T.Prover(g))
+    assert T.verify_transcript(tr, T.Verifier(4, g))
+    assert not T.verify_transcript(tr[:3], T.Verifier(4, g))
+    T.set_option("strict_verifier", 0)  # fiat-shamir/src/lib.rs:131-141 loops over whatever it is given
+    assert T.verify_transcript(tr[:3], T.Verifier(4, g))
+
+
 # ----------------------------------------------------------------------------- size-independent properties at scale
 @pytest.mark.parametrize("OF,v,K", [(O.FP1572869, 22, 3), (O.FP1572869, 26, 3), (O.Field(268435399), 25, 4), (O.FP389, 23, 2), (O.BLS12_381_FR, 18, 3),
                                     (O.Field((1 << 61) - 1), 20, 2)], ids=lambda x: str(getattr(x, "bits", x)))
@@ -396,7 +447,7 @@ def test_tail_kernel_matches_per_round_launches():
 
     code = (
         "import sys; sys.path.insert(0, %r)\n"
-        "import thaler_study_b200 as T\n"
+        "import thaler_study_b200 as T; T.options_from_env()\n"
         "for p, v, K in ((1572869, 13, 3), (5, 9, 2), (0xFFFFFFFF00000001, 11, 4), (%d, 10, 3)):\n"
         "    F = T.Field(p)\n"
         "    g = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, 50 + k) for k in range(K)])\n"
@@ -430,7 +481,7 @@ def test_grid_resident_kernel_matches_per_round_launches():
 
     code = (
         "import sys; sys.path.insert(0, %r)\n"
-        "import thaler_study_b200 as T\n"
+        "import thaler_study_b200 as T; T.options_from_env()\n"
         "for p, v, K in ((1572869, 19, 3), (1572869, 16, 4), (1572869, 6, 1), (5, 15, 2), (0xFFFFFFFF00000001, 17, 3), (%d, 15, 2)):\n"
         "    F = T.Field(p)\n"
         "    g = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, 90 + k) for k in range(K)])\n"

@@ -25,13 +25,13 @@ def _stats():
     return a.value, b.value
 
 
-def _small(monkeypatch, threads=3, raw=1, chunk_log2=6, wire=21, nt=1):
-    monkeypatch.setenv("SCB_HOST_PACK_MIN_VARS", "6")
-    monkeypatch.setenv("SCB_HOST_PACK_WIRE", str(wire))  # 21: three entries per word when p < 2^21; 32: uint32
-    monkeypatch.setenv("SCB_HOST_PACK_NT", str(nt))
-    monkeypatch.setenv("SCB_HOST_PACK_CHUNK_LOG2", str(chunk_log2))
-    monkeypatch.setenv("SCB_HOST_PACK_THREADS", str(threads))
-    monkeypatch.setenv("SCB_HOST_PACK_RAW", "2" if raw else "0")  # 2: device lane even from pageable (numpy) memory
+def _small(threads=3, raw=1, chunk_log2=6, wire=21, nt=1):
+    T.set_option("host_pack_min_vars", 6)
+    T.set_option("host_pack_wire", wire)  # 21: three entries per word when p < 2^21; 32: uint32
+    T.set_option("host_pack_nt", nt)
+    T.set_option("host_pack_chunk_log2", chunk_log2)
+    T.set_option("host_pack_threads", threads)
+    T.set_option("host_pack_raw", 2 if raw else 0)  # 2: device lane even from pageable (numpy) memory
 
 
 @pytest.mark.parametrize("p", [5, 389, 1572869])
@@ -44,7 +44,7 @@ def test_packed_upload_matches_oracle_transcript(p, K, monkeypatch):
     # chunk sizes 2^6 and 2^7: a chunk's last 21-bit word holds one entry (64 = 3*21 + 1) or two (128 = 3*42 + 2)
     for v, threads, raw, wire, nt, cl in ((6, 1, 1, 21, 1, 6), (7, 2, 0, 21, 0, 6), (7, 2, 0, 32, 1, 6), (9, 3, 1, 32, 0, 6), (12, 4, 1, 21, 1, 6),
                                           (12, 4, 0, 21, 1, 6), (9, 3, 1, 21, 0, 7), (11, 2, 0, 21, 1, 7)):
-        _small(monkeypatch, threads, raw, chunk_log2=cl, wire=wire, nt=nt)
+        _small(threads, raw, chunk_log2=cl, wire=wire, nt=nt)
         vals = [[rnd.randrange(p) for _ in range(1 << v)] for _ in range(K)]
         g = T.ProductMLE.from_host_tables(F, v, vals)
         packed_chunks, raw_chunks = _stats()
@@ -70,23 +70,42 @@ def test_packed_upload_matches_oracle_transcript(p, K, monkeypatch):
 
 
 def test_packed_upload_rejects_non_canonical_entries(monkeypatch):
-    _small(monkeypatch)
+    _small()
     F = T.Field(1572869)
     v = 10
     for lane_raw, wire in ((0, 21), (1, 21), (0, 32), (1, 32)):
-        monkeypatch.setenv("SCB_HOST_PACK_RAW", "2" if lane_raw else "0")
-        monkeypatch.setenv("SCB_HOST_PACK_WIRE", str(wire))
+        T.set_option("host_pack_raw", 2 if lane_raw else 0)
+        T.set_option("host_pack_wire", wire)
         for where in (0, 517, (1 << v) - 1):
+            # a real comparison with p: 2^bits(p), p itself, the largest 21-bit value and a 64-bit value all fail
+            for bad in (1 << 21, 1572869, (1 << 21) - 1, (1 << 63) + 5):
+                t = np.zeros([1 << v, 1], dtype=np.uint64)
+                t[where, 0] = bad
+                with pytest.raises(T.ScbError) as ei:
+                    T.ProductMLE.from_host_tables(F, v, [t, np.ones([1 << v, 1], dtype=np.uint64)])
+                assert ei.value.code == _lib.SCB_EINVAL
             t = np.zeros([1 << v, 1], dtype=np.uint64)
-            t[where, 0] = 1 << 21  # >= 2^bits(p)
-            with pytest.raises(T.ScbError) as ei:
-                T.ProductMLE.from_host_tables(F, v, [t, np.ones([1 << v, 1], dtype=np.uint64)])
-            assert ei.value.code == _lib.SCB_EINVAL
+            t[where, 0] = 1572868  # p - 1 is fine
+            T.ProductMLE.from_host_tables(F, v, [t, np.ones([1 << v, 1], dtype=np.uint64)])
+    # the plain 8-byte uploads check the same precondition on the device
+    T.set_option("host_pack", 0)
+    for Fp, n, bad in ((F, 1, 1572869), (T.Field((1 << 61) - 1), 1, (1 << 61) - 1), (T.Field(O.BLS12_381_FR.p), 4, O.BLS12_381_FR.p)):
+        t = np.zeros([1 << v, n], dtype=np.uint64)
+        for l in range(n):
+            t[33, l] = (bad >> (64 * l)) & 0xFFFFFFFFFFFFFFFF
+        with pytest.raises(T.ScbError) as ei:
+            T.DenseMultilinearExtension.from_evaluations_vec(Fp, v, t)
+        assert ei.value.code == _lib.SCB_EINVAL
+        with pytest.raises(T.ScbError) as ei:
+            T.ProductMLE.from_host_tables(Fp, v, [t, t])
+        assert ei.value.code == _lib.SCB_EINVAL
+        t[33, 0] -= 1
+        T.DenseMultilinearExtension.from_evaluations_vec(Fp, v, t)
 
 
 @pytest.mark.parametrize("p", [(1 << 61) - 1, O.BLS12_381_FR.p], ids=["p61", "bls12_381_fr"])
 def test_other_fields_take_the_plain_copy(p, monkeypatch):
-    _small(monkeypatch)
+    _small()
     OF, F = O.Field(p), T.Field(p)
     rnd = random.Random(9)
     v, K = 8, 2
@@ -102,13 +121,13 @@ def test_other_fields_take_the_plain_copy(p, monkeypatch):
 def test_large_tables_default_switches(switch, monkeypatch):
     """2^24-entry tables with the default chunking (2^20 entries): both lanes run; the proof equals the plain upload's,
     which the C oracle anchors through the round sums of the first rounds."""
-    monkeypatch.setenv("SCB_HOST_PACK_RAW", "2")  # numpy tables are pageable: ask for the device lane explicitly
+    T.set_option("host_pack_raw", 2)  # numpy tables are pageable: ask for the device lane explicitly
     if switch == "no_raw_lane":
-        monkeypatch.setenv("SCB_HOST_PACK_RAW", "0")
+        T.set_option("host_pack_raw", 0)
     if switch == "wire32":
-        monkeypatch.setenv("SCB_HOST_PACK_WIRE", "32")
+        T.set_option("host_pack_wire", 32)
     if switch == "off":
-        monkeypatch.setenv("SCB_HOST_PACK", "0")
+        T.set_option("host_pack", 0)
     p, v, K = 1572869, 24, 3
     F, cf = T.Field(p), CField(p)
     tabs = [cf.synth(500 + k, 0, 1 << v) for k in range(K)]  # Montgomery words, ark's layout
@@ -139,7 +158,7 @@ def test_mle_from_host_narrows_large_tables_on_the_way(p, monkeypatch):
     want = dev.evaluate_be(r)
     outs = []
     for switch in ("1", "0"):
-        monkeypatch.setenv("SCB_HOST_PACK", switch)
+        T.set_option("host_pack", int(switch))
         m = T.DenseMultilinearExtension.from_evaluations_vec(F, v, tab)
         if switch == "1":
             packed_chunks, raw_chunks = _stats()
@@ -151,7 +170,7 @@ def test_mle_from_host_narrows_large_tables_on_the_way(p, monkeypatch):
     assert outs == [want, want]
     bad = np.array(tab, copy=True)
     bad[12345] = 1 << 40
-    monkeypatch.setenv("SCB_HOST_PACK", "1")
+    T.set_option("host_pack", 1)
     with pytest.raises(T.ScbError) as ei:
         T.DenseMultilinearExtension.from_evaluations_vec(F, v, bad)
     assert ei.value.code == _lib.SCB_EINVAL

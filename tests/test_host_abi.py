@@ -126,7 +126,7 @@ def test_sha256_scalar_and_sha_extension_paths_agree():
     code = (
         "import sys; sys.path.insert(0, %r)\n"
         "import ctypes as C, numpy as np\n"
-        "import thaler_study_b200 as T\n"
+        "import thaler_study_b200 as T; T.options_from_env()\n"
         "from thaler_study_b200._lib import lib\n"
         "for p in (5, 389, 1572869, 0xFFFFFFFF00000001, %d):\n"
         "    F = T.Field(p)\n"
@@ -148,3 +148,70 @@ def test_sha256_scalar_and_sha_extension_paths_agree():
             msg = bytes((j * 31 + n) & 255 for j in range(n))
             assert int(vals[i]) == O.hash_to_field(OF, msg), (p, n)
             i += 1
+
+
+# ----------------------------------------------------------------------------- options (no environment reads)
+def test_options_are_set_through_the_abi_only():
+    names = T.option_names()
+    assert "pairs" in names and "strict_verifier" in names and len(names) == len(set(names))
+    assert T.get_option("tail_vars") == 14
+    T.set_option("tail_vars", 5)
+    assert T.get_option("tail_vars") == 5
+    T.reset_options()
+    assert T.get_option("tail_vars") == 14
+    with pytest.raises(T.ScbError) as ei:
+        T.set_option("no_such_switch", 1)
+    assert ei.value.code == _lib.SCB_EINVAL
+    # the harness helper maps SCB_<NAME> variables to scb_set_option calls; the library itself has no getenv
+    assert T.options_from_env({"SCB_TAIL_VARS": "7", "SCB_PAIRS": "0", "SCB_UNRELATED": "1", "HOME": "/"}) == {"tail_vars": 7, "pairs": 0}
+    assert T.get_option("tail_vars") == 7 and T.get_option("pairs") == 0
+    T.reset_options()
+    src = os.path.join(ROOT, "thaler_study_b200", "csrc")
+    for dirpath, _, files in os.walk(src):
+        for fn in files:
+            if fn.endswith((".cu", ".cuh", ".cpp", ".hpp", ".inc")):
+                assert "getenv" not in open(os.path.join(dirpath, fn)).read(), fn
+
+
+# ----------------------------------------------------------------------------- verifier hardening (host-only parts)
+def _final_round_without_link(strict):
+    """n = 2, no oracle: g_1 consistent with a false c_1, g_2 NOT linked to g_1(r_1).  The reference's last-round
+    branch (sum-check-protocol/src/lib.rs:298-310) goes straight to the oracle; the strict verifier rejects first."""
+    F = T.Field(1572869)
+    T.set_option("strict_verifier", 1 if strict else 0)
+    v = T.Verifier(2, None, F)
+    v.set_c_1(7)                                      # g_1(0) + g_1(1) = 3 + 4
+
+    class R:
+        def __init__(self, vals):
+            self.vals = list(vals)
+
+        def draw(self):
+            return self.vals.pop(0)
+
+    rng = R([5, 6])
+    assert v.round(T.SparsePolynomial(F, [(0, 3), (1, 1)]), rng) == ("JthRound", 5)   # g_1 = 3 + X, g_1(5) = 8
+    return v.round(T.SparsePolynomial(F, [(0, 1), (1, 1)]), rng)                      # g_2(0) + g_2(1) = 3 != 8
+
+
+def test_strict_verifier_checks_the_link_in_the_final_round():
+    with pytest.raises(T.ProverClaimMismatch):
+        _final_round_without_link(strict=True)
+    with pytest.raises(T.NoPolySet):   # the reference's literal logic gets as far as the oracle call
+        _final_round_without_link(strict=False)
+
+
+def test_verify_transcript_validates_offsets():
+    import ctypes as C
+
+    import numpy as np
+
+    F = T.Field(389)
+    v = T.Verifier(3, None, F)
+    raw = bytes(40)
+    buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+    acc = C.c_int(1)
+    for offs in ([0, 50], [1, 10], [0, 20, 10]):
+        o = np.array(offs, dtype=np.uint64)
+        rc = _lib.lib.scb_fs_verify_transcript(v._h, buf, len(raw), o.ctypes.data_as(_lib.u64p), len(offs) - 1, C.byref(acc))
+        assert rc == _lib.SCB_EINVAL and acc.value == 0, offs

@@ -5,7 +5,18 @@ The compute lives in ``libsumcheck_b200.so`` (hand-written sm_100a CUDA + a C++ 
 and the multi-GPU driver.  There is no CPU fallback: importing fails loudly if the library is not built, and every
 compute call fails with SCB_ECUDA without a CUDA device.
 """
-from ._lib import SO_PATH, NoPolySet, ProverClaimMismatch, ScbError, lib  # noqa: F401
+from ._lib import (  # noqa: F401
+    SO_PATH,
+    NoPolySet,
+    ProverClaimMismatch,
+    ScbError,
+    get_option,
+    lib,
+    option_names,
+    options_from_env,
+    reset_options,
+    set_option,
+)
 from .api import (  # noqa: F401
     KIND_GKR_W,
     KIND_MATMUL_G,

@@ -30,6 +30,10 @@ SIGNATURES = {
     "scb_set_stream": (C.c_int, [vp]),
     "scb_synchronize": (C.c_int, []),
     "scb_launch_count": (C.c_int, [u64p, C.c_int]),
+    "scb_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
+    "scb_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64)]),
+    "scb_option_name": (C.c_char_p, [C.c_uint32]),
+    "scb_reset_options": (None, []),
     "scb_field_create": (C.c_int, [C.c_uint32, u64p, vpp]),
     "scb_field_free": (None, [vp]),
     "scb_field_n_limbs": (C.c_int, [vp, u32p]),
@@ -99,7 +103,7 @@ SIGNATURES = {
     "scb_verifier_set_c_1": (C.c_int, [vp, u64p]),
     "scb_verifier_round": (C.c_int, [vp, u64p, u64p, C.c_uint32, u64p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "scb_fs_generate_transcript": (C.c_int, [vp, u8p, C.c_size_t, C.POINTER(C.c_size_t), u64p]),
-    "scb_fs_verify_transcript": (C.c_int, [vp, u8p, u64p, C.c_uint32, C.POINTER(C.c_int)]),
+    "scb_fs_verify_transcript": (C.c_int, [vp, u8p, C.c_size_t, u64p, C.c_uint32, C.POINTER(C.c_int)]),
     "scb_circuit_create": (C.c_int, [vp, C.c_uint32, u32p, u8p, u32p, u32p, C.c_uint32, vpp]),
     "scb_circuit_free": (None, [vp]),
     "scb_circuit_num_vars_at": (C.c_int, [vp, C.c_uint32, u32p]),
@@ -165,3 +169,41 @@ def check(rc: int) -> None:
     if rc == SCB_ENOPOLY:
         raise NoPolySet(rc, msg)
     raise ScbError(rc, msg)
+
+
+# ---------------------------------------------------------------- options (scb_set_option; csrc/options.hpp)
+def set_option(name: str, value: int) -> None:
+    check(lib.scb_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str) -> int:
+    out = C.c_int64()
+    check(lib.scb_get_option(name.encode(), C.byref(out)))
+    return out.value
+
+
+def option_names():
+    names, i = [], 0
+    while True:
+        n = lib.scb_option_name(i)
+        if not n:
+            return names
+        names.append(n.decode())
+        i += 1
+
+
+def reset_options() -> None:
+    lib.scb_reset_options()
+
+
+def options_from_env(environ=None) -> dict:
+    """Harness helper (tests, scripts, bench.py): applies ``SCB_<NAME>=<int>`` variables as scb_set_option calls.
+    The LIBRARY never reads the environment; only a caller that asks for it here does."""
+    environ = os.environ if environ is None else environ
+    applied = {}
+    for n in option_names():
+        v = environ.get("SCB_" + n.upper())
+        if v is not None and v.strip().lstrip("-").isdigit():
+            set_option(n, int(v))
+            applied[n] = int(v)
+    return applied

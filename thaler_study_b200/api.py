@@ -542,7 +542,7 @@ def verify_transcript(transcript: Sequence[bytes], verifier: Verifier) -> bool:
         offs[i + 1] = o
     buf = (C.c_uint8 * max(len(raw), 1)).from_buffer_copy(raw.ljust(1, b"\0"))
     acc = C.c_int()
-    check(lib.scb_fs_verify_transcript(verifier._h, buf, _p64(offs), len(transcript), C.byref(acc)))
+    check(lib.scb_fs_verify_transcript(verifier._h, buf, len(raw), _p64(offs), len(transcript), C.byref(acc)))
     return bool(acc.value)
 
 

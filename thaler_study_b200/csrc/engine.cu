@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "internal.hpp"
+#include "options.hpp"
 #include "kernels.cuh"
 #include "eqfix.cuh"
 #include "gkr.cuh"
@@ -74,6 +75,7 @@ struct Ctx {
     uint64_t* d_scratch = nullptr; // small device scratch (points, results)
     TailMailbox* mailbox = nullptr; // mapped pinned host memory shared with the persistent tail kernel
     PersistCtl* persist_ctl = nullptr; // device memory: barrier state of the grid-wide resident kernel
+    unsigned int* d_flag = nullptr; // device word raised by k_check_canonical
     int coop = 0;                   // cooperative launches supported
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // bracket the resident kernels (scb_resident_stats)
 };
@@ -109,6 +111,7 @@ static int get_ctx(Ctx** out) {
             CU_TRY(cudaHostAlloc(&c.mailbox, sizeof(TailMailbox), cudaHostAllocMapped | cudaHostAllocPortable));
             std::memset((void*)c.mailbox, 0, sizeof(TailMailbox));
             CU_TRY(cudaMalloc(&c.persist_ctl, sizeof(PersistCtl)));
+            CU_TRY(cudaMalloc(&c.d_flag, 64));
             CU_TRY(cudaDeviceGetAttribute(&c.coop, cudaDevAttrCooperativeLaunch, dev));
             CU_TRY(cudaEventCreate(&c.ev0));
             CU_TRY(cudaEventCreate(&c.ev1));
@@ -150,7 +153,7 @@ static int occ_grid(const Ctx* c, KernelT kernel, uint64_t items, size_t dyn_sme
         }
     }
     if (pref_bps > 0) nb = pref_bps;
-    static const int bps_env = getenv("SCB_BPS") ? atoi(getenv("SCB_BPS")) : 0;
+    const int bps_env = (int)opt(OPT_bps);
     if (bps_env > 0) nb = bps_env;
     uint64_t want = (items + kThreads - 1) / kThreads;
     uint64_t cap = (uint64_t)c->sms * nb;
@@ -329,6 +332,28 @@ extern "C" int scb_synchronize(void) {
     CU_TRY(cudaStreamSynchronize(g_stream));
     return SCB_OK;
 }
+extern "C" int scb_set_option(const char* name, int64_t value) {
+    ARG_TRY(name, "null argument");
+    const int i = option_index(name);
+    if (i < 0) {
+        set_error("unknown option '%s'", name);
+        return SCB_EINVAL;
+    }
+    option_table().v[i].store(value);
+    return SCB_OK;
+}
+extern "C" int scb_get_option(const char* name, int64_t* out) {
+    ARG_TRY(name && out, "null argument");
+    const int i = option_index(name);
+    if (i < 0) {
+        set_error("unknown option '%s'", name);
+        return SCB_EINVAL;
+    }
+    *out = option_table().v[i].load();
+    return SCB_OK;
+}
+extern "C" const char* scb_option_name(uint32_t index) { return option_name((int)index); }
+extern "C" void scb_reset_options(void) { option_table().reset(); }
 extern "C" int scb_launch_count(uint64_t* out, int reset) {
     ARG_TRY(out, "null out");
     *out = reset ? g_launches.exchange(0) : g_launches.load();
@@ -409,6 +434,9 @@ static int mle_new(const std::shared_ptr<FieldImpl>& f, uint32_t nv, scb_mle** o
 }
 
 static int mle_upload_packed(Ctx* c, const FieldImpl& fi, uint32_t num_vars, const uint64_t* evals, Table* out, bool* done);  // upload_engine.inc
+// every entry of a freshly uploaded table must be a canonical field element (< p): the lazy accumulators of the
+// small-prime kernels size their head-room on it.  One read of the table on the device (upload_engine.inc); waits.
+static int check_canonical_table(Ctx* c, const FieldImpl& fi, const uint64_t* d_ptr, uint64_t n);
 extern "C" int scb_mle_from_host(const scb_field* f, uint32_t num_vars, const uint64_t* evals, scb_mle** out) {
     ARG_TRY(f && evals && out, "null argument");
     Ctx* c;
@@ -431,11 +459,15 @@ extern "C" int scb_mle_from_host(const scb_field* f, uint32_t num_vars, const ui
     scb_mle* m = nullptr;
     RC_TRY(mle_new(f->impl, num_vars, &m, true));
     cudaError_t e = cudaMemcpyAsync(m->t.buf->ptr, evals, m->t.buf->bytes, cudaMemcpyHostToDevice, g_stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);  // the caller may reuse `evals` on return
     if (e != cudaSuccess) {
         delete m;
         set_error("H2D copy failed: %s", cudaGetErrorString(e));
         return SCB_ECUDA;
+    }
+    const int rc = check_canonical_table(c, *f->impl, m->t.buf->ptr, m->t.len());  // waits: the caller may reuse `evals` on return
+    if (rc != SCB_OK) {
+        delete m;
+        return rc;
     }
     *out = m;
     return SCB_OK;
@@ -589,7 +621,7 @@ static int build_eq_tables(Ctx* c, const FieldImpl& f, const uint64_t* bitpt, ui
     if (v) std::memcpy(pa.w, bitpt, (size_t)8 * N * v);
     const uint32_t cap_bits = N == 1 ? 12 : 10;
     const size_t smem = (size_t)8 * N << cap_bits;
-    static const bool split = !(getenv("SCB_EQ_SPLIT") && atoi(getenv("SCB_EQ_SPLIT")) == 0);
+    const bool split = opt(OPT_eq_split) != 0;
     const uint32_t hb = v - lb;
     if (split && lb <= 18 && hb <= 18 && v >= 2) {
         // sub-tables of at most 2^9 entries in shared memory, the last level spread over the grid (eqfix.cuh)
@@ -612,8 +644,8 @@ static int eval_table(Ctx* c, const FieldImpl& f, const Table& t, const uint64_t
     ARG_TRY(v <= 34, "table too large for MLE evaluation");
     for (uint32_t j = 0; j < v; ++j) ARG_TRY(elem_canonical(f, bitpt + (size_t)j * N), "point coordinate is not canonical");
     // low table (shared memory, copied by every CTA) over lb index bits, high table (L2) over the rest
-    static const uint32_t lb_env = getenv("SCB_MLE_LB") ? (uint32_t)atoi(getenv("SCB_MLE_LB")) : 0;
-    static const int u_env = getenv("SCB_MLE_U") ? atoi(getenv("SCB_MLE_U")) : 0;
+    const uint32_t lb_env = (uint32_t)opt(OPT_mle_lb);
+    const int u_env = (int)opt(OPT_mle_u);
     uint32_t lb_max = N == 1 ? 12 : 10;
     if (lb_env >= 2 && lb_env < lb_max) lb_max = lb_env;
     const uint32_t lb = v < lb_max ? v : lb_max;
@@ -1064,7 +1096,7 @@ extern "C" int scb_poly_round_evals_device(const scb_poly* p, uint32_t n_points,
 template <int K, bool IN32, bool OUT32, int QP>
 static void launch_fold_sp(Ctx* c, const FieldDesc& d, TabsIn<K> in, TabsOut<K> o, ElemArg ra, uint64_t n_quads, uint64_t* res) {
     auto kern = k_fold_round_sp<K, IN32, OUT32, QP>;
-    static const int bps32 = getenv("SCB_BPS32") ? atoi(getenv("SCB_BPS32")) : 8;
+    const int bps32 = (int)opt(OPT_bps32);
     const int pref = IN32 ? bps32 : 5;  // measured sweet spots (profiles/r01_kernel_sweep.md)
     kern<<<occ_grid(c, kern, n_quads / QP, 0, pref), kThreads, 0, g_stream>>>(d, in, o, ra, n_quads / QP, c->partials, c->ticket, res, peer_arg(c));
 }
@@ -1130,7 +1162,7 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
             RC_TRY(alloc_buf((size_t)(out32 ? 4 : 8 * N) << q->t[k].nv, &q->t[k].buf));
         }
         const ElemArg ra = elem_arg(f, r);
-        static const int qp32 = getenv("SCB_QP32") && atoi(getenv("SCB_QP32")) > 0 ? atoi(getenv("SCB_QP32")) : 4;
+        const int qp32 = opt(OPT_qp32) > 0 ? (int)opt(OPT_qp32) : 4;
         if (f.policy == POL_SP && (in32 || out32)) {
             DISPATCH_K(p->t.size(), {
                 TabsIn<K> in;

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "hostfield.hpp"
+#include "../options.hpp"
 
 #if defined(__x86_64__) && defined(__GNUC__)
 #include <cpuid.h>
@@ -29,9 +30,8 @@ namespace scb {
 // The challenge derivation sits on the prover's critical path once the tables are small: two hash-to-field
 // evaluations per turn-around of the resident kernels.
 inline bool sha_ni_available() {
+    if (opt(OPT_sha_scalar) != 0) return false;  // tests: force the portable compression function
     static const bool ok = [] {
-        const char* off = std::getenv("SCB_SHA_SCALAR");  // tests: force the portable compression function
-        if (off && off[0] == '1') return false;
         unsigned a = 0, b = 0, c = 0, d = 0;
         if (!__get_cpuid_count(7, 0, &a, &b, &c, &d)) return false;
         const bool sha = (b >> 29) & 1;

@@ -21,12 +21,17 @@
 
 namespace scb {
 
-// narrow n 8-byte entries to 4 bytes; returns the OR of all entries (the caller checks the bits above the modulus)
-static inline uint64_t pack32_host(const uint64_t* __restrict__ src, uint32_t* __restrict__ dst, uint64_t n) {
+// Canonical-entry check shared by all lanes: acc |= v | (pm1 - v) with pm1 = p - 1.  For v < p both terms are below p;
+// for v >= p the difference wraps and sets bit 63.  So "every entry < p"  <=>  acc >> 63 == 0 -- a real comparison with
+// the modulus (not only with 2^bits(p)) at the price of one subtraction per entry.
+static inline bool pack_acc_ok(uint64_t acc) { return (acc >> 63) == 0; }
+
+// narrow n 8-byte entries to 4 bytes; returns the check accumulator (pack_acc_ok)
+static inline uint64_t pack32_host(const uint64_t* __restrict__ src, uint32_t* __restrict__ dst, uint64_t n, uint64_t pm1) {
     uint64_t acc = 0;
     for (uint64_t i = 0; i < n; ++i) {
         const uint64_t v = src[i];
-        acc |= v;
+        acc |= v | (pm1 - v);
         dst[i] = (uint32_t)v;
     }
     return acc;
@@ -37,12 +42,13 @@ static inline uint64_t pack32_host(const uint64_t* __restrict__ src, uint32_t* _
 #include <emmintrin.h>
 namespace scb {
 // the same with streaming stores: the staging buffer is written past the caches (no read-for-ownership of its lines)
-static inline uint64_t pack32_host_nt(const uint64_t* __restrict__ src, uint32_t* __restrict__ dst, uint64_t n) {
+static inline uint64_t pack32_host_nt(const uint64_t* __restrict__ src, uint32_t* __restrict__ dst, uint64_t n, uint64_t pm1) {
     __m128i acc = _mm_setzero_si128();
+    const __m128i pv = _mm_set1_epi64x((long long)pm1);
     uint64_t i = 0;
     for (; i + 4 <= n; i += 4) {
         const __m128i a = _mm_loadu_si128((const __m128i*)(src + i)), b = _mm_loadu_si128((const __m128i*)(src + i + 2));
-        acc = _mm_or_si128(acc, _mm_or_si128(a, b));
+        acc = _mm_or_si128(acc, _mm_or_si128(_mm_or_si128(a, b), _mm_or_si128(_mm_sub_epi64(pv, a), _mm_sub_epi64(pv, b))));
         const __m128i lo = _mm_castps_si128(_mm_shuffle_ps(_mm_castsi128_ps(a), _mm_castsi128_ps(b), _MM_SHUFFLE(2, 0, 2, 0)));
         _mm_stream_si128((__m128i*)(dst + i), lo);  // staging buffers are 16-byte aligned, chunks are multiples of 4
     }
@@ -50,25 +56,25 @@ static inline uint64_t pack32_host_nt(const uint64_t* __restrict__ src, uint32_t
     _mm_storeu_si128((__m128i*)w, acc);
     uint64_t r = w[0] | w[1];
     for (; i < n; ++i) {
-        r |= src[i];
+        r |= src[i] | (pm1 - src[i]);
         dst[i] = (uint32_t)src[i];
     }
     _mm_sfence();
     return r;
 }
 #else
-static inline uint64_t pack32_host_nt(const uint64_t* src, uint32_t* dst, uint64_t n) { return pack32_host(src, dst, n); }
+static inline uint64_t pack32_host_nt(const uint64_t* src, uint32_t* dst, uint64_t n, uint64_t pm1) { return pack32_host(src, dst, n, pm1); }
 #endif
 
 // Three entries below 2^21 per 64-bit word (entry i of a chunk in bits 21*(i%3) .. of word i/3; a last partial word is
 // zero-filled): the wire format for fields of at most 21 bits, such as the reference's F_1572869.  ceil(n/3) words.
 static inline uint64_t pack21_words(uint64_t n) { return (n + 2) / 3; }
 template <bool NT>
-static inline uint64_t pack21_host(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, uint64_t n) {
+static inline uint64_t pack21_host(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, uint64_t n, uint64_t pm1) {
     uint64_t acc = 0, i = 0, j = 0;
     for (; i + 3 <= n; i += 3, ++j) {
         const uint64_t a = src[i], b = src[i + 1], c = src[i + 2];
-        acc |= a | b | c;
+        acc |= a | b | c | (pm1 - a) | (pm1 - b) | (pm1 - c);
         const uint64_t w = a | (b << 21) | (c << 42);
 #if defined(__SSE2__) && defined(__x86_64__)
         if (NT) _mm_stream_si64((long long*)(dst + j), (long long)w);
@@ -79,7 +85,7 @@ static inline uint64_t pack21_host(const uint64_t* __restrict__ src, uint64_t* _
     }
     if (i < n) {
         const uint64_t a = src[i], b = i + 1 < n ? src[i + 1] : 0;
-        acc |= a | b;
+        acc |= a | b | (pm1 - a) | (pm1 - b);
         dst[j] = a | (b << 21);
     }
 #if defined(__SSE2__) && defined(__x86_64__)
@@ -126,7 +132,7 @@ struct PackStats {
 // started).  Nothing is thrown.
 template <class B>
 int run_pack_upload(B& be, const uint64_t* const* tables, uint32_t k, uint64_t len, uint64_t chunk, int workers, int raw_slots,
-                    uint64_t* or_acc, PackStats* stats, bool streaming_stores = false, bool wire21 = false) {
+                    uint64_t* or_acc, PackStats* stats, uint64_t pm1, bool streaming_stores = false, bool wire21 = false) {
     PackUnits units(k, len, chunk);
     std::atomic<int> err{0};
     std::atomic<uint64_t> acc{0}, n_packed{0}, n_raw{0};
@@ -140,8 +146,8 @@ int run_pack_upload(B& be, const uint64_t* const* tables, uint32_t k, uint64_t l
             rc = be.stage_wait(w, slot);
             if (rc != 0) break;
             const uint64_t* src = tables[t] + off;
-            if (wire21) a |= streaming_stores ? pack21_host<true>(src, (uint64_t*)be.stage(w, slot), chunk) : pack21_host<false>(src, (uint64_t*)be.stage(w, slot), chunk);
-            else a |= streaming_stores ? pack32_host_nt(src, be.stage(w, slot), chunk) : pack32_host(src, be.stage(w, slot), chunk);
+            if (wire21) a |= streaming_stores ? pack21_host<true>(src, (uint64_t*)be.stage(w, slot), chunk, pm1) : pack21_host<false>(src, (uint64_t*)be.stage(w, slot), chunk, pm1);
+            else a |= streaming_stores ? pack32_host_nt(src, be.stage(w, slot), chunk, pm1) : pack32_host(src, be.stage(w, slot), chunk, pm1);
             rc = be.submit_packed(w, slot, t, off, chunk);
             slot ^= 1;
             ++cnt;
@@ -190,6 +196,7 @@ struct MemcpyPackBackend {
     std::vector<std::vector<uint32_t>>* dst;     // [table]
     std::atomic<uint64_t> raw_or{0};
     bool wire21 = false;
+    uint64_t pm1 = ~0ull >> 1;
     MemcpyPackBackend(uint64_t chunk_, int workers, std::vector<std::vector<uint32_t>>* dst_) : chunk(chunk_), dst(dst_) {
         staging.resize((size_t)workers * 2);
         for (auto& s : staging) s.resize(chunk_ + 4);
@@ -207,7 +214,7 @@ struct MemcpyPackBackend {
     }
     int raw_wait(int) { return 0; }
     int submit_raw(int, uint32_t t, uint64_t off, uint64_t n, const uint64_t* src) {
-        raw_or.fetch_or(pack32_host(src, (*dst)[t].data() + off, n));
+        raw_or.fetch_or(pack32_host(src, (*dst)[t].data() + off, n, pm1));
         return 0;
     }
 };

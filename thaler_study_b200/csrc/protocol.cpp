@@ -14,6 +14,7 @@
 #include "host/fiat_shamir.hpp"
 #include "host/unipoly.hpp"
 #include "internal.hpp"
+#include "options.hpp"
 #include "sumcheck_b200.h"
 
 using namespace scb;
@@ -132,10 +133,7 @@ extern "C" int scb_hash_to_field(const scb_field* f, const uint8_t* msg, size_t 
 }
 
 // ------------------------------------------------------------------------------------------ Prover
-static int packed_enabled() {
-    static const int v = getenv("SCB_PACKED") ? atoi(getenv("SCB_PACKED")) : 1;
-    return v;
-}
+static int packed_enabled() { return opt(OPT_packed) != 0; }
 struct scb_prover {
     scb_poly* g = nullptr;      // g: P
     Fe c_1;                     // c_1: F
@@ -321,17 +319,13 @@ static int verifier_round(scb_verifier* v, const SparsePoly& g_j, const Fe& r_j,
     const HostField& F = v->f->h;
     *final_round = 0;
     *accepted = 0;
-    if (v->r.empty()) {  // first round :284-297
-        Fe evaluation = F.add(g_j.evaluate(F, F.zero()), g_j.evaluate(F, F.one()));
-        if (v->c_1 != evaluation) {
-            set_error("prover claim mismatches evaluation (start)");
-            return SCB_EVERIFY;
-        }
-        v->g_part.push_back(g_j);
-        v->r.push_back(r_j);
-        return SCB_OK;
-    } else if (v->r.size() == (size_t)v->n - 1) {  // last round :298-310
-        v->r.push_back(r_j);
+    // The reference's last-round branch (:298-310) checks g_n(r_n) == g(r) but NOT g_n(0) + g_n(1) == g_{n-1}(r_{n-1}),
+    // and for n == 1 its first-round branch (:284-297) returns before the oracle is ever evaluated: a prover can send
+    // self-consistent g_1..g_{n-1} for a false c_1 followed by the honest g_n and be accepted.  With option
+    // strict_verifier (default 1) both checks are made; honest transcripts and every byte of them are unchanged.
+    // strict_verifier = 0 is the reference's literal behaviour (tests/test_host_abi.py shows the difference).
+    const bool strict = opt(OPT_strict_verifier) != 0;
+    auto final_check = [&](const SparsePoly& g_last, const Fe& r_last) -> int {
         if (!v->g) {
             set_error("verifier has no oracle access to the polynomial");
             return SCB_ENOPOLY;
@@ -343,8 +337,34 @@ static int verifier_round(scb_verifier* v, const SparsePoly& g_j, const Fe& r_j,
         Fe oracle;
         F.load(w, oracle);
         *final_round = 1;
-        *accepted = g_j.evaluate(F, r_j) == oracle ? 1 : 0;
+        *accepted = g_last.evaluate(F, r_last) == oracle ? 1 : 0;
         return SCB_OK;
+    };
+    if (strict && v->r.size() >= (size_t)v->n) {
+        set_error("verifier has already run its %u rounds", v->n);
+        return SCB_EINVAL;
+    }
+    if (v->r.empty()) {  // first round :284-297
+        Fe evaluation = F.add(g_j.evaluate(F, F.zero()), g_j.evaluate(F, F.one()));
+        if (v->c_1 != evaluation) {
+            set_error("prover claim mismatches evaluation (start)");
+            return SCB_EVERIFY;
+        }
+        v->g_part.push_back(g_j);
+        v->r.push_back(r_j);
+        if (strict && v->n == 1) return final_check(g_j, r_j);
+        return SCB_OK;
+    } else if (v->r.size() == (size_t)v->n - 1) {  // last round :298-310
+        if (strict) {
+            Fe prev = v->g_part.back().evaluate(F, v->r.back());
+            Fe evaluation = F.add(g_j.evaluate(F, F.zero()), g_j.evaluate(F, F.one()));
+            if (prev != evaluation) {
+                set_error("prover claim mismatches evaluation (round %zu)", v->r.size());
+                return SCB_EVERIFY;
+            }
+        }
+        v->r.push_back(r_j);
+        return final_check(g_j, r_j);
     } else {  // j-th round :311-329
         Fe prev = v->g_part.back().evaluate(F, v->r.back());
         Fe evaluation = F.add(g_j.evaluate(F, F.zero()), g_j.evaluate(F, F.one()));
@@ -526,9 +546,9 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
         int rc = SCB_OK;
         size_t base = 0;  // challenges already folded into p->g
         if (p->num_vars > 2) pc.next_challenge();
-        // SCB_PAIR_RESIDENT=0: every pass is an ordinary launch (k_pair_pass_sp) -- the same pass bodies, visible to
+        // option pair_resident = 0: every pass is an ordinary launch (k_pair_pass_sp) -- the same pass bodies, visible to
         // ncu, which cannot run the resident kernel (it serialises kernel and host)
-        static const bool resident = !(getenv("SCB_PAIR_RESIDENT") && atoi(getenv("SCB_PAIR_RESIDENT")) == 0);
+        const bool resident = opt(OPT_pair_resident) != 0;
         while (pc.msgs < p->num_vars && rc == SCB_OK) {
             base = pc.used.size() - 2;
             const uint64_t* pair = &pc.used[base];
@@ -538,9 +558,9 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
             // The pass over the caller's 8-byte tables runs as its own launch when the tables are large (>= 2^26
             // entries): the stand-alone kernel fits 3 CTAs per SM (80 registers), the resident one 2; without the
             // 8-byte path the resident kernel has the registers to pipeline its packed loads across tables; and the
-            // extra launch + wait costs less than the two gains (SCB_PAIR_FIRST_ALONE=0: everything in the resident
-            // kernel; =n: threshold 2^n).
-            static const uint32_t first_alone = getenv("SCB_PAIR_FIRST_ALONE") ? (uint32_t)atoi(getenv("SCB_PAIR_FIRST_ALONE")) : 26;
+            // extra launch + wait costs less than the two gains (option pair_first_alone = 0: everything in the
+            // resident kernel; n: threshold 2^n).
+            const uint32_t first_alone = (uint32_t)opt(OPT_pair_first_alone);
             const bool alone_now = resident && first_alone != 0 && live >= first_alone && !poly_is_packed(p->g) &&
                                    (!p->sharded || (live > p->consolidate_at && live >= 4));  // sharded: two local variables stay
             if (!resident || alone_now) {
@@ -647,11 +667,17 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
     return SCB_OK;
 }
 
-extern "C" int scb_fs_verify_transcript(scb_verifier* v, const uint8_t* transcript, const uint64_t* offsets, uint32_t n_msgs, int* accepted) {
-    // fiat-shamir/src/lib.rs:123-143 with InteractiveVerifier for Verifier (:151-171)
+extern "C" int scb_fs_verify_transcript(scb_verifier* v, const uint8_t* transcript, size_t transcript_len, const uint64_t* offsets,
+                                        uint32_t n_msgs, int* accepted) {
+    // fiat-shamir/src/lib.rs:123-143 with InteractiveVerifier for Verifier (:151-171).  The transcript comes from an
+    // untrusted prover: offsets must start at 0, be non-decreasing and stay inside transcript_len.
     ARG_TRY(v && transcript && offsets && accepted, "null argument");
     const HostField& F = v->f->h;
     *accepted = 0;
+    ARG_TRY(n_msgs == 0 || offsets[0] == 0, "offsets[0] must be 0");
+    for (uint32_t j = 0; j < n_msgs; ++j) ARG_TRY(offsets[j] <= offsets[j + 1] && offsets[j + 1] <= transcript_len, "message offsets out of range");
+    const bool strict = opt(OPT_strict_verifier) != 0;
+    bool reached_final = false;
     for (uint32_t j = 0; j < n_msgs; ++j) {
         const uint8_t* msg = transcript + offsets[j];
         const size_t len = offsets[j + 1] - offsets[j];
@@ -672,16 +698,19 @@ extern "C" int scb_fs_verify_transcript(scb_verifier* v, const uint8_t* transcri
         }
         SparsePoly g_j;
         size_t used = SparsePoly::deserialize(F, msg + off, len - off, g_j);
-        if (used == 0) {
+        if (used == 0 || (strict && used != len - off)) {
             set_error("Codec error");
             return SCB_EINVAL;
         }
         int fin = 0, acc = 0;
         RC_TRY(verifier_round(v, g_j, r_j, &fin, &acc));
-        if (j == 0) continue;       // :155-161 returns Ok(true) for the first message
+        if (fin) reached_final = true;
         if (fin && !acc) return SCB_OK;  // *accepted stays 0
+        if (j == 0 && !fin) continue;    // :155-161 returns Ok(true) for the first message
     }
-    *accepted = 1;
+    // the reference accepts whatever prefix it was given (:131-141 loops over transcript.g.len()); a truncated
+    // transcript never reaches the oracle check, so strict mode rejects it
+    *accepted = (!strict || reached_final) ? 1 : 0;
     return SCB_OK;
 }
 
