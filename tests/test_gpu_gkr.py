@@ -76,8 +76,12 @@ def random_layers(rnd, sizes, num_inputs):
 
 @pytest.mark.parametrize("OF", [O.FP389, O.FP1572869, O.Field(0xFFFFFFFF00000001), O.BLS12_381_FR], ids=lambda F: f"p{F.bits}")
 def test_messages_equal_dense_reference_formulation(OF):
-    """Same challenges into the oracle's dense-table prover and the gate-list prover: identical c_1, identical round
-    polynomials, identical q, for every layer."""
+    """Same challenges into the oracle's dense-table prover and the gate-list prover: identical c_1 and identical round
+    polynomials for every layer.  q is the same POLYNOMIAL; its term list can differ from the reference's in one
+    documented way: restrict_poly (gkr-protocol/src/lib.rs:291-321) multiplies sparse
+    polynomials term by term and can keep explicit zero-coefficient terms, the engine sends the unique interpolant
+    with zero terms dropped.  The comparison below is therefore on the non-zero terms, and
+    test_restrict_poly_zero_term_deviation pins a case where the two term lists really differ."""
     F = T.Field(OF.p)
     rnd = random.Random(OF.bits)
     gen = GENERATOR.get(OF.p, 2)
@@ -123,6 +127,23 @@ def test_messages_equal_dense_reference_formulation(OF):
             w = O.DenseMLE(OF, half, op.layers[i + 1])
             for t in (0, 1, 5):
                 assert dm[2].evaluate(t) == w.evaluate([(bb + t * (cc - bb)) % OF.p for bb, cc in zip(b, c)])
+
+
+def test_restrict_poly_zero_term_deviation():
+    """b[bit] = 0 puts an explicit (0, 0) term into the reference's line factor (from_coefficients_vec strips only
+    TRAILING zeros) and the term-by-term products carry it into q; the engine's q is the unique interpolant with zero
+    terms dropped.  Same values everywhere, different term lists -- the one representation difference to the
+    reference, stated in DESIGN.md section 5."""
+    OF, F = O.FP389, T.Field(389)
+    evals, b, c = [0, 5, 0, 0], [0, 0], [3, 2]
+    want = O.restrict_poly(OF, b, c, O.DenseMLE(OF, 2, evals))
+    assert want.coeffs[0] == (0, 0)  # the explicit zero term of the reference's bookkeeping
+    m = T.DenseMultilinearExtension.from_evaluations_vec(F, 2, evals)
+    line = lambda t: [(bb + t * (cc - bb)) % OF.p for bb, cc in zip(b, c)]
+    got = T.evals_to_univariate(F, T.KIND_GKR_W, [m.evaluate(line(t)) for t in range(3)])
+    assert got.coeffs == [(d, cf) for d, cf in want.coeffs if cf != 0] and got.coeffs != list(want.coeffs)
+    for t in range(6):
+        assert got.evaluate(t) == want.evaluate(t)
 
 
 def test_wiring_eval_matches_dense_tables():

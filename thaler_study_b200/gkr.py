@@ -119,7 +119,7 @@ class GkrProver:
             qe = np.zeros((self.k + 1, F.n), dtype=np.uint64)
             n = C.c_uint32()
             check(lib.scb_gkr_prover_restrict_evals(self._h, api._p64(F.elem(self.r[j])), api._p64(qe), self.k + 1, C.byref(n)))
-            q = api.evals_to_univariate_mont(F, api.KIND_GKR_W, qe)  # restrict_poly: unique interpolant, zero terms dropped
+            q = api.evals_to_univariate_mont(F, api.KIND_GKR_W, qe)  # restrict_poly's polynomial as the unique interpolant, zero terms dropped (the reference can keep explicit zero terms: DESIGN.md section 5)
             return ("FinalRoundMessage", p, q)
         return ("SumCheckProverMessage", self._round_poly(j))
 
