@@ -7,8 +7,17 @@ three 2^28-entry multilinear tables (BASELINE.json configs[4]) over the referenc
   python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (C restatement, all host cores)
 
 A "step" is one complete proof: Prover::new (c_1) + all v prover rounds + the Fiat-Shamir chain that supplies the
-challenges (fiat_shamir::generate_transcript), i.e. first message ... last message.  N>1: weak scaling, every rank
-holds a 2^28-entry slab of each table (total 2^(28+log2 N) entries), one tiny all-gather per round.
+challenges (fiat_shamir::generate_transcript), i.e. first message ... last message.
+
+N>1, headline line: WEAK scaling -- every rank holds a 2^28-entry slab of each table (total 2^(28+log2 N) entries),
+one tiny exchange per pass inside the kernels.  The same line carries the STRONG-scaling curve of BASELINE.json's own
+metric ("2^28 table at 1/2/4/8 B200") as `strong_scaling`: ONE 2^28-entry table set split over the N GPUs, timed the
+same way (--scaling strong makes that the headline instead).
+
+Every proof that is timed is checked: `verified` = the last timed transcript passes verify_transcript (N>1: the
+sharded verifier, whose final oracle query is the sharded MLE evaluation); `sharded_equals_single` (N>1) = a sharded
+proof of a 2^20-per-rank instance equals, byte for byte, the proof rank 0 computes alone from the concatenated tables.
+
 Prints ONE JSON line on rank 0 (contract in the task statement).
 """
 from __future__ import annotations
@@ -26,9 +35,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 MODULUS = 1572869
+BLS12_381_FR = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 K_TABLES = 3
 METRIC = "sumcheck_prover_throughput"
 UNIT = "Melem/s"
+POLICY_NAME = {0: "small-prime 32-bit", 1: "generic 64-bit", 4: "4-limb"}
 
 
 def parse():
@@ -37,18 +48,49 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--vars", type=int, default=28, help="log2 of table entries PER GPU")
-    ap.add_argument("--cpu-vars", type=int, default=24, help="log2 table size of the bounded CPU sample")
+    ap.add_argument("--vars", type=int, default=28, help="log2 of table entries PER GPU (weak) / in total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="which curve is the headline at N>1")
+    ap.add_argument("--cpu-vars", type=int, default=24, help="log2 table size of the bounded sample in the cpu_baseline leg")
+    ap.add_argument("--ref-vars", type=int, default=0, help="--impl reference: log2 table size per step (0 = the workload's own size if it fits)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="N>1: skip the second (strong-scaling) curve")
+    ap.add_argument("--no-fields", action="store_true", help="N=1: skip the 4-limb (BLS12-381 Fr) record")
+    ap.add_argument("--no-trait-leg", action="store_true", help="N=1: skip the trait-only e2e leg")
     ap.add_argument("--modulus", type=int, default=MODULUS)
     return ap.parse_args()
 
 
-def workload_name(v, n_gpus, p):
-    return (f"fiat-shamir sum-check, ProductMLE<3> (degree-3 product of 3 multilinear tables), 2^{v} entries per GPU x "
+def workload_name(v, n_gpus, p, scaling="weak"):
+    per = v if scaling == "weak" else v - (n_gpus.bit_length() - 1)
+    return (f"fiat-shamir sum-check, ProductMLE<3> (degree-3 product of 3 multilinear tables), 2^{per} entries per GPU x "
             f"{n_gpus} GPU, field F_{p} (Fp64 Montgomery, 8 B/element)")
+
+
+def config_dict(v_arg, n_gpus, p, n_limbs, policy, exchange="p2p", scaling="weak"):
+    """The workload both arms are quoted on (same dict from `--impl ours` and `--impl reference`).  v_arg = --vars:
+    per-GPU table variables for weak scaling, total variables for strong scaling."""
+    E = 8 * n_limbs
+    lg = n_gpus.bit_length() - 1
+    v_per_gpu = v_arg if scaling == "weak" else v_arg - lg
+    return {"workload": workload_name(v_arg, n_gpus, p, scaling), "tables": K_TABLES, "vars_per_gpu": v_per_gpu, "total_vars": v_per_gpu + lg,
+            "field_modulus": p, "bytes_per_element": E, "arith_policy": POLICY_NAME[policy],
+            "l2": "inputs (%.1f GB per GPU) larger than L2; no flush needed" % (K_TABLES * (1 << v_per_gpu) * E / 1e9),
+            "parallelism": f"tables sharded by top variables over {n_gpus} GPU(s)" + ("" if n_gpus == 1 else f"; per-pass exchange: {exchange}")}
+
+
+def policy_of(p):
+    return 4 if p.bit_length() > 64 else (0 if p.bit_length() <= 28 else 1)
+
+
+def host_threads():
+    """Threads the CPU legs use: the cores this process may run on.  NOT omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1, which made round 1's N>1 reference arm single-threaded."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -155,15 +197,28 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kernel, v, K, p):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` captures
+    (profiles/traffic.json lists them with the capture they come from).  None for a shape that was never captured."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None
+    for e in tab.get("captures", []):
+        if e["kernel"] == kernel and e["vars"] == v and e["tables"] == K and e["modulus"] == p:
+            return float(e["dram_bytes_per_launch"])
+    return None
+
+
 # ------------------------------------------------------------------------------------------------ CPU legs (oracle)
-def cpu_prove_sample(p, v, threads, steps=1):
+def cpu_prove_sample(p, v, threads, steps=1, tabs=None):
     """Times the C restatement of the reference's prover (oracle/oracle.c::orc_product_prove: Prover::new + v rounds,
-    separate fold and message passes, table copies included) on a 2^v sample.  Returns (Melem/s, seconds/step)."""
-    import numpy as np
+    separate fold and message passes, table copies included) on 2^v-entry tables.  Returns (Melem/s, seconds/step)."""
     from oracle.coracle import CField
 
     cf = CField(p)
-    tabs = [cf.synth(0xB200 + k, 0, 1 << v) for k in range(K_TABLES)]
+    if tabs is None:
+        tabs = [cf.synth(0xB200 + k, 0, 1 << v) for k in range(K_TABLES)]
     ch = cf.synth(0xC4A1, 0, max(v - 1, 1))
     best = None
     for _ in range(steps):
@@ -174,43 +229,88 @@ def cpu_prove_sample(p, v, threads, steps=1):
     return (1 << v) / best / 1e6, best
 
 
+def mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return 0
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The Rust crates cannot be built in this
     image (no cargo/rustc; arkworks is not vendored), so this times oracle/oracle.c -- a C restatement in the
-    reference's structure -- with all host threads, on a bounded 2^cpu_vars sample of the same workload."""
+    reference's structure -- with ALL host threads (counted from the affinity mask, whatever OMP_NUM_THREADS says).
+    Same `config` as the GPU arm.  Each step is one full proof of the per-GPU share of that workload (2^vars entries
+    per table: at N = 1 that IS the workload; the per-element throughput of this streaming prover does not depend on the
+    table size) unless host memory or the time budget forces a smaller sample, which `cpu_baseline.sample` then says."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.coracle import max_threads
+    from oracle.coracle import CField
 
-    cores = max_threads()
-    v = args.cpu_vars
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_prove_sample(args.modulus, v, cores)
+    cores = host_threads()
+    p = args.modulus
+    n_limbs = 4 if p.bit_length() > 64 else 1
+    v = args.ref_vars or args.vars
+    # inputs + the folded copies the reference's structure keeps (1 + 1/2 + 1/4 .. of the tables) + slack
+    need = lambda vv: int(2.3 * K_TABLES * (1 << vv) * 8 * n_limbs) + (2 << 30)
+    avail = mem_available_bytes()
+    while avail and need(v) > avail and v > 20:
+        v -= 1
+    cf = CField(p)
+    tabs = [cf.synth(0xB200 + k, 0, 1 << 20) for k in range(K_TABLES)]
+    _, t20 = cpu_prove_sample(p, 20, cores, tabs=tabs)  # calibration: keep the whole run within a few minutes
+    budget_s = 240.0
+    total_steps = max(1, args.steps) + max(0, args.warmup)
+    while v > 20 and t20 * (1 << (v - 20)) * total_steps > budget_s:
+        v -= 1
+    tabs = [cf.synth(0xB200 + k, 0, 1 << v) for k in range(K_TABLES)]
+    for _ in range(max(0, args.warmup)):
+        cpu_prove_sample(p, v, cores, tabs=tabs)
     times = []
     for _ in range(max(1, args.steps)):
-        _, dt = cpu_prove_sample(args.modulus, v, cores)
+        _, dt = cpu_prove_sample(p, v, cores, tabs=tabs)
         times.append(dt)
     dt = sum(times) / len(times)
     val = (1 << v) / dt / 1e6
-    sample = f"2^{v}-entry tables (bounded sample of the 2^{args.vars} workload), {cores} OpenMP threads over pair ranges"
+    full = v == args.vars
+    sample = (f"oracle/oracle.c orc_product_prove, 2^{v}-entry tables per step "
+              + ("(the workload's per-GPU size)" if full else f"(bounded sample of the 2^{args.vars} workload: host memory / time budget)")
+              + f", {cores} OpenMP threads over pair ranges")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_name(args.vars, args.gpus, args.modulus), "sample": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": config_dict(args.vars, args.gpus, p, n_limbs, policy_of(p), scaling=args.scaling),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "sample_vars": v,
+                         "sample_is_full_per_gpu_workload": full},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_threads": cores, "omp_num_threads_env_ignored": os.environ.get("OMP_NUM_THREADS"),
         "gpu_launches": 0,
     }))
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def pass_bytes(v, K, E):
+    """Algorithmic bytes of the pair passes of a 2^v proof (small-prime policy): pass over tables of 2^m entries reads
+    K * 2^m entries (E bytes the first time, 4 afterwards) and writes K * 2^(m-2) packed entries (nothing after the
+    last fold).  DESIGN.md section 4a."""
+    out, m, in_b = [], v, E
+    while m >= 3:
+        out.append(K * ((1 << m) * in_b + ((1 << (m - 2)) * 4 if m >= 4 else 0)))
+        m, in_b = m - 2, 4
+    return out
+
+
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
 
     import thaler_study_b200 as T
-    from thaler_study_b200.distributed import CudaProductEngine, Peers, prove_sharded, prove_sharded_p2p
+    from thaler_study_b200.distributed import (CudaProductEngine, Peers, prove_sharded, prove_sharded_p2p, verify_transcript_sharded)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -222,14 +322,14 @@ def run_ours(args):
     os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    T.options_from_env()  # harness opt-in: SCB_<OPTION>=n variables become scb_set_option calls (the library reads no environment)
     n_gpus = world
-    v, p, K = args.vars, args.modulus, K_TABLES
+    lg = world.bit_length() - 1
+    p, K = args.modulus, K_TABLES
     F = T.Field(p)
     E = 8 * F.n
-    # rank g owns entries [g*2^v, (g+1)*2^v) of every table: the synthetic stream is indexed globally
-    tabs = [T.DenseMultilinearExtension.synthetic(F, v, 0xB200 + k, start=rank << v) for k in range(K)]
-    g = T.ProductMLE.new(tabs)
-    T.synchronize()
+    headline = args.scaling if world > 1 else "weak"
+    v_weak, v_strong = args.vars, args.vars - lg  # per-GPU variables of the two curves
 
     exchange = os.environ.get("SCB_EXCHANGE", "p2p")  # p2p: in-kernel exchange over NVLink peer memory; nccl: all-gather
     peers = None
@@ -247,71 +347,118 @@ def run_ours(args):
         if flag.item() == 0:
             peers, exchange = None, "nccl"
 
-    def prove(poly):
-        if world == 1:
-            return T.generate_transcript(T.Prover(poly))
-        if peers is not None:
-            return prove_sharded_p2p(poly, peers)[1]
-        return prove_sharded(CudaProductEngine(poly.clone()))[1]
-
-    def step():
-        return prove(g)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        transcript = step()
-    assert len(transcript) == v + (world.bit_length() - 1)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    T.launch_count(reset=True)
-    T.lib.scb_resident_stats_reset()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    barrier()
-    launches = T.launch_count()
-    clocks = sampler.stop() if rank == 0 else None  # samples cover exactly the timed region
-    res_stats = resident_stats(T)  # CUDA-event time of the resident kernels launched inside the timed region
-    ms = ev0.elapsed_time(ev1) / args.steps
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    total_entries = (1 << v) * n_gpus
+    def all_true(ok):
+        if world == 1:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def prove(poly):
+        if world == 1:
+            return T.generate_transcript(T.Prover(poly))
+        if peers is not None:
+            return prove_sharded_p2p(poly, peers, consolidate_at=0)[1]
+        return prove_sharded(CudaProductEngine(poly.clone()))[1]
+
+    def verify(transcript, poly, v_local):
+        if world == 1:
+            return T.verify_transcript(transcript, T.Verifier(v_local, poly))
+        if peers is not None:
+            return verify_transcript_sharded(transcript, poly, peers)
+        return len(transcript) == v_local + lg  # NCCL fallback path: no sharded oracle query available
+
+    def timed_run(v_local, steps, warmup, collect_stats):
+        """Builds the slabs (rank g owns entries [g*2^v_local, (g+1)*2^v_local) of every table: the synthetic stream is
+        indexed globally), W warm-up proofs, then K proofs between barriers, CUDA events, max over ranks."""
+        tabs = [T.DenseMultilinearExtension.synthetic(F, v_local, 0xB200 + k, start=rank << v_local) for k in range(K)]
+        g = T.ProductMLE.new(tabs)
+        T.synchronize()
+        for _ in range(max(warmup, 3)):
+            transcript = prove(g)
+        assert len(transcript) == v_local + lg
+        barrier()
+        sampler = ClockSampler(local_rank) if (collect_stats and rank == 0) else None
+        if sampler:
+            sampler.start()
+        T.launch_count(reset=True)
+        T.lib.scb_resident_stats_reset()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            transcript = prove(g)
+        ev1.record()
+        barrier()
+        launches = T.launch_count()
+        clocks = sampler.stop() if sampler else None  # samples cover exactly the timed region
+        res = resident_stats(T)  # CUDA-event time of the resident kernels launched inside the timed region
+        pst = pair_pass_stats(T)
+        ms = ev0.elapsed_time(ev1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        verified = all_true(verify(transcript, g, v_local))  # the LAST TIMED proof, not a separate run
+        return {"ms": ms, "launches": launches, "clocks": clocks, "res": res, "pass": pst, "verified": verified, "g": g, "tabs": tabs,
+                "transcript_bytes": sum(map(len, transcript))}
+
+    # ---- the two curves
+    runs = {}
+    order = ["weak"] if world == 1 else ([headline] + ([] if args.no_strong and headline == "weak" else [("strong" if headline == "weak" else "weak")]))
+    for which in order:
+        v_local = v_weak if which == "weak" else v_strong
+        r = timed_run(v_local, args.steps, args.warmup, collect_stats=(which == headline))
+        r["v_local"] = v_local
+        if which != headline:  # free the second curve's tables right away
+            r["g"], r["tabs"] = None, None
+        runs[which] = r
+    main = runs[headline]
+    v, ms, g, tabs = main["v_local"], main["ms"], main["g"], main["tabs"]
+    total_entries = 1 << (v + lg)
     value = total_entries / (ms * 1e-3) / 1e6
+    res_stats, pass_stats = main["res"], main["pass"]
+
+    # ---- sharded == single, byte for byte (N > 1): a 2^20-per-rank instance proved sharded and by rank 0 alone
+    sharded_equals_single = None
+    if world > 1:
+        sv = 20
+        slabs = [T.DenseMultilinearExtension.synthetic(F, sv, 0x51AB + k, start=rank << sv) for k in range(K)]
+        sharded_tr = prove(T.ProductMLE.new(slabs))
+        ok = True
+        if rank == 0:
+            full = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, sv + lg, 0x51AB + k) for k in range(K)])
+            single_tr = T.generate_transcript(T.Prover(full))
+            ok = single_tr == sharded_tr and T.verify_transcript(single_tr, T.Verifier(sv + lg, full))
+            del full
+        sharded_equals_single = all_true(ok)
+        del slabs
 
     # ---- roofline of the dominant kernel
-    # Small-prime fields (the default workload): two rounds per pass (csrc/pairs.cuh).  A proof of 2^28-entry tables is
-    # three launches: k_grid_sp_pf (Prover::new: the (K+1)^2 grid sums that yield c_1, g_1 and g_2), k_pair_pass_sp (the
-    # pair pass over the caller's 8-byte tables: folds two variables, accumulates the next grid) and the resident
-    # k_persist_pairs_sp (the 12 remaining passes over packed tables).  The pair pass over the full tables is the
-    # dominant kernel; the library times it with CUDA events around the launch, on its stream, for every launch inside
-    # the timed region above (scb_pair_pass_stats); likewise the resident kernel (scb_resident_stats).
+    # Small-prime fields (the default workload): two rounds per pass (csrc/pairs.cuh).  A proof of 2^28-entry tables
+    # (per GPU) is three launches: k_grid_sp_pf (Prover::new: the (K+1)^2 grid sums that yield c_1, g_1 and g_2),
+    # k_pair_pass_sp (the pair pass over the caller's 8-byte tables: folds two variables, accumulates the next grid;
+    # sharded: its finishing thread also exchanges the 16 sums with the peers) and the resident k_persist_pairs_sp (the
+    # remaining passes over packed tables).  The pair pass over the full tables is the dominant kernel; the library
+    # times it with CUDA events around the launch, on its stream, for every launch of the timed region
+    # (scb_pair_pass_stats); likewise the resident kernel(s) (scb_resident_stats).  The same code describes N > 1: these
+    # are the kernels the sharded proof runs.
     # Other fields: one round per pass; the dominant launch is the fused fold + message kernel of round 1, timed alone.
     roof = None
-    pass_stats = pair_pass_stats(T)
-    first_alone = pass_stats["launches"] == args.steps  # the pass over the 8-byte tables ran as its own launch
-    n_res_passes = (v - 1) // 2 - (1 if first_alone else 0)
-    if rank == 0 and F.policy == 0 and world == 1 and os.environ.get("SCB_PAIRS", "1") != "0" \
-            and res_stats["launches"] == args.steps and res_stats["last_rounds"] == n_res_passes:
+    steps = args.steps
+    first_alone = pass_stats["launches"] == steps  # the pass over the 8-byte tables ran as its own launch
+    if rank == 0 and F.policy == 0 and T.get_option("pairs") != 0 and res_stats["launches"] >= steps:
         peak, peak_src = hbm_peak()
-        pbytes, m, in_b = [], v, E
-        while m >= 3:  # pass: read K tables of 2^m entries, write 2^(m-2) packed entries (nothing after the last fold)
-            pbytes.append(K * ((1 << m) * in_b + ((1 << (m - 2)) * 4 if m >= 4 else 0)))
-            m, in_b = m - 2, 4
-        res_ms = res_stats["total_ms"] / res_stats["launches"]
+        pbytes = pass_bytes(v, K, E)  # local passes over this rank's slab (sharded: until consolidation, then replicated)
+        res_ms = res_stats["total_ms"] / steps  # all resident launches of a proof (sharded: before + after consolidation)
         res_bytes = sum(pbytes[1:]) if first_alone else sum(pbytes)
         times = []
-        for i in range(3 + max(args.steps, 5)):  # Prover::new's grid kernel, timed alone (call includes one sync + 128 B D2H)
+        for i in range(3 + max(steps, 5)):  # Prover::new's grid kernel, timed alone (call includes one sync + 128 B D2H)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             g.grid_evals()
@@ -321,117 +468,49 @@ def run_ours(args):
                 times.append(a.elapsed_time(b))
         gms = sum(times) / len(times)
         grid_bytes = K * (1 << v) * E
-        std = v == 28 and K == 3 and p == MODULUS
-        proof_bytes = grid_bytes + sum(pbytes)
+        proof_bytes = grid_bytes + sum(pbytes)  # per GPU: 8 (grid) + 8+1 (first pair pass) + 1.25*(1+1/4+..) = 18.7 B per entry-column
+        floor_bytes = 2.0 * K * (1 << v) * E  # any schedule reads the caller's 8-byte tables once before r_1 exists and once after
         grid = {"kernel": "k_grid_sp_pf<3> (Prover::new; u64 input, register double buffer), 2^%d-entry tables" % v, "kernel_ms": gms,
                 "achieved": grid_bytes / (gms * 1e-3) / 1e9, "frac": grid_bytes / (gms * 1e-3) / 1e9 / peak,
-                "algorithmic_bytes_per_launch": grid_bytes, "traffic": 6.457139e9 if std else None, "share_of_step": gms / ms,
+                "algorithmic_bytes_per_launch": grid_bytes, "traffic": ncu_traffic("k_grid_sp_pf", v, K, p), "share_of_step": gms / ms,
                 "timing": "CUDA events around the call, timed alone after the timed region (call includes one sync + 128 B D2H)"}
-        resident = {"kernel": "k_persist_pairs_sp<3> (%d resident pair passes: the remaining rounds, one cooperative launch)" % n_res_passes,
+        resident = {"kernel": "k_persist_pairs_sp<3> (the remaining pair passes, %d resident launch(es) per proof)" % (res_stats["launches"] // steps),
                     "kernel_ms": res_ms, "algorithmic_bytes_per_launch": res_bytes, "achieved": res_bytes / (res_ms * 1e-3) / 1e9,
                     "frac": res_bytes / (res_ms * 1e-3) / 1e9 / peak, "share_of_step": res_ms / ms,
-                    "latency_us": {"host_turnaround_total": sum(res_stats["turn_us"]), "device_passes_total": sum(res_stats["work_us"])},
+                    "latency_us": {"host_turnaround_total_last_launch": sum(res_stats["turn_us"]), "device_passes_total_last_launch": sum(res_stats["work_us"])},
                     "traffic": None, "traffic_note": "ncu serialises kernel and host, so a resident kernel cannot run under it"}
-        proof = {"proof_bytes_moved": proof_bytes, "proof_frac_of_hbm_roofline": (proof_bytes / (ms * 1e-3) / 1e9) / peak,
+        proof = {"proof_bytes_moved_per_gpu": proof_bytes, "proof_frac_of_hbm_roofline": (proof_bytes / (ms * 1e-3) / 1e9) / peak,
+                 "proof_floor_bytes_per_gpu": floor_bytes, "proof_frac_vs_floor": (floor_bytes / (ms * 1e-3) / 1e9) / peak,
+                 "proof_floor_note": "any schedule must read the caller's 8-byte tables once before r_1 exists and once after: 2*K*2^v*E",
                  "proof_survey_bytes": 4.0 * K * (1 << v) * E,
-                 "proof_frac_vs_survey_bytes": (4.0 * K * (1 << v) * E / (ms * 1e-3) / 1e9) / peak}
+                 "proof_survey_note": "SURVEY 8d's 4*K*2^v*E assumes one round per pass and 8-byte intermediates; two rounds per pass with "
+                                      "uint32 intermediates move fewer bytes, so a fraction against it can exceed 1 and is not reported"}
         if first_alone:
-            # dominant kernel of the step: the pair pass over the caller's 8-byte tables, an ordinary launch timed with CUDA
-            # events around it on its stream, every launch of the timed region (scb_pair_pass_stats)
             pms = pass_stats["total_ms"] / pass_stats["launches"]
             roof = {"bound": "hbm",
                     "kernel": "k_pair_pass_sp<3,in=u64,out=u32> (rounds 3-4 of the proof: folds two variables of the 2^%d-entry tables and "
-                              "accumulates the 16 grid sums of the next two messages)" % v,
+                              "accumulates the 16 grid sums of the next two messages%s)" % (v, "" if world == 1 else "; finishing thread exchanges them with the peers"),
                     "achieved": pbytes[0] / (pms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": pbytes[0] / (pms * 1e-3) / 1e9 / peak,
-                    "traffic": 7.241953e9 if std else None, "kernel_ms": pms, "algorithmic_bytes_per_launch": pbytes[0], "peak_source": peak_src,
-                    "timing": "CUDA events around the launch on its stream, all %d launches of the timed region" % pass_stats["launches"],
+                    "traffic": ncu_traffic("k_pair_pass_sp", v, K, p), "kernel_ms": pms, "algorithmic_bytes_per_launch": pbytes[0], "peak_source": peak_src,
+                    "timing": "CUDA events around the launch on its stream, all %d launches of the timed region (rank 0)" % pass_stats["launches"],
                     "share_of_step": pms / ms, "grid_kernel_alone": grid, "resident_kernel": resident}
         else:
-            w0 = res_stats["work_us"][0]
             roof = {"bound": "hbm", "kernel": resident["kernel"], "achieved": resident["achieved"], "peak": peak, "unit": "GB/s",
                     "frac": resident["frac"], "traffic": None, "traffic_note": resident["traffic_note"], "kernel_ms": res_ms,
                     "algorithmic_bytes_per_launch": res_bytes, "peak_source": peak_src,
-                    "timing": "CUDA events around the launch on its stream, all %d launches of the timed region" % res_stats["launches"],
-                    "share_of_step": res_ms / ms,
-                    "pass0_phase": {"us": w0, "achieved": pbytes[0] / (w0 * 1e-6) / 1e9, "frac": pbytes[0] / (w0 * 1e-6) / 1e9 / peak,
-                                    "bytes": pbytes[0], "source": "%globaltimer stamps inside the kernel, last launch"},
-                    "pass0_alone_traffic": 7.241953e9 if std else None, "latency_us": resident["latency_us"], "grid_kernel_alone": grid}
+                    "timing": "CUDA events around the launches on their stream, all %d launches of the timed region (rank 0)" % res_stats["launches"],
+                    "share_of_step": res_ms / ms, "latency_us": resident["latency_us"], "grid_kernel_alone": grid}
         roof.update(proof)
     elif rank == 0:
-        # Timed alone, on the same kernel variant the proof runs in round 1: with the small-prime policy the prover's
-        # folded tables are packed uint32 (packed.cuh), so the launch reads 2^v ark elements (E bytes) per table and
-        # writes 2^(v-1) 4-byte entries; otherwise it writes 2^(v-1) E-byte elements (SURVEY 8d's 1.5*K*2^v*E).
-        packed = F.policy == 0 and os.environ.get("SCB_PACKED", "1") != "0"
-        gk = g.clone().allow_packed(packed)
-        d_out = torch.empty([K + 1, F.n], dtype=torch.int64, device="cuda")
-        r = 123456 % p
-        times = []
-        for i in range(3 + max(args.steps, 5)):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            nxt = gk.fix_and_round_evals_device(r, d_out.data_ptr())
-            b.record()
-            torch.cuda.synchronize()
-            if i >= 3:
-                times.append(a.elapsed_time(b))
-            del nxt
-        kms = sum(times) / len(times)
-        survey_bytes = 1.5 * K * (1 << v) * E
-        alg_bytes = K * (1 << v) * (E + (2 if packed else E / 2))
-        proof_bytes = K * (1 << v) * (3.0 * E if packed else 4.0 * E)  # packed: 8+8+2+3*(1+1/2+..)=24 B per entry-column
-        peak, peak_src = hbm_peak()
-        achieved = alg_bytes / (kms * 1e-3) / 1e9
-        kname = "k_fold_round_sp<3,in=u64,out=u32>" if packed else "k_fold_round<%s,3>" % {0: "PolSP", 1: "PolG1", 4: "PolGN<4>"}[F.policy]
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size from the committed ncu --set full
-        # capture (profiles/r01_ncu_summary_final.md: 6.442495 GB + 1.613603 GB per launch); null for other shapes
-        traffic = 8.056098e9 if (packed and v == 28 and K == 3 and p == MODULUS) else None
-        alone = {"kernel": kname + " (fused fold + round message), 2^%d-entry tables, timed alone" % v,
-                 "achieved": achieved, "frac": achieved / peak, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
-                 "traffic": traffic, "survey_bytes_per_launch_unpacked": survey_bytes,
-                 "frac_vs_survey_bytes": survey_bytes / (kms * 1e-3) / 1e9 / peak}
-        proof = {"proof_bytes_moved": proof_bytes, "proof_frac_of_hbm_roofline": (proof_bytes / (ms * 1e-3) / 1e9) / peak,
-                 "proof_survey_bytes": 4.0 * K * (1 << v) * E,
-                 "proof_frac_vs_survey_bytes": (4.0 * K * (1 << v) * E / (ms * 1e-3) / 1e9) / peak}
-        resident = world == 1 and res_stats["launches"] == args.steps and res_stats["last_rounds"] == v - 1
-        if resident:
-            # algorithmic bytes of rounds 1..v-1: round j reads K tables of 2^(v-j+1) entries and writes 2^(v-j)
-            in_b, out_b = E, (4 if packed else E)
-            rbytes = []
-            for j in range(1, v):
-                rbytes.append(K * ((1 << (v - j + 1)) * in_b + (1 << (v - j)) * out_b))
-                in_b = out_b
-            res_ms = res_stats["total_ms"] / res_stats["launches"]
-            res_achieved = sum(rbytes) / (res_ms * 1e-3) / 1e9
-            w0 = res_stats["work_us"][0]
-            roof = {"bound": "hbm", "kernel": "k_persist_rounds<%s,3> (rounds 1..%d of the proof, fused fold + round message, one "
-                                              "cooperative launch)" % ({0: "PolSP", 1: "PolG1", 4: "PolGN<4>"}[F.policy], v - 1),
-                    "achieved": res_achieved, "peak": peak, "unit": "GB/s", "frac": res_achieved / peak, "traffic": None,
-                    "traffic_note": "ncu serialises kernel and host, so the resident kernel cannot run under it; its passes are "
-                                    "the per-round kernels' loop bodies, whose captured DRAM traffic equals the algorithmic bytes "
-                                    "(round1_kernel_alone.traffic, profiles/)",
-                    "kernel_ms": res_ms, "algorithmic_bytes_per_launch": sum(rbytes), "peak_source": peak_src,
-                    "timing": "CUDA events around the launch on its stream, all %d launches of the timed region" % res_stats["launches"],
-                    "share_of_step": res_ms / ms,
-                    "round1_phase": {"us": w0, "achieved": rbytes[0] / (w0 * 1e-6) / 1e9, "frac": rbytes[0] / (w0 * 1e-6) / 1e9 / peak,
-                                     "source": "%globaltimer stamps inside the kernel, last launch"},
-                    "latency_us": {"host_turnaround_total": sum(res_stats["turn_us"]), "rounds_after_1_total": sum(res_stats["work_us"][1:])},
-                    "round1_kernel_alone": alone}
-        else:
-            roof = {"bound": "hbm", "kernel": alone["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                    "survey_bytes_per_launch_unpacked": survey_bytes, "frac_vs_survey_bytes": alone["frac_vs_survey_bytes"]}
-        roof.update(proof)
+        roof = generic_roofline(T, torch, F, g, v, K, p, ms, steps, res_stats, world)
 
     # ---- e2e: the same proof through the C ABI with HOST tables (pinned), H2D inside the timed region
     e2e = None
     if not args.no_e2e:
-        import numpy as np
-
         host = []
         for t in tabs:
             ht = torch.empty([1 << v, F.n], dtype=torch.int64, pin_memory=True)
-            # device -> pinned host staging (outside the timed region)
-            dt_ = torch.empty([1 << v, F.n], dtype=torch.int64, device="cuda")
+            dt_ = torch.empty([1 << v, F.n], dtype=torch.int64, device="cuda")  # device -> pinned host staging (outside the timed region)
             T._lib.check(T.lib.scb_mle_copy_to_device(t._h, dt_.data_ptr()))
             ht.copy_(dt_)
             del dt_
@@ -441,34 +520,37 @@ def run_ours(args):
         # One GPU: scb_poly_product_from_host -- for the small-prime field the tables cross PCIe as packed uint32 where
         # the host cores keep up and as 8-byte entries where not (narrowed on the device).  Sharded runs keep one plain
         # cudaMemcpy per table: the ranks of a box share its host memory system, which is what bounds the narrowing
-        # upload (2 GPUs measured with it: 117.8 ms per step against 119.0 plain, profiles/r01_bench_2gpu_packed_upload.json;
-        # SCB_BENCH_E2E_UPLOAD=1 selects it anyway).
+        # upload (profiles/r01_upload_ab.md; SCB_BENCH_E2E_UPLOAD=1 selects it anyway).
         one_call = (world == 1 or os.environ.get("SCB_BENCH_E2E_UPLOAD", "0") == "1") and os.environ.get("SCB_BENCH_E2E_PLAIN", "0") == "0"
 
-        def e2e_step():
+        def e2e_step(tables):
             if one_call:
-                gg = T.ProductMLE.from_host_tables(F, v, host)
+                gg = T.ProductMLE.from_host_tables(F, v, tables)
             else:
-                hs = [T.DenseMultilinearExtension.from_evaluations_vec(F, v, h) for h in host]  # cudaMemcpy H2D
+                hs = [T.DenseMultilinearExtension.from_evaluations_vec(F, v, h) for h in tables]  # cudaMemcpy H2D
                 gg = T.ProductMLE.new(hs)
-            return prove(gg)  # messages come back device -> host every round
+            return prove(gg), gg  # messages come back device -> host every round
 
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        b.record()
-        barrier()
-        wall = (time.perf_counter() - t0) / args.e2e_steps
-        ems = max(a.elapsed_time(b) / args.e2e_steps, wall * 1e3)
-        if world > 1:
-            t = torch.tensor([ems], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = float(t.item())
-        rounds = v + (world.bit_length() - 1)
+        def time_e2e(tables, n_steps):
+            e2e_step(tables)
+            barrier()
+            t0 = time.perf_counter()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n_steps):
+                tr, gg = e2e_step(tables)
+            b.record()
+            barrier()
+            wall = (time.perf_counter() - t0) / n_steps
+            ems = max(a.elapsed_time(b) / n_steps, wall * 1e3)
+            if world > 1:
+                t = torch.tensor([ems], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ems = float(t.item())
+            return ems, all_true(verify(tr, gg, v))
+
+        ems, e2e_ok = time_e2e(host, args.e2e_steps)
+        rounds = v + lg
         h2d = K * (1 << v) * E * n_gpus
         note = "scb_mle_from_host x%d (pinned host tables, H2D) + Prover::new + all rounds + Fiat-Shamir, per step" % K
         upload = None
@@ -478,50 +560,224 @@ def run_ours(args):
             pc, rc_, hb = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
             T._lib.check(T.lib.scb_host_pack_stats(ctypes.byref(pc), ctypes.byref(rc_), ctypes.byref(hb)))
             note = "scb_poly_product_from_host (pinned host tables, H2D) + Prover::new + all rounds + Fiat-Shamir, per step"
-            if F.policy == 0 and pc.value + rc_.value > 0 and os.environ.get("SCB_HOST_PACK", "1") != "0":
+            if F.policy == 0 and pc.value + rc_.value > 0 and T.get_option("host_pack") != 0:
                 h2d = hb.value  # bytes of the copies the last step queued, counted by the library as it queued them
                 if world > 1:
                     tb = torch.tensor([h2d], device="cuda", dtype=torch.int64)
                     dist.all_reduce(tb, op=dist.ReduceOp.SUM)
                     h2d = int(tb.item())
-                wire21 = p < (1 << 21) and os.environ.get("SCB_HOST_PACK_WIRE", "21") == "21"
+                wire21 = p < (1 << 21) and T.get_option("host_pack_wire") == 21
                 upload = {"chunk_entries": K * (1 << v) // (pc.value + rc_.value), "chunks_narrowed_on_host": pc.value,
                           "chunks_narrowed_on_device": rc_.value,
                           "host_lane_wire_format": "three 21-bit entries per 64-bit word" if wire21 else "uint32",
-                          "host_pack_threads_per_rank": min(32, int(os.environ.get("SCB_HOST_PACK_THREADS", max(1, (os.cpu_count() or 1) // world))))}
-        e2e = {"value": total_entries / (ems * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ems,
+                          "host_pack_threads_per_rank": min(32, T.get_option("host_pack_threads") or max(1, host_threads() // world))}
+        e2e = {"value": total_entries / (ems * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ems, "verified": e2e_ok,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": rounds * (K + 1) * E * n_gpus, "note": note}
         if upload:
             e2e["upload"] = upload
+        # what a Rust caller has: tables in PAGEABLE memory (Vec<F>); the device-side narrowing lane needs pinned memory
+        # and is skipped, the host lane stages through the library's pinned buffers
+        if world == 1 and one_call:
+            pageable = [np.array(h, copy=True) for h in host]
+            pms_, pok = time_e2e(pageable, max(1, args.e2e_steps - 1))
+            e2e["pageable_host_tables"] = {"value": total_entries / (pms_ * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": pms_, "verified": pok,
+                                           "note": "same call with the tables in pageable memory (what `Vec<F>::as_ptr()` gives a Rust shim)"}
+            del pageable
+        # The drop-in through the TRAIT ONLY: exactly the calls an unmodified sum_check_protocol::Prover<F, GpuPoly> and
+        # fiat_shamir::generate_transcript issue (sum-check-protocol/src/lib.rs:88-112): Prover::new = to_evaluations()
+        # (the 2^v-entry product table device -> host) + a host sum; per round fix_variables then to_univariate as two
+        # separate calls; the hash chain on the host.  No fused call, no pair passes, no resident kernel, no packing.
+        if world == 1 and not args.no_trait_leg:
+            e2e["trait_only"] = trait_only_leg(T, np, torch, F, v, K, host, total_entries)
         del host
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        from oracle.coracle import max_threads
-
         cv = args.cpu_vars
         v1, t1 = cpu_prove_sample(p, cv, 1)
-        cores = max_threads()
+        cores = host_threads()
         vN, tN = cpu_prove_sample(p, cv, cores)
         cpu = {"value": vN, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"oracle/oracle.c orc_product_prove on 2^{cv}-entry tables (bounded sample), {cores} OpenMP threads; "
                          f"single-thread (reference-faithful) = {v1:.2f} {UNIT}",
                "single_thread_value": v1, "seconds": tN}
 
+    # ---- second field: the 4-limb path (north_star kernel #1, "multi-limb Montgomery"), N = 1 only
+    fields = None
+    if world == 1 and not args.no_fields and p == MODULUS:
+        del g, tabs
+        main["g"] = main["tabs"] = None
+        torch.cuda.empty_cache()
+        fields = {"bls12_381_fr": field_record(T, torch, BLS12_381_FR, args.vars, K, max(3, min(args.steps, 5)), not args.no_cpu_baseline)}
+
     if rank == 0:
-        sys.stdout.flush()
-        os.write(json_fd, (json.dumps({
+        cfg = config_dict(args.vars, n_gpus, p, F.n, F.policy, exchange, scaling=headline)
+        line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(v, n_gpus, p), "tables": K, "vars_per_gpu": v, "total_vars": v + (world.bit_length() - 1),
-                       "field_modulus": p, "bytes_per_element": E, "arith_policy": {0: "small-prime 32-bit", 1: "generic 64-bit", 4: "4-limb"}[F.policy],
-                       "l2": "inputs (%.1f GB per GPU) larger than L2; no flush needed" % (K * (1 << v) * E / 1e9),
-                       "parallelism": f"tables sharded by top variables over {n_gpus} GPU(s)"
-                                      + ("" if world == 1 else f"; per-round exchange: {exchange}")},
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        }) + "\n").encode())
+            "ms_per_step": ms, "higher_is_better": True, "scaling": headline, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": cfg, "verified": main["verified"], "sharded_equals_single": sharded_equals_single,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": main["launches"], "clocks": main["clocks"],
+            "host_threads": host_threads(), "transcript_bytes": main["transcript_bytes"],
+        }
+        other = "strong" if headline == "weak" else "weak"
+        if other in runs:
+            o = runs[other]
+            tot = 1 << (o["v_local"] + lg)
+            line[other + "_scaling"] = {"scaling": other, "value": tot / (o["ms"] * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": o["ms"],
+                                        "vars_per_gpu": o["v_local"], "total_vars": o["v_local"] + lg, "verified": o["verified"],
+                                        "gpu_launches": o["launches"], "steps": args.steps,
+                                        "note": ("ONE 2^%d-entry table set split over the %d GPUs (BASELINE.json metric)" % (args.vars, n_gpus)) if other == "strong"
+                                                else "2^%d entries per GPU" % o["v_local"]}
+        if fields:
+            line["fields"] = fields
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
+        if peers is not None:
+            peers.close()
         dist.destroy_process_group()
+
+
+def generic_roofline(T, torch, F, g, v, K, p, ms, steps, res_stats, world):
+    """One round per pass (generic / 4-limb fields, or option pairs = 0).  Timed alone, on the kernel variant the proof
+    runs in round 1: with the small-prime policy the folded tables are packed uint32, so the launch reads 2^v ark
+    elements (E bytes) per table and writes 2^(v-1) 4-byte entries; otherwise it writes 2^(v-1) E-byte elements
+    (SURVEY 8d's 1.5*K*2^v*E)."""
+    E = 8 * F.n
+    packed = F.policy == 0 and T.get_option("packed") != 0
+    gk = g.clone().allow_packed(packed)
+    d_out = torch.empty([K + 1, F.n], dtype=torch.int64, device="cuda")
+    r = 123456 % p
+    times = []
+    for i in range(3 + max(steps, 5)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        nxt = gk.fix_and_round_evals_device(r, d_out.data_ptr())
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append(a.elapsed_time(b))
+        del nxt
+    kms = sum(times) / len(times)
+    alg_bytes = K * (1 << v) * (E + (2 if packed else E / 2))
+    proof_bytes = K * (1 << v) * (3.0 * E if packed else 4.0 * E)  # packed: 8+8+2+3*(1+1/2+..)=24 B per entry-column
+    peak, peak_src = hbm_peak()
+    achieved = alg_bytes / (kms * 1e-3) / 1e9
+    kname = {0: "k_fold_round_sp<3,in=u64,out=u32>", 1: "k_fold_round<PolG1,3>", 4: "fused fold+message kernel of the 4-limb policy (option g4_kernel=%d)" % T.get_option("g4_kernel")}[F.policy] \
+        if (packed or F.policy != 0) else "k_fold_round<PolSP,3>"
+    tkey = {0: "k_fold_round_sp", 1: "k_fold_round_g1", 4: "k_fold_round_g4"}[F.policy]
+    # integer roofline (SURVEY 8d): modmuls per launch x IMAD.WIDE per modmul / measured IMAD.WIDE peak
+    imad_peak = 17.9e12  # profiles/r01_imad_peak.jsonl (IMAD.WIDE.U32, full rate)
+    imads_per_mul = {0: 3, 1: 11, 4: 128}[F.policy]
+    modmuls_launch = (2 * K + (K + 1) * (K - 1)) * (1 << v) / 4.0
+    modmuls_proof = (K * K + K - 1) * float(1 << v)
+    t_int_launch = modmuls_launch * imads_per_mul / imad_peak
+    t_hbm_launch = alg_bytes / (peak * 1e9)
+    t_int_proof = modmuls_proof * imads_per_mul / imad_peak
+    t_hbm_proof = proof_bytes / (peak * 1e9)
+    alone = {"kernel": kname + ", 2^%d-entry tables, timed alone" % v,
+             "achieved": achieved, "frac": achieved / peak, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
+             "traffic": ncu_traffic(tkey, v, K, p),
+             "modmuls_per_launch": modmuls_launch, "imad_wide_per_modmul": imads_per_mul, "imad_wide_peak_per_s": imad_peak,
+             "t_integer_bound_ms": t_int_launch * 1e3, "t_hbm_bound_ms": t_hbm_launch * 1e3,
+             "frac_of_slower_bound": max(t_int_launch, t_hbm_launch) / (kms * 1e-3)}
+    proof = {"proof_bytes_moved": proof_bytes, "proof_frac_of_hbm_roofline": (proof_bytes / (ms * 1e-3) / 1e9) / peak,
+             "proof_modmuls": modmuls_proof, "proof_t_integer_bound_ms": t_int_proof * 1e3, "proof_t_hbm_bound_ms": t_hbm_proof * 1e3,
+             "proof_frac_of_slower_bound": max(t_int_proof, t_hbm_proof) / (ms * 1e-3)}
+    int_bound = t_int_launch > t_hbm_launch
+    roof = {"bound": "hbm", "kernel": alone["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": alone["traffic"], "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+            "share_of_step": kms / ms,
+            "binding_roofline": "integer (IMAD.WIDE)" if int_bound else "hbm",
+            "note": "contract fields describe the HBM side; for this policy the integer pipe binds -- see frac_of_slower_bound" if int_bound else None,
+            "integer": {k: alone[k] for k in ("modmuls_per_launch", "imad_wide_per_modmul", "imad_wide_peak_per_s", "t_integer_bound_ms", "t_hbm_bound_ms", "frac_of_slower_bound")}}
+    if world == 1 and res_stats["launches"] >= steps and res_stats["last_rounds"] > 0:
+        res_ms = res_stats["total_ms"] / steps
+        roof["resident_kernel"] = {"kernel_ms": res_ms, "rounds_last_launch": res_stats["last_rounds"], "share_of_step": res_ms / ms,
+                                   "latency_us": {"host_turnaround_total": sum(res_stats["turn_us"]), "device_rounds_total": sum(res_stats["work_us"])}}
+    roof.update(proof)
+    return roof
+
+
+def field_record(T, torch, p, v, K, steps, with_cpu):
+    """A second record inside the JSON line: the same proof over another field (the 4-limb BLS12-381 Fr =
+    ark_ed_on_bls12_381::Fq of the reference's Cargo.toml:20), device-timed, verified, with its own roofline (integer
+    vs HBM, the slower one) and CPU port number."""
+    F = T.Field(p)
+    tabs = [T.DenseMultilinearExtension.synthetic(F, v, 0xB200 + k) for k in range(K)]
+    g = T.ProductMLE.new(tabs)
+    T.synchronize()
+    for _ in range(3):
+        tr = T.generate_transcript(T.Prover(g))
+    torch.cuda.synchronize()
+    T.launch_count(reset=True)
+    T.lib.scb_resident_stats_reset()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        tr = T.generate_transcript(T.Prover(g))
+    ev1.record()
+    torch.cuda.synchronize()
+    launches = T.launch_count()
+    ms = ev0.elapsed_time(ev1) / steps
+    res = resident_stats(T)
+    ok = T.verify_transcript(tr, T.Verifier(v, g))
+    roof = generic_roofline(T, torch, F, g, v, K, p, ms, steps, res, 1)
+    rec = {"metric": METRIC, "value": (1 << v) / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "steps": steps, "verified": ok,
+           "config": {"workload": f"fiat-shamir sum-check, ProductMLE<3>, 2^{v} entries, 4-limb field (BLS12-381 Fr, 32 B/element)",
+                      "field_modulus_bits": F.bits, "bytes_per_element": 8 * F.n, "arith_policy": POLICY_NAME[F.policy]},
+           "gpu_launches": launches, "roofline": roof}
+    if with_cpu:
+        cv = 20
+        cores = host_threads()
+        vN, tN = cpu_prove_sample(p, cv, cores)
+        rec["cpu_baseline"] = {"value": vN, "unit": UNIT, "cores": cores, "kind": "port", "seconds": tN,
+                               "sample": f"oracle/oracle.c orc_product_prove on 2^{cv}-entry tables (bounded sample), {cores} OpenMP threads"}
+    del g, tabs
+    torch.cuda.empty_cache()
+    return rec
+
+
+def trait_only_leg(T, np, torch, F, v, K, host, total_entries):
+    """Times exactly what an unmodified `Prover<F, GpuPoly>` + `generate_transcript` would do through the five trait
+    methods (sum-check-protocol/src/lib.rs:88-112, fiat-shamir/src/lib.rs:75-98), host tables in, transcript out."""
+    p = F.p
+
+    def step():
+        mles = [T.DenseMultilinearExtension.from_evaluations_vec(F, v, h) for h in host]  # from_evaluations_vec: H2D
+        g = T.ProductMLE.new(mles)
+        # Prover::new: g.to_evaluations().into_iter().sum()
+        n = 1 << v
+        ev = np.empty((n, F.n), dtype=np.uint64)
+        T._lib.check(T.lib.scb_poly_to_evaluations(g._h, T.api._p64(ev), n))
+        if F.n == 1:
+            c1_m = int(ev[:, 0].sum(dtype=np.uint64) % np.uint64(p)) if p < (1 << 36) else int(sum(int(x) for x in ev[:, 0]) % p)
+            c_1 = F.from_mont(np.array([[c1_m]], dtype=np.uint64))[0]  # Montgomery form is linear: sum of residues, then one conversion
+        else:
+            c_1 = sum(F.from_mont(ev)) % p
+        # generate_transcript: g_1 = (c_1, round(1, 0)); then r_j = hash(transcript so far), round(r_j, j)
+        msgs, sofar = [], b""
+        for j in range(v):
+            if j > 0:
+                r = F.hash_to_field(sofar)
+                g = g.fix_variables([r])        # self.g = self.g.fix_variables(&[r])
+            poly = g.to_univariate()            # self.g.to_univariate()
+            m = (c_1.to_bytes(F.ser_bytes, "little") if j == 0 else b"") + poly.serialize_uncompressed()
+            msgs.append(m)
+            sofar += m
+        return msgs, g
+
+    msgs, _ = step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    msgs, _ = step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    fast = T.generate_transcript(T.Prover(T.ProductMLE.from_host_tables(F, v, host)))
+    return {"value": total_entries / dt / 1e6, "unit": UNIT, "ms_per_step": dt * 1e3, "equals_fast_path_bytes": msgs == fast,
+            "h2d_bytes_per_step": K * (1 << v) * 8 * F.n, "d2h_bytes_per_step": (1 << v) * 8 * F.n + v * (K + 1) * 8 * F.n,
+            "note": "only the five SumCheckPolynomial methods: from_evaluations_vec (H2D), Prover::new = to_evaluations() (2^v-entry D2H) + host sum, "
+                    "per round fix_variables then to_univariate (two launches), host hash chain; no fused/pair/resident/packed path"}
 
 
 def main():

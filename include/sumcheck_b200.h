@@ -336,9 +336,17 @@ int scb_peers_set_current(scb_peers* p);
 /* all-gather the slabs of `slab` (rank-order concatenation of every table) into a replicated polynomial */
 int scb_peers_gather_poly(scb_peers* p, const scb_poly* slab, scb_poly** out);
 /* Prover::new for a polynomial sharded by its top log2(world) variables; `slab` is this rank's part.  The prover
- * consolidates (scb_peers_gather_poly) once a slab has at most consolidate_at variables; scb_prover_round and
+ * consolidates (scb_peers_gather_poly) once a slab has at most consolidate_at variables (0: the library's default,
+ * option consolidate_auto); scb_prover_round and
  * scb_fs_generate_transcript then work as for a single GPU and return identical bytes on every rank. */
 int scb_prover_new_sharded(const scb_poly* slab, scb_peers* peers, uint32_t world, uint32_t consolidate_at, scb_prover** out);
+/* vsbw_multilinear_from_evaluations / [ARK] evaluate (multilinear-extensions/src/lib.rs:6-24) of a table sharded by its top
+ * log2(world) variables: `slab` = this rank's entries [rank 2^lv, (rank+1) 2^lv), point = lv + log2(world) coordinates
+ * (big_endian != 0: r[0] <-> index MSB as in multilinear-extensions; 0: LSB-first as in ark).  One launch per rank; the
+ * E-byte exchange and the modular sum run in the kernel's finishing thread over the peer windows.  Same element on
+ * every rank.  The slab needs at least 8 variables (10 for 4-limb fields). */
+int scb_mle_evaluate_sharded(const scb_mle* slab, scb_peers* peers, const uint64_t* point, uint32_t n_point, int big_endian,
+                             uint64_t* out_elem);
 
 #ifdef __cplusplus
 }

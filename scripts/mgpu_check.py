@@ -7,7 +7,8 @@ sys.path.insert(0, ROOT)
 import torch
 import torch.distributed as dist
 import thaler_study_b200 as T
-from thaler_study_b200.distributed import CudaProductEngine, Peers, prove_sharded, prove_sharded_p2p
+from thaler_study_b200.distributed import (CudaProductEngine, Peers, mle_evaluate_sharded, prove_sharded, prove_sharded_p2p,
+                                           verify_transcript_sharded)
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -27,6 +28,29 @@ for p, lv, K, cat in ((1572869, 20, 3, 16), (1572869, 18, 3, 3), (1572869, 17, 4
         if msgs_b != msgs or c_1b != c_1:
             print(f"rank {rank}: P2P transcript differs from the NCCL one (p_bits={F.bits} lv={lv} rep={rep})")
             ok = False
+    if lv >= (8 if F.n == 1 else 10):
+        # sharded verifier (final oracle query = sharded MLE evaluation) accepts, and rejects a tampered transcript
+        if not verify_transcript_sharded(msgs, T.ProductMLE.new(slabs), peers):
+            print(f"rank {rank}: sharded verifier rejects the honest transcript (p_bits={F.bits} lv={lv})")
+            ok = False
+        bad = list(msgs)
+        bad[-1] = bad[-1][:-1] + bytes([bad[-1][-1] ^ 1])
+        try:
+            if verify_transcript_sharded(bad, T.ProductMLE.new(slabs), peers):
+                print(f"rank {rank}: sharded verifier accepts a tampered transcript (p_bits={F.bits} lv={lv})")
+                ok = False
+        except ValueError:
+            pass  # the flipped bit made the coefficient non-canonical: Codec error
+        import random as _random
+        _r = _random.Random(lv * 131 + K)
+        pt = [_r.randrange(p) for _ in range(lv + lg)]
+        got_le = mle_evaluate_sharded(slabs[0], peers, pt)
+        got_be = mle_evaluate_sharded(slabs[0], peers, list(reversed(pt)), big_endian=True)
+        if rank == 0:
+            want = T.DenseMultilinearExtension.synthetic(F, lv + lg, 900).evaluate(pt)
+            if got_le != want or got_be != want:
+                print(f"sharded MLE evaluation differs from the single-GPU one (p_bits={F.bits} lv={lv})")
+                ok = False
     if rank == 0:
         full = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, lv + lg, 900 + k) for k in range(K)])
         prover = T.Prover(full)

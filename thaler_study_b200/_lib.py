@@ -121,6 +121,7 @@ SIGNATURES = {
     "scb_peers_set_current": (C.c_int, [vp]),
     "scb_peers_gather_poly": (C.c_int, [vp, vp, vpp]),
     "scb_prover_new_sharded": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vpp]),
+    "scb_mle_evaluate_sharded": (C.c_int, [vp, vp, u64p, C.c_uint32, C.c_int, u64p]),
     "scb_transcript_new": (C.c_int, [vp, C.c_uint32, vpp]),
     "scb_transcript_free": (None, [vp]),
     "scb_transcript_absorb_round": (C.c_int, [vp, u64p, C.c_uint32, C.c_uint32, u64p]),

@@ -639,10 +639,42 @@ static int build_eq_tables(Ctx* c, const FieldImpl& f, const uint64_t* bitpt, ui
 
 // MLE evaluation through eq tables (K4).  bitpt[j] = coordinate bound to index bit j (host memory).
 // Result goes to host (h_out) or, if d_out != nullptr, stays on the device.
+// One launch: every CTA builds the eq sub-tables in shared memory, warps take rows, last CTA adds up (eqfix.cuh).
+// v_total > t.nv: `t` is this rank's slab of a table sharded by its top variables, row0 its first row; the finishing
+// thread then adds the peer GPUs' sums (current peer group).  res: mapped host or device memory.
+static bool eval_fused_ok(const FieldImpl& f, const Table& t, uint32_t v_total) {
+    const uint32_t lb = f.d.n == 1 ? 8 : 10;
+    return opt(OPT_mle_fused) != 0 && !t.p32 && t.nv >= lb && v_total >= t.nv && v_total - lb <= 27 && v_total <= (uint32_t)kMaxPointCoords;
+}
+static int eval_table_fused(Ctx* c, const FieldImpl& f, const Table& t, const uint64_t* bitpt, uint32_t v_total, uint64_t row0, uint64_t* res) {
+    const uint32_t N = f.d.n;
+    PointArg pa;
+    std::memset(&pa, 0, sizeof pa);
+    std::memcpy(pa.w, bitpt, (size_t)8 * N * v_total);
+    DISPATCH_POLICY(f.policy, {
+        auto kern = k_mle_eval_fused<A>;
+        constexpr size_t smem = MleFusedCfg<A>::smem_bytes;
+        RC_TRY(allow_smem(kern, smem));
+        const uint64_t n_rows = t.len() >> MleFusedCfg<A>::LB;
+        kern<<<occ_grid(c, kern, n_rows * 32, smem), kThreads, smem, g_stream>>>(f.d, pa, t.buf->ptr, t.nv, v_total, row0, c->partials, c->ticket, res,
+                                                                             peer_arg(c));
+    });
+    LAUNCH_CHECK();
+    return SCB_OK;
+}
+
 static int eval_table(Ctx* c, const FieldImpl& f, const Table& t, const uint64_t* bitpt, uint64_t* h_out, uint64_t* d_out) {
     const uint32_t v = t.nv, N = f.d.n;
     ARG_TRY(v <= 34, "table too large for MLE evaluation");
     for (uint32_t j = 0; j < v; ++j) ARG_TRY(elem_canonical(f, bitpt + (size_t)j * N), "point coordinate is not canonical");
+    if (eval_fused_ok(f, t, v) && !(g_cur_peers && g_cur_peers->world > 1)) {
+        RC_TRY(eval_table_fused(c, f, t, bitpt, v, 0, d_out ? d_out : c->h_res));
+        if (!d_out) {
+            CU_TRY(cudaStreamSynchronize(g_stream));
+            std::memcpy(h_out, c->h_res, 8 * N);
+        }
+        return SCB_OK;
+    }
     // low table (shared memory, copied by every CTA) over lb index bits, high table (L2) over the rest
     const uint32_t lb_env = (uint32_t)opt(OPT_mle_lb);
     const int u_env = (int)opt(OPT_mle_u);
@@ -737,6 +769,40 @@ extern "C" int scb_mle_evaluate_be(const scb_mle* m, const uint64_t* r, uint32_t
     Ctx* c;
     RC_TRY(get_ctx(&c));
     return eval_table_be(c, *m->f, m->t, r, out_elem);
+}
+// MLE evaluation of a table sharded by its top log2(world) variables ("each GPU dots its slab with its
+// slice of the eq table; one exchange of E bytes"): rank g holds entries [g 2^lv, (g+1) 2^lv).  The point has
+// lv + log2(world) coordinates; big_endian != 0: r[0] <-> index MSB (multilinear-extensions), else LSB-first ([ARK]).
+// One launch per rank; the exchange and the modular sum happen in the kernel's finishing thread over NVLink peer
+// memory.  Every rank returns the same element.
+extern "C" int scb_mle_evaluate_sharded(const scb_mle* slab, scb_peers* peers, const uint64_t* point, uint32_t n_point, int big_endian,
+                                        uint64_t* out_elem) {
+    ARG_TRY(slab && peers && out_elem && point, "null argument");
+    ARG_TRY(peers->connected || peers->world == 1, "scb_peers_connect has not been called");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    const FieldImpl& f = *slab->f;
+    const uint32_t N = f.d.n, lv = slab->t.nv, lg = 31 - __builtin_clz(peers->world);
+    ARG_TRY(n_point == lv + lg, "point dimension does not match num_vars + log2(world)");
+    ARG_TRY(eval_fused_ok(f, slab->t, n_point), "slab too small (or table too large) for the sharded evaluation: gather it first");
+    std::vector<uint64_t> bitpt((size_t)N * n_point);
+    for (uint32_t j = 0; j < n_point; ++j) {
+        const uint64_t* src = point + (size_t)(big_endian ? n_point - 1 - j : j) * N;
+        ARG_TRY(elem_canonical(f, src), "point coordinate is not canonical");
+        std::memcpy(&bitpt[(size_t)j * N], src, 8 * N);
+    }
+    const uint32_t lb = N == 1 ? 8 : 10;
+    scb_peers* prev = g_cur_peers;
+    RC_TRY(scb_peers_set_current(peers));
+    int rc = eval_table_fused(c, f, slab->t, bitpt.data(), n_point, (uint64_t)peers->rank << (lv - lb), c->h_res);
+    if (rc == SCB_OK && cudaStreamSynchronize(g_stream) != cudaSuccess) {
+        set_error("sharded MLE evaluation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = SCB_ECUDA;
+    }
+    if (rc == SCB_OK) rc = peers_check(c);
+    g_cur_peers = prev;
+    if (rc == SCB_OK) std::memcpy(out_elem, c->h_res, 8 * N);
+    return rc;
 }
 extern "C" int scb_mle_relabel(const scb_mle* m, uint32_t a, uint32_t b, uint32_t k, scb_mle** out) {
     ARG_TRY(m && out, "null argument");

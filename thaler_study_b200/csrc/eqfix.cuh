@@ -188,6 +188,109 @@ __global__ void __launch_bounds__(kThreads) k_mle_dot_multi(FieldDesc f, const u
     grid_reduce_finish<A, TC>(ar, acc, partials, ticket, out);
 }
 
+// ------------------------------------------------------------------------------------------
+// MLE evaluation in ONE launch (multilinear-extensions/src/lib.rs:6-24; [ARK] evaluate for the LSB-first order).
+// eq(i) over v index bits is the outer product of a table over the low LB bits and up to three sub-tables of at most
+// 9 bits each over the rest (exact arithmetic: the same field elements as v doublings).  Every CTA builds all of them
+// in its own shared memory by parallel doubling (four thread groups side by side, at most 10 levels), so nothing has
+// to be written to global memory or waited for; then a WARP takes a row (2^LB consecutive entries, one value of the
+// high bits): each lane adds up its entries' products with the low table and multiplies the sum by the row's high
+// factor -- 1 + 3/EPL multiplications per entry -- and the last CTA to finish adds the per-CTA partial sums
+// (grid_reduce_finish; sharded: the finishing thread also adds the peer GPUs' sums over NVLink, `row0` being this
+// rank's first row of the whole table).
+// ------------------------------------------------------------------------------------------
+template <class A>
+struct MleFusedCfg {
+    static constexpr int LB = A::N == 1 ? 8 : 10;      // index bits of a row
+    static constexpr int SUB = 9;                       // bits per high sub-table
+    static constexpr int MAX_HB = 3 * SUB;              // high bits covered
+    static constexpr size_t smem_bytes = ((size_t)8 * A::N << LB) + 3 * ((size_t)8 * A::N << SUB);
+};
+template <class A>
+__global__ void __launch_bounds__(kThreads) k_mle_eval_fused(FieldDesc f, PointArg pt, const uint64_t* __restrict__ evals, uint32_t v_local,
+                                                            uint32_t v_total, uint64_t row0, uint64_t* partials, unsigned int* ticket,
+                                                            uint64_t* out, PeerArg peer) {
+    constexpr int N = A::N, LB = MleFusedCfg<A>::LB, SUB = MleFusedCfg<A>::SUB;
+    extern __shared__ uint64_t eq_sm[];
+    const A ar(f);
+    const uint32_t hb = v_total - LB;
+    const uint32_t nsub = hb == 0 ? 0 : (hb + SUB - 1) / SUB;  // <= 3
+    const uint32_t q = nsub ? hb / nsub : 0, rem = nsub ? hb % nsub : 0;
+    const uint32_t b1 = nsub > 0 ? q + (0 < rem ? 1 : 0) : 0, b2 = nsub > 1 ? q + (1 < rem ? 1 : 0) : 0, b3 = nsub > 2 ? q + (2 < rem ? 1 : 0) : 0;
+    uint64_t* const t1 = eq_sm + ((size_t)N << LB);
+    uint64_t* const t2 = t1 + ((size_t)N << SUB);
+    uint64_t* const t3 = t2 + ((size_t)N << SUB);
+    {  // thread group g (64 threads) doubles table g: g = 0 the low table, 1..3 the high sub-tables
+        const uint32_t g = threadIdx.x >> 6, tid = threadIdx.x & 63;
+        uint64_t* const tg = g == 0 ? eq_sm : (g == 1 ? t1 : (g == 2 ? t2 : t3));
+        const uint32_t gbits = g == 0 ? (uint32_t)LB : (g == 1 ? b1 : (g == 2 ? b2 : b3));
+        const uint32_t gfirst = g == 0 ? 0u : (g == 1 ? (uint32_t)LB : (g == 2 ? LB + b1 : LB + b1 + b2));
+        if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) tg[i] = f.one[i];
+        }
+        __syncthreads();
+        for (uint32_t l = 0; l < (uint32_t)(LB > SUB ? LB : SUB); ++l) {
+            if (l < gbits) {
+                const typename A::El c = ar.from_words(pt.w + (size_t)(gfirst + l) * N);
+                const uint32_t half = 1u << l;
+                for (uint32_t i = tid; i < half; i += 64) {
+                    typename A::El cur = ar.from_words(tg + (size_t)i * N);
+                    typename A::El hi = ar.mul(cur, c);
+                    ar.to_words(hi, tg + (size_t)(i + half) * N);
+                    ar.to_words(ar.sub(cur, hi), tg + (size_t)i * N);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    typename A::Acc acc[1];
+    ar.acc_zero(acc[0]);
+    const int lane = threadIdx.x & 31;
+    const uint64_t n_rows = 1ull << (v_local - LB);
+    const uint64_t n_warps = (uint64_t)gridDim.x * (kThreads / 32);
+    const uint64_t m1 = (1ull << b1) - 1, m2 = (1ull << b2) - 1;
+    for (uint64_t row = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); row < n_rows; row += n_warps) {
+        const uint64_t* src = evals + ((row << LB) * N);
+        typename A::Lz s;
+        if constexpr (N == 1) {
+            constexpr int JL = (1 << LB) / 128;  // 256-bit loads per lane per row
+            uint64_t w[JL][4];
+#pragma unroll
+            for (int j = 0; j < JL; ++j) ld_words<4>(src + (size_t)(j * 32 + lane) * 4, w[j]);
+#pragma unroll
+            for (int j = 0; j < JL; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const typename A::Lz m = ar.lz_mul(ar.lz(ar.from_words(&w[j][e])), ar.lz(ar.from_words(eq_sm + (size_t)(j * 32 + lane) * 4 + e)));
+                    s = (j == 0 && e == 0) ? m : ar.lz_add(s, m);
+                }
+        } else {
+            constexpr int JL = (1 << LB) / 32;  // one element (256-bit load) per lane per step
+#pragma unroll 1
+            for (int j0 = 0; j0 < JL; j0 += 4) {
+                uint64_t w[4][N];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ld_words<N>(src + (size_t)((j0 + j) * 32 + lane) * N, w[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const typename A::Lz m = ar.lz_mul(ar.lz(ar.from_words(w[j])), ar.lz(ar.from_words(eq_sm + (size_t)((j0 + j) * 32 + lane) * N)));
+                    s = (j0 == 0 && j == 0) ? m : ar.lz_add(s, m);
+                }
+            }
+        }
+        if (nsub > 0) {
+            const uint64_t ih = row0 + row;
+            typename A::Lz h = ar.lz(ar.from_words(t1 + (size_t)(ih & m1) * N));
+            if (nsub > 1) h = ar.lz_mul(h, ar.lz(ar.from_words(t2 + (size_t)((ih >> b1) & m2) * N)));
+            if (nsub > 2) h = ar.lz_mul(h, ar.lz(ar.from_words(t3 + (size_t)(ih >> (b1 + b2)) * N)));
+            s = ar.lz_mul(s, h);
+        }
+        ar.acc_add(acc[0], s);
+    }
+    grid_reduce_finish<A, 1>(ar, acc, partials, ticket, out, 0, &peer);
+}
+
 // out[j] = sum_{i < 2^m} eq[i] * t[j * 2^m + i]      (the LOW m variables fixed); one warp per output
 template <class A>
 __global__ void __launch_bounds__(kThreads) k_fix_low_eq(FieldDesc f, const uint64_t* __restrict__ tab, const uint64_t* __restrict__ eq,

@@ -44,7 +44,7 @@ namespace scb {
     X(local_ranks, 1)          /* processes sharing this box's host cores (set by the sharded driver) */                    \
     X(sha_scalar, 0)           /* portable SHA-256 compression instead of the x86 SHA extensions */                         \
     X(strict_verifier, 1)      /* Verifier::round checks the round link in the final round too */    \
-    X(consolidate_auto, 1)     /* sharded prover: consolidate_at = 0 picks the threshold from world size */
+    X(consolidate_auto, 16)    /* sharded prover: the slab size (variables) at which consolidate_at = 0 gathers the slabs */
 
 enum Opt : int {
 #define X(name, dflt) OPT_##name,

@@ -193,7 +193,10 @@ static int prover_new_impl(const scb_poly* g, scb_peers* peers, uint32_t world, 
         while ((1u << lg) < world) ++lg;
         p->num_vars += lg;  // the top log2(world) variables are the rank index
         p->peers = peers;
-        p->consolidate_at = consolidate_at < 1 ? 1 : consolidate_at;
+        // consolidate_at = 0: the library picks the threshold.  Above it every pass costs one exchange (~6 us flag
+        // round-trip over NVLink, profiles/r01_pairs.md); below it the passes run replicated on all ranks with no
+        // exchange but on world x the data, and the gather itself moves world x K x 4 x 2^lv bytes into every window.
+        p->consolidate_at = consolidate_at < 1 ? (opt(OPT_consolidate_auto) > 1 ? (uint32_t)opt(OPT_consolidate_auto) : 16) : consolidate_at;
         p->sharded = true;
         RC_TRY(maybe_consolidate(p.get()));
     }

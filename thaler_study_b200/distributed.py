@@ -168,6 +168,12 @@ class Peers:
 
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # the ranks of one box share its host cores (pack threads of the narrowing upload); the library does not read
+        # the environment, so the driver tells it
+        from ._lib import set_option
+        import os
+
+        set_option("local_ranks", max(1, int(os.environ.get("LOCAL_WORLD_SIZE", self.world))))
         self._h = C.c_void_p()
         handle = (C.c_uint8 * 64)()
         # every rank takes part in every collective below even if a local step fails; the outcome is agreed on last
@@ -208,3 +214,76 @@ def prove_sharded_p2p(slab_poly: api.SumCheckPolynomial, peers: Peers, consolida
     check(lib.scb_prover_new_sharded(slab_poly._h, peers._h, peers.world, consolidate_at, C.byref(prover._h)))
     c_1 = prover.c_1()
     return c_1, api.generate_transcript(prover)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Sharded MLE evaluation and the verifier's final oracle query for a sharded polynomial ("MLE-eval shards
+# trivially: each GPU dots its slab with its slice of the eq table; one exchange of E bytes").
+# ---------------------------------------------------------------------------------------------------------------------
+def mle_evaluate_sharded(slab: api.DenseMultilinearExtension, peers: Peers, point: Sequence[int], big_endian: bool = False) -> int:
+    """Evaluation of the table whose rank-order concatenation of slabs is the full table, at a point with
+    num_vars(slab) + log2(world) coordinates (LSB-first like ark's evaluate, or the multilinear-extensions order with
+    ``big_endian``).  One launch per rank (scb_mle_evaluate_sharded); same value on every rank."""
+    F = slab.F
+    pt = F.to_mont(list(point))
+    out = np.zeros((1, F.n), dtype=np.uint64)
+    check(lib.scb_mle_evaluate_sharded(slab._h, peers._h, api._p64(pt), len(point), 1 if big_endian else 0, api._p64(out)))
+    return F.from_mont(out)[0]
+
+
+def poly_evaluate_sharded(slab_poly: api.SumCheckPolynomial, peers: Peers, point: Sequence[int]) -> int:
+    """SumCheckPolynomial::evaluate of a sharded product polynomial: the product of its tables' evaluations
+    (matrix-multiplication/src/lib.rs:96-101)."""
+    assert slab_poly.kind in (api.KIND_PRODUCT, api.KIND_MATMUL_G), "only product polynomials shard"
+    o = C.c_uint32()
+    check(lib.scb_poly_n_tables(slab_poly._h, C.byref(o)))
+    val = 1
+    for k in range(o.value):
+        val = val * mle_evaluate_sharded(slab_poly.table(k), peers, point) % slab_poly.F.p
+    return val
+
+
+def parse_message(F: api.Field, msg: bytes, first: bool):
+    """One transcript message -> (c_1 or None, SparsePolynomial): [ARK] serialize_uncompressed of (c_1, g_1) or g_j
+    (fiat-shamir/src/lib.rs:48-50,58): canonical little-endian field elements, u64 lengths and degrees."""
+    sb, off, c_1 = F.ser_bytes, 0, None
+    if first:
+        c_1 = int.from_bytes(msg[:sb], "little")
+        off = sb
+    n = int.from_bytes(msg[off:off + 8], "little")
+    off += 8
+    terms = []
+    for _ in range(n):
+        d = int.from_bytes(msg[off:off + 8], "little")
+        cf = int.from_bytes(msg[off + 8:off + 8 + sb], "little")
+        if cf >= F.p:
+            raise ValueError("Codec error")
+        terms.append((d, cf))
+        off += 8 + sb
+    if off != len(msg) or (c_1 is not None and c_1 >= F.p):
+        raise ValueError("Codec error")
+    return c_1, api.SparsePolynomial(F, terms)
+
+
+def verify_transcript_sharded(transcript: Sequence[bytes], slab_poly: api.SumCheckPolynomial, peers: Peers) -> bool:
+    """fiat_shamir::verify_transcript (fiat-shamir/src/lib.rs:123-143) over Verifier::round
+    (sum-check-protocol/src/lib.rs:278-330, with the strict final-round link check) for a polynomial that only exists
+    as slabs: the hash chain and the round checks are host arithmetic on every rank; the final oracle query g(r) is the
+    sharded evaluation above.  Same verdict on every rank."""
+    F = slab_poly.F
+    lg = peers.world.bit_length() - 1
+    n = slab_poly.num_vars() + lg
+    if len(transcript) != n:
+        return False
+    claim, rs, sofar = None, [], b""
+    for j, msg in enumerate(transcript):
+        c_1, g_j = parse_message(F, msg, j == 0)
+        sofar += msg
+        r_j = F.hash_to_field(sofar)
+        if j == 0:
+            claim = c_1
+        if (g_j.evaluate(0) + g_j.evaluate(1)) % F.p != claim:
+            return False  # Error::ProverClaimMismatch
+        claim = g_j.evaluate(r_j)
+        rs.append(r_j)
+    return claim == poly_evaluate_sharded(slab_poly, peers, rs)
