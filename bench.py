@@ -648,11 +648,18 @@ def generic_roofline(T, torch, F, g, v, K, p, ms, steps, res_stats, world):
     gk = g.clone().allow_packed(packed)
     d_out = torch.empty([K + 1, F.n], dtype=torch.int64, device="cuda")
     r = 123456 % p
+    claim = None
+    if F.policy == 4:
+        # what Prover::round's caller knows before the pass: g_1(r_1) of the first message (the 4-limb kernel uses it)
+        claim = T.evals_to_univariate(F, T.KIND_PRODUCT, g.round_evals()).evaluate(r)
     times = []
     for i in range(3 + max(steps, 5)):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        nxt = gk.fix_and_round_evals_device(r, d_out.data_ptr())
+        if claim is not None:
+            nxt, _ = gk.fix_and_round_evals(r, claim=claim)  # includes the wait for the sums and their host rebuild (microseconds)
+        else:
+            nxt = gk.fix_and_round_evals_device(r, d_out.data_ptr())
         b.record()
         torch.cuda.synchronize()
         if i >= 3:
@@ -669,7 +676,9 @@ def generic_roofline(T, torch, F, g, v, K, p, ms, steps, res_stats, world):
     # integer roofline: modmuls per launch x IMAD.WIDE per modmul / measured IMAD.WIDE peak
     imad_peak = 17.9e12  # profiles/r01_imad_peak.jsonl (IMAD.WIDE.U32, full rate)
     imads_per_mul = {0: 3, 1: 11, 4: 128}[F.policy]
-    modmuls_launch = (2 * K + (K + 1) * (K - 1)) * (1 << v) / 4.0
+    modmuls_launch = (2 * K + (K + 1) * (K - 1)) * (1 << v) / 4.0  # fold K per output + message at X = 0..K
+    g4_on = F.policy == 4 and T.get_option("g4_kernel") != 0
+    modmuls_executed = ((2 * K + K * (K - 1)) if g4_on else (2 * K + (K + 1) * (K - 1))) * (1 << v) / 4.0  # g4.cuh skips one point
     modmuls_proof = (K * K + K - 1) * float(1 << v)
     t_int_launch = modmuls_launch * imads_per_mul / imad_peak
     t_hbm_launch = alg_bytes / (peak * 1e9)
@@ -678,7 +687,7 @@ def generic_roofline(T, torch, F, g, v, K, p, ms, steps, res_stats, world):
     alone = {"kernel": kname + ", 2^%d-entry tables, timed alone" % v,
              "achieved": achieved, "frac": achieved / peak, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
              "traffic": ncu_traffic(tkey, v, K, p),
-             "modmuls_per_launch": modmuls_launch, "imad_wide_per_modmul": imads_per_mul, "imad_wide_peak_per_s": imad_peak,
+             "modmuls_per_launch": modmuls_launch, "modmuls_executed_per_launch": modmuls_executed, "imad_wide_per_modmul": imads_per_mul, "imad_wide_peak_per_s": imad_peak,
              "t_integer_bound_ms": t_int_launch * 1e3, "t_hbm_bound_ms": t_hbm_launch * 1e3,
              "frac_of_slower_bound": max(t_int_launch, t_hbm_launch) / (kms * 1e-3)}
     proof = {"proof_bytes_moved": proof_bytes, "proof_frac_of_hbm_roofline": (proof_bytes / (ms * 1e-3) / 1e9) / peak,
@@ -690,7 +699,7 @@ def generic_roofline(T, torch, F, g, v, K, p, ms, steps, res_stats, world):
             "share_of_step": kms / ms,
             "binding_roofline": "integer (IMAD.WIDE)" if int_bound else "hbm",
             "note": "contract fields describe the HBM side; for this policy the integer pipe binds -- see frac_of_slower_bound" if int_bound else None,
-            "integer": {k: alone[k] for k in ("modmuls_per_launch", "imad_wide_per_modmul", "imad_wide_peak_per_s", "t_integer_bound_ms", "t_hbm_bound_ms", "frac_of_slower_bound")}}
+            "integer": {k: alone[k] for k in ("modmuls_per_launch", "modmuls_executed_per_launch", "imad_wide_per_modmul", "imad_wide_peak_per_s", "t_integer_bound_ms", "t_hbm_bound_ms", "frac_of_slower_bound")}}
     if world == 1 and res_stats["launches"] >= steps and res_stats["last_rounds"] > 0:
         res_ms = res_stats["total_ms"] / steps
         roof["resident_kernel"] = {"kernel_ms": res_ms, "rounds_last_launch": res_stats["last_rounds"], "share_of_step": res_ms / ms,

@@ -173,6 +173,13 @@ int scb_poly_sum(const scb_poly* p, uint64_t* out_elem);
 /* fused `g = g.fix_variables(&[r]); g.to_univariate()` of Prover::round (:105-112): one pass */
 int scb_poly_fix_and_round_evals(const scb_poly* p, const uint64_t* r, uint32_t n_points, scb_poly** out,
                                  uint64_t* out_elems);
+/* The same with the claim the message must satisfy, g(0) + g(1) = claim (= g_{j-1}(r_{j-1}), which Prover::round's caller
+ * holds: sum-check-protocol/src/lib.rs:286-291,316-323 is the verifier's side of it).  4-limb fields then run the leaner
+ * kernel of csrc/g4.cuh, which skips the X = 1 point and the highest point (it sums the leading coefficient instead) and
+ * rebuilds the K+1 values with exact field arithmetic: identical out_elems, 12 instead of 14 Montgomery products per 4
+ * table entries for K = 3.  Other fields: same as scb_poly_fix_and_round_evals.  A wrong claim gives wrong out_elems[1..]. */
+int scb_poly_fix_and_round_evals_claim(const scb_poly* p, const uint64_t* r, const uint64_t* claim, uint32_t n_points, scb_poly** out,
+                                       uint64_t* out_elems);
 /* sharded / device-resident variant: the partial sums stay on the device (n_points elements at
  * d_out) so that the per-round exchange of the multi-GPU prover never touches the host */
 int scb_poly_round_evals_device(const scb_poly* p, uint32_t n_points, uint64_t* d_out);

@@ -1,0 +1,116 @@
+"""The second-generation 4-limb kernel (csrc/g4.cuh: one point fewer thanks to the claim, leading coefficient instead
+of the highest point, lazy 288-bit sums, leaner carry chains) against the C oracle and against round 1's kernel."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from oracle.coracle import CField
+
+import thaler_study_b200 as T
+
+pytestmark = pytest.mark.gpu
+
+BLS = O.BLS12_381_FR.p
+BN254 = 21888242871839275222246405745257275088548364400416034343698204186575808495617  # 254 bits
+P255 = (1 << 255) - 19                                                                   # 255 bits, top word all ones
+P4 = [BLS, BN254, P255]
+pid = lambda p: f"p{p.bit_length()}_{p % 1000}"
+
+
+@pytest.mark.parametrize("p", P4, ids=pid)
+def test_g4_kernel_matches_oracle_and_first_generation(p):
+    F, cf = T.Field(p), CField(p)
+    assert F.policy == 4
+    rnd = random.Random(p & 0xFFFF)
+    for v in (2, 3, 4, 7, 11, 14):
+        seeds = [rnd.randrange(1 << 20) for _ in range(4)]
+        tabs_c = [cf.synth(s, 0, 1 << v) for s in seeds]
+        tabs_g = [T.DenseMultilinearExtension.synthetic(F, v, s) for s in seeds]
+        r = rnd.randrange(p)
+        for K in (1, 2, 3, 4):
+            g = T.ProductMLE.new(tabs_g[:K])
+            f_c = [cf.fix_variable(t, cf.to_mont([r])) for t in tabs_c[:K]]
+            want = cf.from_mont(cf.product_round_evals(f_c, K + 1))
+            claim = (want[0] + want[1]) % p
+            T.set_option("g4_kernel", 1)
+            g_new, ev_new = g.fix_and_round_evals(r, claim=claim)
+            T.set_option("g4_kernel", 0)
+            g_old, ev_old = g.fix_and_round_evals(r, claim=claim)
+            _, ev_plain = g.fix_and_round_evals(r)
+            assert ev_new == want and ev_old == want and ev_plain == want, (v, K)
+            for k in range(K):
+                assert np.array_equal(g_new.table(k).to_evaluations_mont(), f_c[k])
+                assert np.array_equal(g_old.table(k).to_evaluations_mont(), f_c[k])
+    T.reset_options()
+
+
+@pytest.mark.parametrize("p", P4, ids=pid)
+def test_g4_kernel_extreme_values(p):
+    """Entries 0 and p-1 in every pattern, challenge p-1: the lazy difference t1 - t0 + p reaches both ends of (0, 2p),
+    the unreduced products their upper bound, and every sum wraps many times."""
+    F, OF = T.Field(p), O.Field(p)
+    v = 9
+    pats = [[0, p - 1, p - 1, 0], [p - 1, 0, 0, p - 1], [p - 1] * 4, [p - 1, p - 2, 1, 0]]
+    for K in (1, 2, 3, 4):
+        vals = [(pats[(k + K) % 4] * (1 << (v - 2))) for k in range(K)]
+        og = O.ProductMLE(OF, [O.DenseMLE(OF, v, t) for t in vals])
+        g = T.ProductMLE.new([T.DenseMultilinearExtension.from_evaluations_vec(F, v, t) for t in vals])
+        for r in (p - 1, 0, 1, (p + 1) // 2):
+            of = og.fix_variables([r])
+            want = of.round_evals()
+            g2, ev = g.fix_and_round_evals(r, claim=(want[0] + want[1]) % p)
+            assert ev == want, (K, r)
+            for k in range(K):
+                assert g2.table(k).to_evaluations() == of.tables[k].evals
+
+
+@pytest.mark.parametrize("p", [BLS, BN254], ids=pid)
+def test_transcripts_through_the_g4_kernel(p):
+    """With the resident kernels switched off every round after the first is a per-round launch, which passes the claim
+    and therefore runs the g4 kernel: transcript bytes against the Python oracle, K = 1..4, and against g4_kernel = 0."""
+    OF, F = O.Field(p), T.Field(p)
+    rnd = random.Random(7)
+    T.set_option("tail_vars", 0)
+    for K, v in ((1, 6), (2, 7), (3, 8), (4, 5)):
+        vals = [[rnd.randrange(p) for _ in range(1 << v)] for _ in range(K)]
+        og = O.ProductMLE(OF, [O.DenseMLE(OF, v, t) for t in vals])
+        want = O.generate_transcript(OF, O.Prover(og))
+        outs = []
+        for flag in (1, 0):
+            T.set_option("g4_kernel", flag)
+            g = T.ProductMLE.new([T.DenseMultilinearExtension.from_evaluations_vec(F, v, t) for t in vals])
+            T.launch_count(reset=True)
+            outs.append(T.generate_transcript(T.Prover(g)))
+            assert T.launch_count() == v  # Prover::new's pass + one launch per later round: no resident kernel ran
+        assert outs[0] == want and outs[1] == want, (K, v)
+    # matrix_multiplication::G (interpolate_quadratic_poly conventions) through the same kernel
+    v = 8
+    a, b = [rnd.randrange(p) for _ in range(1 << v)], [rnd.randrange(p) for _ in range(1 << v)]
+    og = O.MatMulG(OF, O.DenseMLE(OF, v, a), O.DenseMLE(OF, v, b))
+    T.set_option("g4_kernel", 1)
+    dg = T.MatMulG.from_tables(T.DenseMultilinearExtension.from_evaluations_vec(F, v, a), T.DenseMultilinearExtension.from_evaluations_vec(F, v, b))
+    assert T.generate_transcript(T.Prover(dg)) == O.generate_transcript(OF, O.Prover(og))
+    T.reset_options()
+
+
+def test_g4_proof_2_24_matches_c_oracle():
+    """2^24 entries: rounds 1 and 2 are per-round launches of the g4 kernel under the default options (the resident
+    kernel takes over at 2^22), the rest resident; every message against the C oracle."""
+    try:
+        from test_gpu_fullsize import oracle_messages
+    except ImportError:
+        from tests.test_gpu_fullsize import oracle_messages
+
+    OF, cf, K, v = O.BLS12_381_FR, CField(BLS), 3, 24
+    F = T.Field(BLS)
+    seeds = [0xB200 + k for k in range(K)]
+    g = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, s) for s in seeds])
+    prover = T.Prover(g)
+    got_c1 = prover.c_1()
+    transcript = T.generate_transcript(prover)
+    assert T.verify_transcript(transcript, T.Verifier(v, g))
+    tabs_c = [cf.synth(s, 0, 1 << v) for s in seeds]
+    want_c1, want = oracle_messages(OF, cf, tabs_c, K, transcript)
+    assert got_c1 == want_c1 and transcript == want

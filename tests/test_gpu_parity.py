@@ -370,7 +370,7 @@ def test_error_conventions():
 @pytest.mark.parametrize("n", [1, 2, 5])
 def test_strict_verifier_rejects_a_false_claim_the_reference_logic_accepts(n):
     """The reference's last-round branch (sum-check-protocol/src/lib.rs:298-310) never links g_n to g_{n-1}: a prover
-    who claims c_1 + 1, shifts g_1 by 1/2 and then sends the honest messages is accepted.  The default (option
+    who claims c_1 + 1, shifts g_j by 2^-j for j < n and then sends the honest g_n is accepted.  The default (option
     strict_verifier = 1) rejects it; honest runs are accepted either way with the same bytes."""
     OF, F = O.FP1572869, T.Field(1572869)
     rnd = random.Random(77 + n)
@@ -386,9 +386,11 @@ def test_strict_verifier_rejects_a_false_claim_the_reference_logic_accepts(n):
         rng, r, out = PyRng(OF, 3), 1, None
         for j in range(n):
             g_j = prover.round(r, j)
-            if cheat and j == 0:
+            if cheat and (j < n - 1 or n == 1):
+                # g_j' = g_j + 2^-(j+1): g_1'(0) + g_1'(1) = c_1 + 1 and g_j'(0) + g_j'(1) = g_{j-1}'(r_{j-1}), so every
+                # check the reference makes before its last round passes; the last message is the honest g_n
                 d = dict(g_j.coeffs)
-                d[0] = (d.get(0, 0) + half) % OF.p
+                d[0] = (d.get(0, 0) + pow(half, j + 1, OF.p)) % OF.p
                 g_j = T.SparsePolynomial(F, sorted(d.items()))
             kind, val = ver.round(g_j, rng)
             if kind == "JthRound":

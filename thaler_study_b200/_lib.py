@@ -78,6 +78,7 @@ SIGNATURES = {
     "scb_poly_round_evals": (C.c_int, [vp, C.c_uint32, u64p]),
     "scb_poly_sum": (C.c_int, [vp, u64p]),
     "scb_poly_fix_and_round_evals": (C.c_int, [vp, u64p, C.c_uint32, vpp, u64p]),
+    "scb_poly_fix_and_round_evals_claim": (C.c_int, [vp, u64p, u64p, C.c_uint32, vpp, u64p]),
     "scb_poly_round_evals_device": (C.c_int, [vp, C.c_uint32, vp]),
     "scb_poly_fix_and_round_evals_device": (C.c_int, [vp, u64p, C.c_uint32, vpp, vp]),
     "scb_poly_allow_packed": (C.c_int, [vp, C.c_int]),

@@ -357,11 +357,16 @@ class SumCheckPolynomial:
         check(lib.scb_poly_round_evals(self._h, npts, _p64(out)))
         return self.F.from_mont(out[:npts])
 
-    def fix_and_round_evals(self, r: int, n_points: Optional[int] = None):
+    def fix_and_round_evals(self, r: int, n_points: Optional[int] = None, claim: Optional[int] = None):
+        """Fused `g = g.fix_variables(&[r]); g.to_univariate()` (sums at X = 0..d).  claim = g(0) + g(1) of the message
+        about to be computed lets 4-limb fields take the leaner kernel (scb_poly_fix_and_round_evals_claim)."""
         npts = self.n_points if n_points is None else n_points
         out = np.zeros((max(npts, 1), self.F.n), dtype=np.uint64)
         h = C.c_void_p()
-        check(lib.scb_poly_fix_and_round_evals(self._h, _p64(self.F.elem(r)), npts, C.byref(h), _p64(out)))
+        if claim is None:
+            check(lib.scb_poly_fix_and_round_evals(self._h, _p64(self.F.elem(r)), npts, C.byref(h), _p64(out)))
+        else:
+            check(lib.scb_poly_fix_and_round_evals_claim(self._h, _p64(self.F.elem(r)), _p64(self.F.elem(claim)), npts, C.byref(h), _p64(out)))
         return self._wrap(h), self.F.from_mont(out[:npts])
 
     # ---- two rounds per pass (small-prime fields, product polynomials; csrc/pairs.cuh)

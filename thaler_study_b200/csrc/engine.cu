@@ -23,6 +23,7 @@
 #include "tail.cuh"
 #include "persist.cuh"
 #include "pairs.cuh"
+#include "g4_launch.hpp"
 #include "sumcheck_b200.h"
 
 using namespace scb;
@@ -1201,8 +1202,31 @@ extern "C" int scb_poly_allow_packed(scb_poly* p, int enable) {
     return SCB_OK;
 }
 
-// fused fold + message (product kinds: one kernel; mixed-arity kinds: fold kernels then message kernel)
-static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_points, scb_poly** out, uint64_t* h_out, uint64_t* d_out) {
+// The 4-limb kernel (g4.cuh) accumulates S_0 = sum prod lo, S_inf = sum prod (hi - lo) (the leading coefficient) and
+// S_x = g(x) for x = 2..K-1; with the claim g(0) + g(1) the message values g(0..K) follow by exact field arithmetic:
+// g(1) = claim - g(0) and, from the K-th finite difference  sum_i (-1)^(K-i) C(K,i) g(i) = K! * lead,
+// g(K) = K! * lead - sum_{i<K} (-1)^(K-i) C(K,i) g(i).  Same field elements as summing every point.
+static void g4_rebuild_evals(const HostField& h, uint32_t K, const Fe& claim, const Fe* S, Fe* ev) {
+    ev[0] = S[0];
+    ev[1] = h.sub(claim, S[0]);
+    if (K == 1) return;
+    for (uint32_t x = 2; x < K; ++x) ev[x] = S[x];
+    Fe fact = h.one(), acc = h.zero();
+    for (uint32_t i = 2; i <= K; ++i) fact = h.mul(fact, h.from_u64(i));
+    uint64_t binom = 1;  // C(K, i)
+    for (uint32_t i = 0; i < K; ++i) {
+        const Fe term = h.mul(h.from_u64(binom), ev[i]);
+        acc = ((K - i) & 1) ? h.sub(acc, term) : h.add(acc, term);
+        binom = binom * (K - i) / (i + 1);
+    }
+    ev[K] = h.sub(h.mul(fact, S[1]), acc);
+}
+
+// fused fold + message (product kinds: one kernel; mixed-arity kinds: fold kernels then message kernel).
+// claim (optional, host results only) = g(0) + g(1) of the message about to be computed, i.e. g_{j-1}(r_{j-1}): lets the
+// 4-limb kernel skip one point (g4.cuh).
+static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_points, scb_poly** out, uint64_t* h_out, uint64_t* d_out,
+                              const uint64_t* claim = nullptr) {
     ARG_TRY(p && r && out && (h_out || d_out), "null argument");
     ARG_TRY(n_points >= 1 && n_points <= poly_n_points(p), "n_points out of range for this polynomial");
     ARG_TRY(poly_num_vars(p) >= 2, "need at least two variables to fix one and send a message");
@@ -1211,8 +1235,40 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
     const FieldImpl& f = *p->f;
     const uint32_t N = f.d.n;
     ARG_TRY(elem_canonical(f, r), "challenge is not a canonical field element");
+    ARG_TRY(!claim || elem_canonical(f, claim), "claim is not a canonical field element");
     uint64_t* res = d_out ? (n_points == poly_n_points(p) ? d_out : c->d_scratch) : c->h_res;
     std::unique_ptr<scb_poly> q;
+    if ((p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) && f.policy == POL_G4 && claim && h_out && opt(OPT_g4_kernel) != 0 &&
+        f.h.bits <= 255 && p->t[0].nv >= 2) {
+        // 4-limb fields: leaner kernel, one point fewer, message rebuilt from the claim on the host
+        const uint32_t K = (uint32_t)p->t.size();
+        q = std::make_unique<scb_poly>(*p);
+        const uint64_t* in[kMaxTables];
+        uint64_t* o[kMaxTables];
+        for (uint32_t k = 0; k < K; ++k) {
+            q->t[k].nv = p->t[k].nv - 1;
+            q->t[k].buf.reset();
+            RC_TRY(alloc_buf((size_t)8 * N << q->t[k].nv, &q->t[k].buf));
+            in[k] = p->t[k].buf->ptr;
+            o[k] = q->t[k].buf->ptr;
+        }
+        const cudaError_t le = launch_fold_round_g4((int)K, (int)opt(OPT_bps), c->sms, g_stream, f.d, in, o, elem_arg(f, r), p->t[0].len() / 4, c->partials,
+                                                    c->ticket, c->h_res, peer_arg(c), kMaxGrid);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (le != cudaSuccess) {
+            set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(le), __FILE__, __LINE__);
+            return SCB_ECUDA;
+        }
+        CU_TRY(cudaStreamSynchronize(g_stream));
+        RC_TRY(peers_check(c));
+        Fe S[kMaxPts], ev[kMaxPts], cl;
+        for (int x = 0; x < g4_n_sums((int)K); ++x) f.h.load(c->h_res + (size_t)x * N, S[x]);
+        f.h.load(claim, cl);
+        g4_rebuild_evals(f.h, K, cl, S, ev);
+        for (uint32_t x = 0; x < n_points; ++x) f.h.store(ev[x], h_out + (size_t)x * N);
+        *out = q.release();
+        return SCB_OK;
+    }
     if (p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) {
         ARG_TRY(f.policy != POL_SP || p->t[0].nv <= 32, "table too large for the small-prime path");
         q = std::make_unique<scb_poly>(*p);
@@ -1277,6 +1333,11 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
 }
 extern "C" int scb_poly_fix_and_round_evals(const scb_poly* p, const uint64_t* r, uint32_t n_points, scb_poly** out, uint64_t* out_elems) {
     return fix_and_round_impl(p, r, n_points, out, out_elems, nullptr);
+}
+extern "C" int scb_poly_fix_and_round_evals_claim(const scb_poly* p, const uint64_t* r, const uint64_t* claim, uint32_t n_points, scb_poly** out,
+                                                  uint64_t* out_elems) {
+    ARG_TRY(claim, "null argument");
+    return fix_and_round_impl(p, r, n_points, out, out_elems, nullptr, claim);
 }
 extern "C" int scb_poly_fix_and_round_evals_device(const scb_poly* p, const uint64_t* r, uint32_t n_points, scb_poly** out, uint64_t* d_out) {
     return fix_and_round_impl(p, r, n_points, out, nullptr, d_out);

@@ -1,0 +1,286 @@
+// g4.cuh -- second-generation fused fold + round message for 4-limb fields (BLS12-381 Fr =
+// ark_ed_on_bls12_381::Fq, /root/reference/Cargo.toml:20; [ARK] Fp<MontBackend<_,4>,4>).
+//
+// Replaces, for round j >= 1 of a product polynomial,
+//     self.g = self.g.fix_variables(&[r_prev]); self.g.to_univariate()     sum-check-protocol/src/lib.rs:105-112
+// like k_fold_round (kernels.cuh), with three changes that cut the instruction count per 4 table entries from ~4100 to
+// ~3000 (profiles/r01_ncu_bls_fold_round_evenodd.md found the kernel issue-bound at IPC 0.38, not HBM-bound):
+//
+//  1. One point fewer.  The prover knows the claim g_j(0) + g_j(1) = g_{j-1}(r_{j-1}) before the pass starts, so g_j(1)
+//     is NOT accumulated; and the leading coefficient (the "point at infinity", prod_k (hi_k - lo_k)) replaces the
+//     highest finite point, which saves the repeated additions that build lo + X (hi - lo).  Per folded pair the pass
+//     accumulates  S_0 = prod lo_k,  S_inf = prod (hi_k - lo_k),  S_x = prod (lo_k + x (hi_k - lo_k)) for x = 2..K-1:
+//     K products instead of K + 1, i.e. 12 Montgomery products per 4 entries instead of 14 for K = 3.  The host rebuilds
+//     g_j(0..K) from them and the claim with exact field arithmetic (engine.cu: g4_rebuild_evals) -- the same field
+//     elements the reference computes, so messages and transcript bytes are unchanged.
+//  2. Leaner carry chains.  In the even/odd CIOS of mont32.cuh every 4-product chain ended with two carry adds into
+//     words 8 and 9 of its accumulator window; an accumulator never exceeds 2^259 relative to its window base (it
+//     receives less than 2^257 per row and loses 64 bits every two rows), so word 9 never changes and its add is
+//     dropped: 32 instructions fewer per product.
+//  3. Lazy sums.  The last factor of every message product is multiplied WITHOUT the final conditional subtraction and
+//     added into a 288-bit integer accumulator (9 instructions instead of 17 + 25); the accumulators are reduced once
+//     per thread (hi * 2^256 = hi * R, one Montgomery product by R^2).  The fold's difference t1 - t0 is formed as
+//     t1 - t0 + p in (0, 2p) without a select: with the canonical challenge as the other operand the product stays
+//     below 2p and the usual single subtraction makes it canonical.
+//
+// Everything stored to HBM is canonical, as everywhere else.
+#pragma once
+#include <cstdint>
+
+#include "kernels.cuh"
+
+namespace scb {
+namespace g4 {
+
+// (t0,t1) += x0*b, (t2,t3) += x1*b, (t4,t5) += x2*b, (t6,t7) += x3*b, carry into t8.  ptxas fuses each
+// mad.lo.cc / madc.hi.cc pair into one IMAD.WIDE.U32.X on the aligned register pair.
+__device__ __forceinline__ void chain(uint32_t* t, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t b) {
+    asm("mad.lo.cc.u32   %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32  %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32  %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32  %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32  %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32  %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32  %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32  %7, %12, %13, %7;\n\t"
+        "addc.u32        %8, %8, 0;\n\t"
+        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
+}
+// the same chain started by the carry of `e0 += orphan` (the word that fell out of the other accumulator when the
+// window moved on by one word)
+__device__ __forceinline__ void chain_fix(uint32_t& e0, uint32_t orphan, uint32_t* t, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t b) {
+    asm("add.cc.u32      %9, %9, %15;\n\t"
+        "madc.lo.cc.u32  %0, %10, %14, %0;\n\t"
+        "madc.hi.cc.u32  %1, %10, %14, %1;\n\t"
+        "madc.lo.cc.u32  %2, %11, %14, %2;\n\t"
+        "madc.hi.cc.u32  %3, %11, %14, %3;\n\t"
+        "madc.lo.cc.u32  %4, %12, %14, %4;\n\t"
+        "madc.hi.cc.u32  %5, %12, %14, %5;\n\t"
+        "madc.lo.cc.u32  %6, %13, %14, %6;\n\t"
+        "madc.hi.cc.u32  %7, %13, %14, %7;\n\t"
+        "addc.u32        %8, %8, 0;\n\t"
+        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(e0)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b), "r"(orphan));
+}
+
+struct W8 {
+    uint32_t w[8];
+};
+struct W9 {  // 288-bit integer: lazy sum of unreduced products
+    uint32_t w[9];
+};
+
+__device__ __forceinline__ W8 load8(const uint64_t* l) {
+    W8 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        r.w[2 * i] = (uint32_t)l[i];
+        r.w[2 * i + 1] = (uint32_t)(l[i] >> 32);
+    }
+    return r;
+}
+__device__ __forceinline__ void store8(const W8& a, uint64_t* l) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) l[i] = (uint64_t)a.w[2 * i] | ((uint64_t)a.w[2 * i + 1] << 32);
+}
+
+struct Arith {
+    uint32_t p[8];
+    uint32_t n0;
+
+    __device__ __forceinline__ explicit Arith(const FieldDesc& f) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            p[2 * i] = (uint32_t)f.p[i];
+            p[2 * i + 1] = (uint32_t)(f.p[i] >> 32);
+        }
+        n0 = (uint32_t)f.inv;
+    }
+    // a * b * 2^-256 as an UNREDUCED 257-bit value (lo, top) < a*b/2^256 + p: below 2p whenever one factor is below p
+    // and the other below 2p.  Even/odd two-accumulator CIOS of mont32.cuh without the dead word-9 carry adds.
+    __device__ __forceinline__ void mul_raw(uint32_t (&lo)[8], uint32_t& top, const W8& a, const W8& b) const {
+        uint32_t A0[20], A1[20], sink = 0;
+#pragma unroll
+        for (int i = 0; i < 20; ++i) A0[i] = A1[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t* E = (i & 1) ? A1 + (i - 1) : A0 + i;
+            uint32_t* O = (i & 1) ? A0 + (i + 1) : A1 + i;
+            if (i == 0) {
+                chain(O, a.w[1], a.w[3], a.w[5], a.w[7], b.w[i]);
+            } else {
+                const uint32_t orphan = (i & 1) ? A0[i] : A1[i - 1];  // previous E[1]
+                chain_fix(E[0], orphan, O, a.w[1], a.w[3], a.w[5], a.w[7], b.w[i]);
+            }
+            chain(E, a.w[0], a.w[2], a.w[4], a.w[6], b.w[i]);
+            const uint32_t m = E[0] * n0;
+            chain(O, p[1], p[3], p[5], p[7], m);
+            chain(E, p[0], p[2], p[4], p[6], m);  // E[0] becomes 0
+            // E[0] is dead from here on; OR-ing it into a sink keeps the low half of its product alive, so ptxas emits
+            // ONE full-rate IMAD.WIDE for the pair instead of IMAD + half-rate IMAD.HI (the carry is all that is needed)
+            sink |= E[0];
+        }
+        A0[16] |= sink;  // always zero
+        // window after row 7: E = A0 + 8, O = A1 + 8, orphan = A1[7];  t = orphan + E + (O << 32)
+        asm("add.cc.u32  %0, %9, %18;\n\t"
+            "addc.cc.u32 %1, %10, %19;\n\t"
+            "addc.cc.u32 %2, %11, %20;\n\t"
+            "addc.cc.u32 %3, %12, %21;\n\t"
+            "addc.cc.u32 %4, %13, %22;\n\t"
+            "addc.cc.u32 %5, %14, %23;\n\t"
+            "addc.cc.u32 %6, %15, %24;\n\t"
+            "addc.cc.u32 %7, %16, %25;\n\t"
+            "addc.u32    %8, %17, %26;\n\t"
+            : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]), "=r"(lo[4]), "=r"(lo[5]), "=r"(lo[6]), "=r"(lo[7]), "=r"(top)
+            : "r"(A0[8]), "r"(A0[9]), "r"(A0[10]), "r"(A0[11]), "r"(A0[12]), "r"(A0[13]), "r"(A0[14]), "r"(A0[15]), "r"(A0[16]),
+              "r"(A1[7]), "r"(A1[8]), "r"(A1[9]), "r"(A1[10]), "r"(A1[11]), "r"(A1[12]), "r"(A1[13]), "r"(A1[14]), "r"(A1[15]));
+    }
+    // (lo, top) < 2p  ->  canonical
+    __device__ __forceinline__ W8 reduce_once(const uint32_t (&lo)[8], uint32_t top) const {
+        uint32_t d[8];
+        const uint32_t borrow = sub8(d, lo, p);
+        const bool use_d = top != 0 || borrow == 0;
+        W8 r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.w[i] = use_d ? d[i] : lo[i];
+        return r;
+    }
+    __device__ __forceinline__ W8 mul(const W8& a, const W8& b) const {
+        uint32_t lo[8], top;
+        mul_raw(lo, top, a, b);
+        return reduce_once(lo, top);
+    }
+    __device__ __forceinline__ W8 add(const W8& a, const W8& b) const {
+        uint32_t s[8], d[8];
+        const uint32_t carry = add8(s, a.w, b.w);
+        const uint32_t borrow = sub8(d, s, p);
+        const bool use_d = carry != 0 || borrow == 0;
+        W8 r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.w[i] = use_d ? d[i] : s[i];
+        return r;
+    }
+    __device__ __forceinline__ W8 sub(const W8& a, const W8& b) const {
+        uint32_t d[8], e[8];
+        const uint32_t borrow = sub8(d, a.w, b.w);
+        add8(e, d, p);
+        W8 r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.w[i] = borrow ? e[i] : d[i];
+        return r;
+    }
+    // a - b + p in (0, 2p) for canonical a, b: no select.  2p < 2^256 needs bits(p) <= 255 (host checks).
+    __device__ __forceinline__ W8 diff_lazy(const W8& a, const W8& b) const {
+        uint32_t s[8];
+        W8 r;
+        add8(s, a.w, p);
+        sub8(r.w, s, b.w);
+        return r;
+    }
+    // t0 + r * (t1 - t0), canonical
+    __device__ __forceinline__ W8 fold(const W8& t0, const W8& t1, const W8& r) const { return add(t0, mul(diff_lazy(t1, t0), r)); }
+};
+
+__device__ __forceinline__ void acc_zero(W9& a) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a.w[i] = 0;
+}
+__device__ __forceinline__ void acc_add(W9& a, const uint32_t (&lo)[8], uint32_t top) {
+    asm("add.cc.u32  %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, %10;\n\t"
+        "addc.cc.u32 %2, %2, %11;\n\t"
+        "addc.cc.u32 %3, %3, %12;\n\t"
+        "addc.cc.u32 %4, %4, %13;\n\t"
+        "addc.cc.u32 %5, %5, %14;\n\t"
+        "addc.cc.u32 %6, %6, %15;\n\t"
+        "addc.cc.u32 %7, %7, %16;\n\t"
+        "addc.u32    %8, %8, %17;\n\t"
+        : "+r"(a.w[0]), "+r"(a.w[1]), "+r"(a.w[2]), "+r"(a.w[3]), "+r"(a.w[4]), "+r"(a.w[5]), "+r"(a.w[6]), "+r"(a.w[7]), "+r"(a.w[8])
+        : "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]), "r"(top));
+}
+
+// Number of sums the pass accumulates for K tables: S_0, S_inf (K >= 2), S_2 .. S_{K-1}.
+__host__ __device__ constexpr int n_sums(int K) { return K; }
+
+// One thread-iteration handles 4 adjacent entries of every table (a "quad"): two folded entries per table = one
+// hypercube pair of the next round.  Sums are written as n_sums(K) canonical elements (order: S_0, S_inf, S_2, ...).
+template <int K>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_fold_round_g4(FieldDesc f, TabsIn<K> in, TabsOut<K> outp, ElemArg rarg, uint64_t n_quads, uint64_t* partials, unsigned int* ticket,
+                    uint64_t* out, PeerArg peer) {
+    constexpr int NS = n_sums(K);
+    const Arith ar(f);
+    const W8 r = load8(rarg.w);
+    W9 acc[NS];
+#pragma unroll
+    for (int x = 0; x < NS; ++x) acc_zero(acc[x]);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_quads; i += stride) {
+        W8 prod[NS];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            uint64_t w[16];
+            ld_words<16>(in.p[k] + i * 16, w);
+            const W8 u0 = ar.fold(load8(w), load8(w + 4), r);
+            const W8 u1 = ar.fold(load8(w + 8), load8(w + 12), r);
+            uint64_t o[8];
+            store8(u0, o);
+            store8(u1, o + 4);
+            st_words<8>(outp.p[k] + i * 8, o);
+            // factors of this table at the points 0, inf, 2, 3, ...: lo, hi - lo, hi + (hi - lo), ...
+            W8 fac[NS];
+            fac[0] = u0;
+            if constexpr (K >= 2) {
+                fac[1] = ar.sub(u1, u0);
+#pragma unroll
+                for (int x = 2; x < NS; ++x) fac[x] = ar.add(x == 2 ? u1 : fac[x - 1], fac[1]);
+            }
+#pragma unroll
+            for (int x = 0; x < NS; ++x) {
+                if (k == 0 && K > 1) {
+                    prod[x] = fac[x];
+                } else if (k < K - 1) {
+                    prod[x] = ar.mul(prod[x], fac[x]);
+                } else {  // last factor: unreduced product straight into the 288-bit sum
+                    uint32_t lo[8], top;
+                    if constexpr (K == 1) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) lo[q] = fac[x].w[q];
+                        top = 0;
+                    } else {
+                        ar.mul_raw(lo, top, prod[x], fac[x]);
+                    }
+                    acc_add(acc[x], lo, top);
+                }
+            }
+        }
+    }
+    // 288-bit sums -> canonical elements: value = hi * 2^256 + lo256, 2^256 = R (mod p), hi * R = montmul(hi, R^2)
+    const PolGN<4> A(f);
+    typename PolGN<4>::Acc fin[NS];
+#pragma unroll
+    for (int x = 0; x < NS; ++x) {
+        // lo256 is an arbitrary 256-bit integer (many multiples of p for small moduli):
+        // lo256 mod p = montmul(montmul(lo256, R^2), 1); mul_raw only needs its operands below 2^256
+        W8 lo, hi, one_int;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            lo.w[q] = acc[x].w[q];
+            hi.w[q] = 0;
+            one_int.w[q] = 0;
+        }
+        hi.w[0] = acc[x].w[8];
+        one_int.w[0] = 1;
+        const W8 r2 = load8(f.r2);
+        const W8 hr = ar.mul(hi, r2);
+        const W8 s = ar.add(ar.mul(ar.mul(lo, r2), one_int), hr);
+        uint64_t l[4];
+        store8(s, l);
+        fin[x] = A.from_words(l);
+    }
+    grid_reduce_finish<PolGN<4>, NS>(A, fin, partials, ticket, out, 0, &peer);
+}
+
+}  // namespace g4
+}  // namespace scb

@@ -1,0 +1,20 @@
+// g4_launch.hpp -- host entry of the 4-limb fused fold + message kernel (g4.cuh), shared by g4.cu and engine.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.cuh"
+
+namespace scb {
+
+// number of sums the kernel writes for K tables (S_0, S_inf, S_2, ..): see g4.cuh
+inline int g4_n_sums(int K) { return K; }
+// Launches k_fold_round_g4<K>: folds variable 0 of the K tables by r (outp: K tables of 2 * n_quads elements) and
+// accumulates the sums of the folded tables' round message.  res: g4_n_sums(K) canonical elements (mapped host or
+// device memory).  One resident wave of CTAs (occupancy calculator, optionally capped).
+cudaError_t launch_fold_round_g4(int K, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
+                                 uint64_t* const* outp, const ElemArg& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res,
+                                 const PeerArg& pa, int max_grid);
+
+}  // namespace scb

@@ -141,6 +141,9 @@ struct scb_prover {
     uint32_t num_vars = 0;
     const FieldImpl* fi = nullptr;
     uint32_t kind = 0, np = 0;
+    // the message sent last, while the per-round path is in use: g_{j-1}(r_{j-1}) is the claim the next message must sum to
+    bool have_last = false;
+    SparsePoly last_msg;
     bool have_round0 = false;   // round-0 sums computed by Prover::new (they also yield c_1)
     std::vector<Fe> round0;
     // small-prime fields: Prover::new's pass accumulates the (K+1)^2 grid H[a][b] (pairs.cuh) instead of the K+1
@@ -266,11 +269,19 @@ static int prover_round(scb_prover* p, const Fe* r_prev, uint32_t j, SparsePoly*
         RC_TRY(maybe_consolidate(p));
         scb_poly* next = nullptr;
         PeersScope scope(p->sharded ? p->peers : nullptr);  // per-round exchange inside the kernel while sharded
-        RC_TRY(scb_poly_fix_and_round_evals(p->g, rw, p->np, &next, w));
+        if (p->have_last) {  // g_j(0) + g_j(1) = g_{j-1}(r_{j-1}) is known before the pass: one point fewer to accumulate
+            uint64_t cw[kHostMaxLimbs];
+            F.store(p->last_msg.evaluate(F, *r_prev), cw);
+            RC_TRY(scb_poly_fix_and_round_evals_claim(p->g, rw, cw, p->np, &next, w));
+        } else {
+            RC_TRY(scb_poly_fix_and_round_evals(p->g, rw, p->np, &next, w));
+        }
         scb_poly_free(p->g);
         p->g = next;
     } else if (p->have_round0) {
         *out = evals_to_poly(F, p->kind, p->round0);
+        p->last_msg = *out;
+        p->have_last = true;
         return SCB_OK;
     } else {
         RC_TRY(scb_poly_round_evals(p->g, p->np, w));
@@ -278,6 +289,8 @@ static int prover_round(scb_prover* p, const Fe* r_prev, uint32_t j, SparsePoly*
     std::vector<Fe> ev(p->np);
     for (uint32_t i = 0; i < p->np; ++i) F.load(w + (size_t)i * F.n, ev[i]);
     *out = evals_to_poly(F, p->kind, ev);
+    p->last_msg = *out;
+    p->have_last = true;
     return SCB_OK;
 }
 extern "C" int scb_prover_round(scb_prover* p, const uint64_t* r_prev, uint32_t j, uint64_t* degrees, uint64_t* coeffs,
@@ -605,6 +618,7 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
         if (rc != SCB_OK && rc != SCB_ETAIL) return rc;
         if (rc == SCB_OK && resident) resident_succeeded();
         j = pc.msgs;
+        p->have_last = false;  // the messages above did not go through prover_round
         if (rc == SCB_ETAIL) {
             // lock-step lost (e.g. a profiler serialises kernel and host): keep the messages that are out, fold the
             // tables by the challenges they were derived with and carry on with one launch per round
@@ -642,6 +656,7 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
                 scb_poly_free(p->g);  // carry on from the slab the kernel left behind: consolidation comes next
                 p->g = folded;
                 j += done;
+                p->have_last = false;
                 continue;
             }
             if (rc != SCB_ETAIL) return rc;
@@ -654,6 +669,7 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
                 scb_poly_free(p->g);
                 p->g = refolded;
                 j += done;
+                p->have_last = false;
             }
             continue;
         }
