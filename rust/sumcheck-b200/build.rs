@@ -8,7 +8,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     let common = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"];
-    for (src, obj, arch) in [("engine.cu", "engine.o", true), ("protocol.cpp", "protocol.o", false)] {
+    for (src, obj, arch) in [("engine.cu", "engine.o", true), ("g4.cu", "g4.o", true), ("protocol.cpp", "protocol.o", false)] {
         let mut c = Command::new(&nvcc);
         if arch {
             c.args(["-gencode", "arch=compute_100a,code=sm_100a"]);
@@ -25,6 +25,7 @@ fn main() {
         .args(["crs"])
         .arg(out.join("libsumcheck_b200.a"))
         .arg(out.join("engine.o"))
+        .arg(out.join("g4.o"))
         .arg(out.join("protocol.o"))
         .status()
         .unwrap();

@@ -166,3 +166,141 @@ impl<F: PrimeField> SumCheckPolynomial<F> for GpuPoly<F> {
         v
     }
 }
+
+// =====================================================================================================================
+// The FAST path: replacements for `sum_check_protocol::Prover::{new, round}` (sum-check-protocol/src/lib.rs:88-112)
+// and `fiat_shamir::generate_transcript` (fiat-shamir/src/lib.rs:75-98) on top of the library's own prover object.
+// `Prover<F, GpuPoly<F>>` above is the drop-in through the trait only: it pays `to_evaluations()` (a 2^v-entry D2H) in
+// `Prover::new` and two launches per round.  `GpuProver<F>` keeps everything on the device: c_1 comes from the first
+// pass (which also yields g_1, and g_2 for small-prime fields), every later round is ONE fused fold+message pass, and
+// under Fiat-Shamir (`generate_transcript_gpu`) the whole proof runs in resident kernels.  Same messages, same bytes
+// (bench.py's `e2e.trait_only.equals_fast_path_bytes`, tests/test_gpu_trait_path.py).
+// =====================================================================================================================
+#[repr(C)] pub struct scb_prover { _p: [u8; 0] }
+
+/// `scb_pair_cb` of include/sumcheck_b200.h
+pub type ScbPairCb = unsafe extern "C" fn(user: *mut std::os::raw::c_void, pass: u32, n_vals: u32, vals: *const u64, next_pair_out: *mut u64) -> c_int;
+
+extern "C" {
+    fn scb_prover_new(g: *const scb_poly, out: *mut *mut scb_prover) -> c_int;                       // Prover::new  :88-97
+    fn scb_prover_free(p: *mut scb_prover);
+    fn scb_prover_c_1(p: *const scb_prover, out: *mut u64) -> c_int;                                 // :100-102
+    fn scb_prover_num_vars(p: *const scb_prover, out: *mut u32) -> c_int;                            // :114-116
+    fn scb_prover_round(p: *mut scb_prover, r_prev: *const u64, j: u32, degrees: *mut u64, coeffs: *mut u64, cap: u32, n: *mut u32) -> c_int; // :105-112
+    fn scb_fs_generate_transcript(p: *mut scb_prover, out: *mut u8, cap: usize, out_len: *mut usize, offsets: *mut u64) -> c_int; // fiat-shamir :75-98
+    fn scb_poly_n_points(p: *const scb_poly, out: *mut u32) -> c_int;
+    fn scb_poly_grid_evals(p: *const scb_poly, out: *mut u64) -> c_int;
+    fn scb_poly_resident_pairs(p: *const scb_poly, ra: *const u64, rb: *const u64, max_passes: u32, cb: ScbPairCb, user: *mut std::os::raw::c_void,
+                               passes_done: *mut u32, out_folded: *mut *mut scb_poly) -> c_int;
+    fn scb_poly_fix_and_round_evals_claim(p: *const scb_poly, r: *const u64, claim: *const u64, n_points: u32, out: *mut *mut scb_poly, out_elems: *mut u64) -> c_int;
+    fn scb_set_option(name: *const std::os::raw::c_char, value: i64) -> c_int;
+}
+
+/// Library switches (csrc/options.hpp).  The library never reads the environment; a host that wants a switch sets it here.
+pub fn set_option(name: &str, value: i64) {
+    let c = std::ffi::CString::new(name).unwrap();
+    check(unsafe { scb_set_option(c.as_ptr(), value) });
+}
+
+/// Drop-in for `sum_check_protocol::Prover<F, P>` with the same four methods.
+pub struct GpuProver<F: PrimeField> {
+    prover: *mut scb_prover,
+    _g: GpuPoly<F>, // keeps the field handle alive
+}
+
+impl<F: PrimeField> GpuProver<F> {
+    /// `Prover::new(g)`: c_1 without the 2^v-entry host `Vec` (:89).
+    pub fn new(g: GpuPoly<F>) -> Self {
+        let mut prover = ptr::null_mut();
+        check(unsafe { scb_prover_new(g.poly, &mut prover) });
+        Self { prover, _g: g }
+    }
+    pub fn c_1(&self) -> F {
+        let mut out = F::zero();
+        check(unsafe { scb_prover_c_1(self.prover, &mut out as *mut F as *mut u64) });
+        out
+    }
+    /// `Prover::round(r_prev, j)`: fold + message in one pass for j >= 1.
+    pub fn round(&mut self, r_prev: F, j: usize) -> SparsePolynomial<F> {
+        let (mut deg, mut co, mut n) = ([0u64; 8], vec![F::zero(); 8], 0u32);
+        check(unsafe { scb_prover_round(self.prover, &r_prev as *const F as *const u64, j as u32, deg.as_mut_ptr(), co.as_mut_ptr() as *mut u64, 8, &mut n) });
+        SparsePolynomial::from_coefficients_vec((0..n as usize).map(|i| (deg[i] as usize, co[i])).collect())
+    }
+    pub fn num_vars(&self) -> usize {
+        let mut n = 0u32;
+        check(unsafe { scb_prover_num_vars(self.prover, &mut n) });
+        n as usize
+    }
+}
+impl<F: PrimeField> Drop for GpuProver<F> {
+    fn drop(&mut self) { unsafe { scb_prover_free(self.prover) } }
+}
+
+/// With this impl the reference's own `fiat_shamir::generate_transcript::<F, GpuProver<F>, H>` runs unchanged, for any
+/// hasher H, one fused pass per round.  (Add `fiat-shamir`, `ark-serialize` to [dependencies].)
+impl<F: PrimeField> fiat_shamir::InteractiveProver<F> for GpuProver<F> {
+    fn g_1(&mut self) -> fiat_shamir::Result<Vec<u8>> {
+        use ark_serialize::CanonicalSerialize;
+        let mut res = vec![];
+        let p: (F, SparsePolynomial<F>) = (self.c_1(), GpuProver::round(self, F::one(), 0));
+        p.serialize_uncompressed(&mut res)?;
+        Ok(res)
+    }
+    fn round(&mut self, j: usize, r_j: F) -> fiat_shamir::Result<Vec<u8>> {
+        use ark_serialize::CanonicalSerialize;
+        let mut res = vec![];
+        GpuProver::round(self, r_j, j).serialize_uncompressed(&mut res)?;
+        Ok(res)
+    }
+    fn num_rounds(&self) -> usize { self.num_vars() }
+}
+
+/// `fiat_shamir::generate_transcript::<F, Prover<F, P>, DefaultFieldHasher<Sha256>>` (fiat-shamir/src/lib.rs:75-98) with
+/// the hash chain inside the library: resident kernels, two rounds per pass for small-prime fields, no per-round launch
+/// or stream synchronisation.  Returns the messages g_1, g_2, ... exactly as `FiatShamirTranscript.g` holds them.
+pub fn generate_transcript_gpu<F: PrimeField>(prover: GpuProver<F>) -> Vec<Vec<u8>> {
+    let nv = prover.num_vars();
+    let elem = (F::MODULUS_BIT_SIZE as usize + 7) / 8;
+    let cap = 64 + nv * (8 + 8 * (8 + elem)) + elem;
+    let (mut buf, mut len, mut offs) = (vec![0u8; cap], 0usize, vec![0u64; nv + 2]);
+    check(unsafe { scb_fs_generate_transcript(prover.prover, buf.as_mut_ptr(), cap, &mut len, offs.as_mut_ptr()) });
+    (0..nv.max(1)).map(|i| buf[offs[i] as usize..offs[i + 1] as usize].to_vec()).collect()
+}
+
+/// The callback form for a host that owns the transcript (any hash, any message format): Prover::new's grid, then every
+/// pass of the proof inside ONE resident kernel; `next` receives a pass's (K+1)^2 grid sums H[a][b] (or the K+1 line sums
+/// when a single variable is left) and returns the next two challenges.  Small-prime fields, product polynomials
+/// (include/sumcheck_b200.h: scb_poly_grid_evals / scb_poly_resident_pairs; csrc/pairs.cuh for the algebra:
+/// g_j(X) = H(X,0) + H(X,1), g_{j+1}(Y) = H(r_j, Y)).
+pub fn prove_with_pair_callback<F: PrimeField, N: FnMut(u32, &[F]) -> (F, F)>(g: &GpuPoly<F>, first_pair: impl FnOnce(&[F]) -> (F, F), mut next: N) {
+    unsafe extern "C" fn tramp<F: PrimeField, N: FnMut(u32, &[F]) -> (F, F)>(user: *mut std::os::raw::c_void, pass: u32, n_vals: u32, vals: *const u64,
+                                                                            out: *mut u64) -> c_int {
+        let f = &mut *(user as *mut N);
+        let vals = std::slice::from_raw_parts(vals as *const F, n_vals as usize);
+        let (ra, rb) = f(pass, vals);
+        *(out as *mut F) = ra;
+        *(out as *mut F).add(1) = rb;
+        0
+    }
+    let mut np = 0u32;
+    check(unsafe { scb_poly_n_points(g.poly, &mut np) });
+    let mut grid = vec![F::zero(); (np * np) as usize];
+    check(unsafe { scb_poly_grid_evals(g.poly, grid.as_mut_ptr() as *mut u64) });
+    let (ra, rb) = first_pair(&grid);
+    let mut done = 0u32;
+    check(unsafe {
+        scb_poly_resident_pairs(g.poly, &ra as *const F as *const u64, &rb as *const F as *const u64, 0, tramp::<F, N>,
+                                &mut next as *mut N as *mut std::os::raw::c_void, &mut done, ptr::null_mut())
+    });
+}
+
+/// One fused round for a host-driven prover that knows the claim g_j(0) + g_j(1) = g_{j-1}(r_{j-1}): 4-limb fields skip a
+/// point (csrc/g4.cuh).  Returns (folded polynomial, sums at X = 0..d).
+pub fn fix_and_round_with_claim<F: PrimeField>(g: &GpuPoly<F>, r: F, claim: F) -> (GpuPoly<F>, Vec<F>) {
+    let mut np = 0u32;
+    check(unsafe { scb_poly_n_points(g.poly, &mut np) });
+    let mut out = vec![F::zero(); np as usize];
+    let mut poly = ptr::null_mut();
+    check(unsafe { scb_poly_fix_and_round_evals_claim(g.poly, &r as *const F as *const u64, &claim as *const F as *const u64, np, &mut poly, out.as_mut_ptr() as *mut u64) });
+    (GpuPoly { field: g.field, poly, owns_field: false, _f: PhantomData }, out)
+}
