@@ -24,6 +24,7 @@
 #include "persist.cuh"
 #include "pairs.cuh"
 #include "g4_launch.hpp"
+#include "tri.cuh"
 #include "sumcheck_b200.h"
 
 using namespace scb;
@@ -286,6 +287,9 @@ struct scb_poly {
     std::vector<Table> t;
     uint32_t var_len = 0;  // triangle_counting::G::var_len
     bool allow_packed = false;  // descendants produced by fix_and_round may keep packed uint32 tables
+    // triangle_counting::G while an x variable is left: M[z][x] = sum_y f2[z][y] f1[y][x] (tri.cuh), index (z << xn) | x
+    bool has_aux = false;
+    Table aux;
     bool any_packed() const {
         for (const Table& x : t)
             if (x.p32) return true;
@@ -938,6 +942,30 @@ extern "C" int scb_poly_matmul_g_new(const scb_field* f, uint32_t n, const uint6
     scb_mle_free(mbf);
     return rc;
 }
+// M = f2 x f1 as matrices (tri.cuh): computed once per polynomial, folded along x with it afterwards
+static int triangle_build_aux(Ctx* c, scb_poly* p) {
+    const uint32_t xn = p->t[0].nv > p->var_len ? p->t[0].nv - p->var_len : 0;
+    const uint32_t yn = p->t[1].nv > p->var_len ? p->t[1].nv - p->var_len : 0;
+    const uint32_t zn = p->t[2].nv < p->var_len ? p->t[2].nv : p->var_len;
+    p->has_aux = false;
+    if (xn == 0 || xn + zn > 30) return SCB_OK;
+    const FieldImpl& f = *p->f;
+    Table m;
+    m.nv = xn + zn;
+    RC_TRY(alloc_buf((size_t)8 * f.d.n << m.nv, &m.buf));
+    const uint32_t X = 1u << xn, Y = 1u << yn, Z = 1u << zn;
+    if (f.policy == POL_SP) {
+        const dim3 grid((X + kMmTile - 1) / kMmTile, (Z + kMmTile - 1) / kMmTile);
+        k_field_matmul_sp<<<grid, 256, 0, g_stream>>>(f.d, p->t[0].buf->ptr, p->t[1].buf->ptr, m.buf->ptr, X, Y, Z);
+    } else {
+        const dim3 grid((X + 15) / 16, (Z + 15) / 16);
+        DISPATCH_POLICY(f.policy, { k_field_matmul_gen<A><<<grid, 256, 0, g_stream>>>(f.d, p->t[0].buf->ptr, p->t[1].buf->ptr, m.buf->ptr, X, Y, Z); });
+    }
+    LAUNCH_CHECK();
+    p->aux = m;
+    p->has_aux = true;
+    return SCB_OK;
+}
 extern "C" int scb_poly_triangle_g_new(const scb_field* f, uint32_t num_vars, const uint8_t* adj, scb_poly** out) {
     // triangle-counting/src/lib.rs:32-51
     ARG_TRY(f && adj && out, "null argument");
@@ -955,6 +983,11 @@ extern "C" int scb_poly_triangle_g_new(const scb_field* f, uint32_t num_vars, co
     p->t = {g->t, g->t, g->t};  // f_a_1, f_a_2, f_a_3 are clones of one table (:46-48)
     p->var_len = num_vars / 2;  // :44
     scb_mle_free(g);
+    if (opt(OPT_tri_tiled) != 0) {
+        Ctx* c;
+        RC_TRY(get_ctx(&c));
+        RC_TRY(triangle_build_aux(c, p.get()));
+    }
     *out = p.release();
     return SCB_OK;
 }
@@ -1081,6 +1114,13 @@ extern "C" int scb_poly_fix_variables(const scb_poly* p, const uint64_t* pp, uin
         RC_TRY(fix_table(c, f, p->t[0], pp, n_xy, &q->t[0]));
         RC_TRY(fix_table(c, f, p->t[1], pp + (size_t)(n_yz ? xn : 0) * N, n_yz, &q->t[1]));
         RC_TRY(fix_table(c, f, p->t[2], xz.data(), n_x + n_z, &q->t[2]));
+        // M folds along x like a table; once no x variable is left it is no longer needed
+        q->has_aux = false;
+        q->aux = Table();
+        if (p->has_aux && n < xn) {
+            RC_TRY(fix_table(c, f, p->aux, pp, n, &q->aux));
+            q->has_aux = true;
+        }
     } else {
         // gkr-protocol/src/round_polynomial.rs:59-76
         const uint32_t bn = p->t[2].nv;
@@ -1117,6 +1157,16 @@ static int launch_round_evals(Ctx* c, const scb_poly* p, uint64_t* res) {
     } else if (p->kind == SCB_POLY_TRIANGLE_G) {
         const uint32_t xn = tri_xn(p), yn = tri_yn(p), zn = tri_zn(p);
         const uint64_t n_t = xn > 0 ? 1ull << (xn - 1 + zn) : (yn > 0 ? 1ull << (yn - 1 + zn) : 1ull << (zn - 1));
+        if (p->has_aux && xn > 0) {
+            // x phase in matrix form: the message of the product of the tables M and f3 over adjacent x pairs (tri.cuh)
+            DISPATCH_POLICY(f.policy, {
+                TabsIn<2> in;
+                in.p[0] = p->aux.buf->ptr;
+                in.p[1] = p->t[2].buf->ptr;
+                auto kern = k_round_evals<A, 2, 1>;
+                kern<<<occ_grid(c, kern, n_t), kThreads, 0, g_stream>>>(f.d, in, n_t, c->partials, c->ticket, res, PeerArg{});
+            });
+        } else
         DISPATCH_POLICY(f.policy, {
             k_triangle_round<A><<<grid_for(c, n_t), kThreads, 0, g_stream>>>(f.d, p->t[0].buf->ptr, p->t[1].buf->ptr, p->t[2].buf->ptr, xn, yn, zn,
                                                                             c->partials, c->ticket, res);
@@ -1363,6 +1413,15 @@ extern "C" int scb_poly_sum(const scb_poly* p, uint64_t* out_elem) {
         }));
     } else if (p->kind == SCB_POLY_TRIANGLE_G) {
         const uint32_t xn = tri_xn(p), yn = tri_yn(p), zn = tri_zn(p);
+        if (p->has_aux && xn > 0) {  // c_1 = sum_{x,z} M[z][x] f3[z][x]
+            DISPATCH_POLICY(f.policy, {
+                TabsIn<2> in;
+                in.p[0] = p->aux.buf->ptr;
+                in.p[1] = p->t[2].buf->ptr;
+                const uint64_t n = 1ull << (xn + zn);
+                k_product_sum<A, 2, 1><<<grid_for(c, n), kThreads, 0, g_stream>>>(f.d, in, n, c->partials, c->ticket, c->h_res);
+            });
+        } else
         DISPATCH_POLICY(f.policy, {
             k_triangle_sum<A><<<grid_for(c, 1ull << (xn + zn)), kThreads, 0, g_stream>>>(f.d, p->t[0].buf->ptr, p->t[1].buf->ptr, p->t[2].buf->ptr, xn, yn,
                                                                                         zn, c->partials, c->ticket, c->h_res);
