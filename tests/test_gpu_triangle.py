@@ -28,6 +28,7 @@ def test_matrix_form_equals_per_round_kernels(OF):
         adj = random_graph(n, rnd)
         flat = adj.reshape(-1).astype(bool).tolist()
         outs = []
+        pt = [prnd.randrange(OF.p) for _ in range(3 * bits)]
         for tiled in (1, 0):
             T.set_option("tri_tiled", tiled)
             g = T.TriangleG.new_adj_matrix(F, 2 * bits, flat)
@@ -35,7 +36,6 @@ def test_matrix_form_equals_per_round_kernels(OF):
             c_1 = prover.c_1()
             tr = T.generate_transcript(prover)
             assert T.verify_transcript(tr, T.Verifier(3 * bits, g))
-            pt = [prnd.randrange(OF.p) for _ in range(3 * bits)]
             partial = []
             for k in (1, bits - 1, bits, bits + 1, 2 * bits):
                 if 1 <= k < 3 * bits:
