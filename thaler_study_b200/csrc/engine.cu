@@ -1302,8 +1302,22 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
             in[k] = p->t[k].buf->ptr;
             o[k] = q->t[k].buf->ptr;
         }
-        const cudaError_t le = launch_fold_round_g4((int)K, (int)opt(OPT_bps), c->sms, g_stream, f.d, in, o, elem_arg(f, r), p->t[0].len() / 4, c->partials,
-                                                    c->ticket, c->h_res, peer_arg(c), kMaxGrid);
+        // option g4_kernel: 2 (default) = radix-2^29 lazy-carry arithmetic (g29.cuh) where the modulus allows, 1 = the
+        // 32-bit-limb carry-chain kernel (g4.cuh)
+        const bool use29 = opt(OPT_g4_kernel) >= 2 && g29_supported(f.d);
+        cudaError_t le;
+        if (use29) {
+            Fe rr, r5;
+            f.h.load(r, rr);
+            r5 = f.h.mul(rr, f.h.from_u64(32));  // r * 2^5: the fold's product divides by 2^261 instead of 2^256
+            uint64_t r5w[kMaxLimbs];
+            f.h.store(r5, r5w);
+            le = launch_fold_round_g29((int)K, (int)opt(OPT_bps), c->sms, g_stream, f.d, in, o, elem_arg(f, r5w), p->t[0].len() / 4, c->partials, c->ticket,
+                                       c->h_res, peer_arg(c), kMaxGrid);
+        } else {
+            le = launch_fold_round_g4((int)K, (int)opt(OPT_bps), c->sms, g_stream, f.d, in, o, elem_arg(f, r), p->t[0].len() / 4, c->partials, c->ticket,
+                                      c->h_res, peer_arg(c), kMaxGrid);
+        }
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (le != cudaSuccess) {
             set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(le), __FILE__, __LINE__);
@@ -1313,6 +1327,10 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
         RC_TRY(peers_check(c));
         Fe S[kMaxPts], ev[kMaxPts], cl;
         for (int x = 0; x < g4_n_sums((int)K); ++x) f.h.load(c->h_res + (size_t)x * N, S[x]);
+        if (use29 && K > 1) {  // every product of K factors came back short of 2^(5 (K-1))
+            const Fe fix = f.h.from_u64(1ull << (5 * (K - 1)));
+            for (int x = 0; x < g4_n_sums((int)K); ++x) S[x] = f.h.mul(S[x], fix);
+        }
         f.h.load(claim, cl);
         g4_rebuild_evals(f.h, K, cl, S, ev);
         for (uint32_t x = 0; x < n_points; ++x) f.h.store(ev[x], h_out + (size_t)x * N);

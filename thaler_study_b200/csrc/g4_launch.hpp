@@ -17,4 +17,12 @@ cudaError_t launch_fold_round_g4(int K, int blocks_per_sm_cap, int sms, cudaStre
                                  uint64_t* const* outp, const ElemArg& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res,
                                  const PeerArg& pa, int max_grid);
 
+// Third generation (g29.cuh, lazy29.hpp): the same pass in radix 2^29 with lazy carries -- full-rate IMAD.WIDE, no carry
+// flags.  r5 = r * 2^5 (field product, Montgomery-256 words); the sums come back multiplied by 2^(-5 (K-1)) (the caller
+// multiplies 32^(K-1) back).  g29_supported: moduli of 250..255 bits.
+bool g29_supported(const FieldDesc& f);
+cudaError_t launch_fold_round_g29(int K, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
+                                  uint64_t* const* outp, const ElemArg& r5, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res,
+                                  const PeerArg& pa, int max_grid);
+
 }  // namespace scb

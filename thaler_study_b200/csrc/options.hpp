@@ -32,7 +32,8 @@ namespace scb {
     X(mle_u, 0)                /* MLE evaluation: 1 = one group per thread-iteration */                                     \
     X(mle_fused, 1)            /* MLE evaluation as ONE launch (eq sub-tables built per CTA in shared memory) */            \
     X(gkr_persist, 1)          /* GKR layer phases as one cooperative launch each */                                        \
-    X(g4_kernel, 1)            /* 4-limb fused fold+message: 1 = shared-memory staged two-product kernel, 0 = round 1's */  \
+    X(g4_kernel, 2)            /* 4-limb fused fold+message with a claim: 2 = radix-2^29 lazy carries (g29.cuh), 1 = 32-bit-limb   \
+                                  carry chains (g4.cuh), 0 = round 1's kernel */                                             \
     X(tri_tiled, 1)            /* triangle x-phase as a shared-memory tiled field matmul */                                 \
     X(host_pack, 1)            /* narrowing upload of host tables (upload_engine.inc) */                                    \
     X(host_pack_threads, 0)    /* pack threads; 0: hardware threads / local_ranks */                                        \
