@@ -1183,6 +1183,7 @@ static int launch_round_evals(Ctx* c, const scb_poly* p, uint64_t* res) {
     return SCB_OK;
 }
 
+static void g4_rebuild_evals(const HostField& h, uint32_t K, const Fe& g1, const Fe* S, Fe* ev);
 static int round_evals_impl(const scb_poly* p, uint32_t n_points, uint64_t* h_out, uint64_t* d_out) {
     ARG_TRY(p && (h_out || d_out), "null argument");
     PLAIN_POLY(p);
@@ -1194,6 +1195,32 @@ static int round_evals_impl(const scb_poly* p, uint32_t n_points, uint64_t* h_ou
         if (n_points == poly_n_points(p)) return launch_round_evals(c, p, d_out);
         RC_TRY(launch_round_evals(c, p, c->d_scratch));
         CU_TRY(cudaMemcpyAsync(d_out, c->d_scratch, (size_t)8 * N * n_points, cudaMemcpyDeviceToDevice, g_stream));
+        return SCB_OK;
+    }
+    if ((p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) && p->f->policy == POL_G4 && opt(OPT_g4_kernel) >= 2 && g29_supported(p->f->d) &&
+        p->t[0].nv >= 1) {
+        // 4-limb fields: the message pass in radix-2^29 lazy-carry arithmetic (g29.cuh); sums at 0, inf, 2..K-1, 1
+        const FieldImpl& f = *p->f;
+        const uint32_t K = (uint32_t)p->t.size();
+        const uint64_t* in[kMaxTables];
+        for (uint32_t k = 0; k < K; ++k) in[k] = p->t[k].buf->ptr;
+        const cudaError_t le = launch_round_evals_g29((int)K, (int)opt(OPT_bps), c->sms, g_stream, f.d, in, p->t[0].len() / 2, c->partials, c->ticket, c->h_res,
+                                                      peer_arg(c), kMaxGrid);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (le != cudaSuccess) {
+            set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(le), __FILE__, __LINE__);
+            return SCB_ECUDA;
+        }
+        CU_TRY(cudaStreamSynchronize(g_stream));
+        RC_TRY(peers_check(c));
+        Fe S[kMaxPts + 1], ev[kMaxPts + 1];
+        for (uint32_t x = 0; x <= K; ++x) f.h.load(c->h_res + (size_t)x * N, S[x]);
+        if (K > 1) {
+            const Fe fix = f.h.from_u64(1ull << (5 * (K - 1)));
+            for (uint32_t x = 0; x <= K; ++x) S[x] = f.h.mul(S[x], fix);
+        }
+        g4_rebuild_evals(f.h, K, S[K], S, ev);
+        for (uint32_t x = 0; x < n_points; ++x) f.h.store(ev[x], h_out + (size_t)x * N);
         return SCB_OK;
     }
     RC_TRY(launch_round_evals(c, p, c->h_res));
@@ -1256,9 +1283,9 @@ extern "C" int scb_poly_allow_packed(scb_poly* p, int enable) {
 // S_x = g(x) for x = 2..K-1; with the claim g(0) + g(1) the message values g(0..K) follow by exact field arithmetic:
 // g(1) = claim - g(0) and, from the K-th finite difference  sum_i (-1)^(K-i) C(K,i) g(i) = K! * lead,
 // g(K) = K! * lead - sum_{i<K} (-1)^(K-i) C(K,i) g(i).  Same field elements as summing every point.
-static void g4_rebuild_evals(const HostField& h, uint32_t K, const Fe& claim, const Fe* S, Fe* ev) {
+static void g4_rebuild_evals(const HostField& h, uint32_t K, const Fe& g1, const Fe* S, Fe* ev) {
     ev[0] = S[0];
-    ev[1] = h.sub(claim, S[0]);
+    ev[1] = g1;  // claim - g(0), or summed directly when no claim exists yet (round 0)
     if (K == 1) return;
     for (uint32_t x = 2; x < K; ++x) ev[x] = S[x];
     Fe fact = h.one(), acc = h.zero();
@@ -1312,10 +1339,10 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
             r5 = f.h.mul(rr, f.h.from_u64(32));  // r * 2^5: the fold's product divides by 2^261 instead of 2^256
             uint64_t r5w[kMaxLimbs];
             f.h.store(r5, r5w);
-            le = launch_fold_round_g29((int)K, (int)opt(OPT_bps), c->sms, g_stream, f.d, in, o, elem_arg(f, r5w), p->t[0].len() / 4, c->partials, c->ticket,
+            le = launch_fold_round_g29((int)K, (int)opt(OPT_g4_blocks), (int)opt(OPT_bps), c->sms, g_stream, f.d, in, o, elem_arg(f, r5w), p->t[0].len() / 4, c->partials, c->ticket,
                                        c->h_res, peer_arg(c), kMaxGrid);
         } else {
-            le = launch_fold_round_g4((int)K, (int)opt(OPT_bps), c->sms, g_stream, f.d, in, o, elem_arg(f, r), p->t[0].len() / 4, c->partials, c->ticket,
+            le = launch_fold_round_g4((int)K, (int)opt(OPT_g4_blocks), (int)opt(OPT_bps), c->sms, g_stream, f.d, in, o, elem_arg(f, r), p->t[0].len() / 4, c->partials, c->ticket,
                                       c->h_res, peer_arg(c), kMaxGrid);
         }
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1332,7 +1359,7 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
             for (int x = 0; x < g4_n_sums((int)K); ++x) S[x] = f.h.mul(S[x], fix);
         }
         f.h.load(claim, cl);
-        g4_rebuild_evals(f.h, K, cl, S, ev);
+        g4_rebuild_evals(f.h, K, f.h.sub(cl, S[0]), S, ev);
         for (uint32_t x = 0; x < n_points; ++x) f.h.store(ev[x], h_out + (size_t)x * N);
         *out = q.release();
         return SCB_OK;

@@ -66,8 +66,8 @@ __device__ __forceinline__ g4::W8 canonical(const g4::Arith& ar, const L9& x) {
     return ar.reduce_once(c.w, 0);
 }
 
-template <int K>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int K, int MINB = 2>
+__global__ void __launch_bounds__(kThreads, MINB)
     k_fold_round_g29(FieldDesc f, Desc29x dx, TabsIn<K> in, TabsOut<K> outp, ElemArg r5arg, uint64_t n_quads, uint64_t* partials, unsigned int* ticket,
                      uint64_t* out, PeerArg peer) {
     constexpr int NS = g4::n_sums(K);
@@ -125,6 +125,86 @@ __global__ void __launch_bounds__(kThreads, 2)
         }
     }
     // lazy sums -> canonical elements:  V = lo9 + h 2^261  =>  V mod p = mont(lo9, 2^261) + mont(h, 2^522)
+    const PolGN<4> A(f);
+    typename PolGN<4>::Acc fin[NS];
+    L9 c1, c2;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        c1.l[j] = dx.c1[j];
+        c2.l[j] = dx.c2[j];
+    }
+#pragma unroll
+    for (int x = 0; x < NS; ++x) {
+        acc_carry(acc[x]);
+        L9 lo, hi;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            lo.l[j] = acc[x].l[j];
+            hi.l[j] = 0;
+        }
+        hi.l[0] = acc[x].l[9] & l29::M29;
+        hi.l[1] = acc[x].l[9] >> 29;
+        const g4::W8 a = canonical(ar, l29::mont(d, lo, c1));
+        const g4::W8 b = canonical(ar, l29::mont(d, hi, c2));
+        const g4::W8 s = ar.add(a, b);
+        uint64_t l[4];
+        g4::store8(s, l);
+        fin[x] = A.from_words(l);
+    }
+    grid_reduce_finish<PolGN<4>, NS>(A, fin, partials, ticket, out, 0, &peer);
+}
+
+// Round-0 message (Prover::new's pass; sum-check-protocol/src/lib.rs:88-97 with G::to_univariate,
+// matrix-multiplication/src/lib.rs:110-122, generalised to K tables): no claim is known yet, so X = 1 is summed as well.
+// One hypercube pair of every table per thread-iteration; sums at the points 0, inf, 2 .. K-1 and, last, 1 -- K + 1
+// values, each short of 2^(5 (K-1)) like k_fold_round_g29's.
+template <int K>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_round_evals_g29(FieldDesc f, Desc29x dx, TabsIn<K> in, uint64_t n_pairs, uint64_t* partials, unsigned int* ticket, uint64_t* out, PeerArg peer) {
+    constexpr int NS = g4::n_sums(K) + 1;  // + the point X = 1
+    const g4::Arith ar(f);
+    const Desc29& d = dx.d;
+    A10 acc[NS];
+#pragma unroll
+    for (int x = 0; x < NS; ++x) acc_zero(acc[x]);
+    uint32_t since_carry = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += stride) {
+        L9 prod[NS];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            uint64_t w[8];
+            ld_words<8>(in.p[k] + i * 8, w);
+            const L9 lo = limbs_of(w), hi = limbs_of(w + 4);
+            L9 fac[NS];
+            fac[0] = lo;
+            fac[NS - 1] = hi;
+            if constexpr (K >= 2) {
+                fac[1] = l29::sub_kp(d, hi, lo);
+#pragma unroll
+                for (int x = 2; x < NS - 1; ++x) {
+                    fac[x] = l29::add(x == 2 ? hi : fac[x - 1], fac[1]);
+                    if (x >= 3) fac[x] = l29::normalise(fac[x]);
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < NS; ++x) {
+                const bool plain = x == 0 || x == NS - 1 || x >= 3;  // already normalised
+                if (k == 0 && K > 1) {
+                    prod[x] = plain ? fac[x] : l29::normalise(fac[x]);
+                } else if (k < K - 1) {
+                    prod[x] = l29::mont(d, prod[x], fac[x]);
+                } else {
+                    acc_add(acc[x], K == 1 ? fac[x] : l29::mont(d, prod[x], fac[x]));
+                }
+            }
+        }
+        if (++since_carry == 4) {
+            since_carry = 0;
+#pragma unroll
+            for (int x = 0; x < NS; ++x) acc_carry(acc[x]);
+        }
+    }
     const PolGN<4> A(f);
     typename PolGN<4>::Acc fin[NS];
     L9 c1, c2;

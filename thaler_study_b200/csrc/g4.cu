@@ -8,10 +8,10 @@
 
 namespace scb {
 
-template <int K>
+template <int K, int MINB>
 static cudaError_t launch_k(int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in, uint64_t* const* outp,
                             const ElemArg& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid) {
-    auto kern = g4::k_fold_round_g4<K>;
+    auto kern = g4::k_fold_round_g4<K, MINB>;
     static int nb_cached = 0;
     if (nb_cached == 0) {
         int nb = 0;
@@ -34,11 +34,11 @@ static cudaError_t launch_k(int blocks_per_sm_cap, int sms, cudaStream_t stream,
     return cudaGetLastError();
 }
 
-template <int K>
+template <int K, int MINB>
 static cudaError_t launch_k29(int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const g29::Desc29x& dx, const uint64_t* const* in,
                               uint64_t* const* outp, const ElemArg& r5, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res,
                               const PeerArg& pa, int max_grid) {
-    auto kern = g29::k_fold_round_g29<K>;
+    auto kern = g29::k_fold_round_g29<K, MINB>;
     static int nb_cached = 0;
     if (nb_cached == 0) {
         int nb = 0;
@@ -94,12 +94,47 @@ static void pow2_mod_limbs(const FieldDesc& f, int e, uint32_t (&out)[9]) {
     for (int j = 0; j < 9; ++j) out[j] = r.l[j];
 }
 
+template <int K>
+static cudaError_t launch_r29(int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const g29::Desc29x& dx, const uint64_t* const* in,
+                              uint64_t n_pairs, uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid) {
+    auto kern = g29::k_round_evals_g29<K>;
+    static int nb_cached = 0;
+    if (nb_cached == 0) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, 0) != cudaSuccess || nb < 1) nb = 1;
+        nb_cached = nb;
+    }
+    int nb = nb_cached;
+    if (blocks_per_sm_cap > 0 && blocks_per_sm_cap < nb) nb = blocks_per_sm_cap;
+    uint64_t want = (n_pairs + kThreads - 1) / kThreads, cap = (uint64_t)sms * nb;
+    if (cap > (uint64_t)max_grid) cap = max_grid;
+    if (want < 1) want = 1;
+    TabsIn<K> ti;
+    for (int k = 0; k < K; ++k) ti.p[k] = in[k];
+    kern<<<(int)(want < cap ? want : cap), kThreads, 0, stream>>>(f, dx, ti, n_pairs, partials, ticket, res, pa);
+    return cudaGetLastError();
+}
+cudaError_t launch_round_evals_g29(int K, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in, uint64_t n_pairs,
+                                   uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid) {
+    g29::Desc29x dx;
+    if (!l29::make_desc(f.p, f.bits, &dx.d)) return cudaErrorInvalidValue;
+    pow2_mod_limbs(f, 261, dx.c1);
+    pow2_mod_limbs(f, 522, dx.c2);
+    switch (K) {
+        case 1: return launch_r29<1>(blocks_per_sm_cap, sms, stream, f, dx, in, n_pairs, partials, ticket, res, pa, max_grid);
+        case 2: return launch_r29<2>(blocks_per_sm_cap, sms, stream, f, dx, in, n_pairs, partials, ticket, res, pa, max_grid);
+        case 3: return launch_r29<3>(blocks_per_sm_cap, sms, stream, f, dx, in, n_pairs, partials, ticket, res, pa, max_grid);
+        case 4: return launch_r29<4>(blocks_per_sm_cap, sms, stream, f, dx, in, n_pairs, partials, ticket, res, pa, max_grid);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 bool g29_supported(const FieldDesc& f) {
     l29::Desc29 d;
     return f.n == 4 && l29::make_desc(f.p, f.bits, &d);
 }
 
-cudaError_t launch_fold_round_g29(int K, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
+cudaError_t launch_fold_round_g29(int K, int minb, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
                                   uint64_t* const* outp, const ElemArg& r5, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res,
                                   const PeerArg& pa, int max_grid) {
     g29::Desc29x dx;
@@ -107,22 +142,22 @@ cudaError_t launch_fold_round_g29(int K, int blocks_per_sm_cap, int sms, cudaStr
     pow2_mod_limbs(f, 261, dx.c1);
     pow2_mod_limbs(f, 522, dx.c2);
     switch (K) {
-        case 1: return launch_k29<1>(blocks_per_sm_cap, sms, stream, f, dx, in, outp, r5, n_quads, partials, ticket, res, pa, max_grid);
-        case 2: return launch_k29<2>(blocks_per_sm_cap, sms, stream, f, dx, in, outp, r5, n_quads, partials, ticket, res, pa, max_grid);
-        case 3: return launch_k29<3>(blocks_per_sm_cap, sms, stream, f, dx, in, outp, r5, n_quads, partials, ticket, res, pa, max_grid);
-        case 4: return launch_k29<4>(blocks_per_sm_cap, sms, stream, f, dx, in, outp, r5, n_quads, partials, ticket, res, pa, max_grid);
+        case 1: return minb >= 3 ? launch_k29<1, 3>(blocks_per_sm_cap, sms, stream, f, dx, in, outp, r5, n_quads, partials, ticket, res, pa, max_grid) : launch_k29<1, 2>(blocks_per_sm_cap, sms, stream, f, dx, in, outp, r5, n_quads, partials, ticket, res, pa, max_grid);
+        case 2: return minb >= 3 ? launch_k29<2, 3>(blocks_per_sm_cap, sms, stream, f, dx, in, outp, r5, n_quads, partials, ticket, res, pa, max_grid) : launch_k29<2, 2>(blocks_per_sm_cap, sms, stream, f, dx, in, outp, r5, n_quads, partials, ticket, res, pa, max_grid);
+        case 3: return minb >= 3 ? launch_k29<3, 3>(blocks_per_sm_cap, sms, stream, f, dx, in, outp, r5, n_quads, partials, ticket, res, pa, max_grid) : launch_k29<3, 2>(blocks_per_sm_cap, sms, stream, f, dx, in, outp, r5, n_quads, partials, ticket, res, pa, max_grid);
+        case 4: return minb >= 3 ? launch_k29<4, 3>(blocks_per_sm_cap, sms, stream, f, dx, in, outp, r5, n_quads, partials, ticket, res, pa, max_grid) : launch_k29<4, 2>(blocks_per_sm_cap, sms, stream, f, dx, in, outp, r5, n_quads, partials, ticket, res, pa, max_grid);
         default: return cudaErrorInvalidValue;
     }
 }
 
-cudaError_t launch_fold_round_g4(int K, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
+cudaError_t launch_fold_round_g4(int K, int minb, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
                                  uint64_t* const* outp, const ElemArg& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res,
                                  const PeerArg& pa, int max_grid) {
     switch (K) {
-        case 1: return launch_k<1>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid);
-        case 2: return launch_k<2>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid);
-        case 3: return launch_k<3>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid);
-        case 4: return launch_k<4>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid);
+        case 1: return minb >= 3 ? launch_k<1, 3>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid) : launch_k<1, 2>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid);
+        case 2: return minb >= 3 ? launch_k<2, 3>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid) : launch_k<2, 2>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid);
+        case 3: return minb >= 3 ? launch_k<3, 3>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid) : launch_k<3, 2>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid);
+        case 4: return minb >= 3 ? launch_k<4, 3>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid) : launch_k<4, 2>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid);
         default: return cudaErrorInvalidValue;
     }
 }

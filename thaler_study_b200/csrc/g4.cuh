@@ -205,8 +205,8 @@ __host__ __device__ constexpr int n_sums(int K) { return K; }
 
 // One thread-iteration handles 4 adjacent entries of every table (a "quad"): two folded entries per table = one
 // hypercube pair of the next round.  Sums are written as n_sums(K) canonical elements (order: S_0, S_inf, S_2, ...).
-template <int K>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int K, int MINB = 2>
+__global__ void __launch_bounds__(kThreads, MINB)
     k_fold_round_g4(FieldDesc f, TabsIn<K> in, TabsOut<K> outp, ElemArg rarg, uint64_t n_quads, uint64_t* partials, unsigned int* ticket,
                     uint64_t* out, PeerArg peer) {
     constexpr int NS = n_sums(K);

@@ -12,8 +12,9 @@ namespace scb {
 inline int g4_n_sums(int K) { return K; }
 // Launches k_fold_round_g4<K>: folds variable 0 of the K tables by r (outp: K tables of 2 * n_quads elements) and
 // accumulates the sums of the folded tables' round message.  res: g4_n_sums(K) canonical elements (mapped host or
-// device memory).  One resident wave of CTAs (occupancy calculator, optionally capped).
-cudaError_t launch_fold_round_g4(int K, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
+// device memory).  One resident wave of CTAs (occupancy calculator, optionally capped).  minb: the kernel variant compiled
+// for that many resident CTAs per SM (2: 128 registers per thread; 3: 80, with a few spills to local memory).
+cudaError_t launch_fold_round_g4(int K, int minb, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
                                  uint64_t* const* outp, const ElemArg& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res,
                                  const PeerArg& pa, int max_grid);
 
@@ -21,8 +22,13 @@ cudaError_t launch_fold_round_g4(int K, int blocks_per_sm_cap, int sms, cudaStre
 // flags.  r5 = r * 2^5 (field product, Montgomery-256 words); the sums come back multiplied by 2^(-5 (K-1)) (the caller
 // multiplies 32^(K-1) back).  g29_supported: moduli of 250..255 bits.
 bool g29_supported(const FieldDesc& f);
-cudaError_t launch_fold_round_g29(int K, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
+cudaError_t launch_fold_round_g29(int K, int minb, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
                                   uint64_t* const* outp, const ElemArg& r5, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res,
                                   const PeerArg& pa, int max_grid);
+
+// Round-0 message in the same arithmetic (k_round_evals_g29): res receives K + 1 sums in the order S_0, S_inf, S_2 ..
+// S_{K-1}, S_1, each short of 2^(5 (K-1)).
+cudaError_t launch_round_evals_g29(int K, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in, uint64_t n_pairs,
+                                   uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid);
 
 }  // namespace scb

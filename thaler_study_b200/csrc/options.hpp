@@ -34,6 +34,7 @@ namespace scb {
     X(gkr_persist, 1)          /* GKR layer phases as one cooperative launch each */                                        \
     X(g4_kernel, 2)            /* 4-limb fused fold+message with a claim: 2 = radix-2^29 lazy carries (g29.cuh), 1 = 32-bit-limb   \
                                   carry chains (g4.cuh), 0 = round 1's kernel */                                             \
+    X(g4_blocks, 2)            /* 4-limb kernels: variant compiled for 2 or 3 resident CTAs per SM */                       \
     X(tri_tiled, 1)            /* triangle x-phase as a shared-memory tiled field matmul */                                 \
     X(host_pack, 1)            /* narrowing upload of host tables (upload_engine.inc) */                                    \
     X(host_pack_threads, 0)    /* pack threads; 0: hardware threads / local_ranks */                                        \
