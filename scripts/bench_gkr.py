@@ -11,6 +11,8 @@ import torch
 import thaler_study_b200 as T
 from thaler_study_b200.gkr import Circuit, GkrProver, GkrVerifier
 
+T.options_from_env()  # harness opt-in: SCB_<OPTION>=n -> scb_set_option
+
 ap = argparse.ArgumentParser()
 ap.add_argument("--width-bits", type=int, default=20)
 ap.add_argument("--depth", type=int, default=16)

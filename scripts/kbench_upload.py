@@ -1,5 +1,6 @@
-"""Sweep of the packed upload's switches on one GPU: time scb_poly_product_from_host alone (three pinned 2^v-entry host
-tables -> packed handle), per chunk size / pack threads / lanes / store kind.  Prints one JSON line per setting."""
+"""Sweep of the narrowing upload's switches on one GPU: time scb_poly_product_from_host alone (three pinned 2^v-entry
+host tables -> packed handle) per raw-lane depth / chunk size / pack threads / store kind, through scb_set_option (the
+library reads no environment).  Prints one JSON line per setting."""
 import ctypes as C
 import json
 import os
@@ -29,12 +30,10 @@ torch.cuda.synchronize()
 ref = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, 900 + k) for k in range(K)]).round_evals()
 
 
-def run(tag, reps=3, **env):
-    keys = ["SCB_HOST_PACK", "SCB_HOST_PACK_THREADS", "SCB_HOST_PACK_CHUNK_LOG2", "SCB_HOST_PACK_RAW", "SCB_HOST_PACK_NT", "SCB_HOST_PACK_WIRE"]
-    for k_ in keys:
-        os.environ.pop(k_, None)
-    for k_, val in env.items():
-        os.environ[k_] = str(val)
+def run(tag, reps=3, **opts):
+    T.reset_options()
+    for k_, val in opts.items():
+        T.set_option(k_, val)
     ts = []
     for i in range(reps + 1):
         t0 = time.perf_counter()
@@ -45,17 +44,20 @@ def run(tag, reps=3, **env):
         del g
     a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
     check(lib.scb_host_pack_stats(C.byref(a), C.byref(b), C.byref(c)))
-    print(json.dumps({"tag": tag, **env, "ms_min": round(min(ts[1:]), 2), "ms_all": [round(t, 1) for t in ts[1:]],
+    print(json.dumps({"tag": tag, **opts, "ms_min": round(min(ts[1:]), 2), "ms_all": [round(t, 1) for t in ts[1:]],
                       "chunks_host": a.value, "chunks_device": b.value, "h2d_GB": round(c.value / 1e9, 3)}), flush=True)
 
 
-run("plain", SCB_HOST_PACK=0)
+run("plain", host_pack=0)
 run("defaults")
-for wire in (21, 32):
-    for nt in (1, 0):
-        for cl in (19, 20, 21, 22):
-            for th in (8, 12, 16):
-                run("sweep", SCB_HOST_PACK_WIRE=wire, SCB_HOST_PACK_CHUNK_LOG2=cl, SCB_HOST_PACK_THREADS=th, SCB_HOST_PACK_NT=nt)
-for wire in (21, 32):
-    for cl in (20, 21):
-        run("host lane only", SCB_HOST_PACK_WIRE=wire, SCB_HOST_PACK_CHUNK_LOG2=cl, SCB_HOST_PACK_RAW=0)
+for slots in (1, 2, 4, 6, 8):
+    run("raw lane depth", host_pack_raw_slots=slots)
+for slots in (4, 8):
+    for cl in (19, 21):
+        run("raw depth x chunk", host_pack_raw_slots=slots, host_pack_chunk_log2=cl)
+for th in (8, 12, 14):
+    run("threads", host_pack_threads=th, host_pack_raw_slots=6)
+run("nt stores", host_pack_nt=1, host_pack_raw_slots=6)
+run("wire32", host_pack_wire=32, host_pack_raw_slots=6)
+run("host lane only", host_pack_raw=0)
+T.reset_options()

@@ -186,6 +186,70 @@ __global__ void __launch_bounds__(kThreads) k_pqs_fold_round(FieldDesc f, const 
     grid_reduce_finish<A, 3>(ar, acc, partials, ticket, out);
 }
 
+// ---- R rounds per pass, challenges known up front (scb_gkr_prover_prove_layer) ----
+// A layer's challenges are public coins: they do not depend on the prover's messages, so when they are handed over up
+// front nothing but the DATA dependency orders the rounds -- and a block of 2^R consecutive entries of a table is closed
+// under R rounds of pairing and folding.  One thread-iteration loads such a block of P, Q and S, accumulates message t
+// from its 2^(R-1) pairs, folds by challenge t, accumulates message t+1 from the 2^(R-2) folded pairs, ... and stores
+// ONE entry per table: R messages (3 R sums) per pass over the tables instead of one, no barrier between them, and the
+// table shrinks by 2^R per launch.  A k-round phase is ceil(k / R) ordinary launches (R = 4: five for k = 20) instead of
+// k grid-wide barriers of ~8 us each.  Same sums, same field elements (gkr-protocol/src/round_polynomial.rs:59-90).
+template <class A, int R>
+__global__ void __launch_bounds__(kThreads) k_pqs_multi(FieldDesc f, const uint64_t* __restrict__ P, const uint64_t* __restrict__ Q,
+                                                        const uint64_t* __restrict__ S, uint64_t* __restrict__ Po, uint64_t* __restrict__ Qo,
+                                                        uint64_t* __restrict__ So, const uint64_t* __restrict__ challenges, uint64_t n_blocks,
+                                                        uint64_t* partials, unsigned int* ticket, uint64_t* out) {
+    constexpr int N = A::N, B = 1 << R;
+    const A ar(f);
+    typename A::El r[R];
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+        uint64_t rw[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) rw[i] = __ldg(challenges + (size_t)s * N + i);
+        r[s] = ar.from_words(rw);
+    }
+    typename A::Acc acc[3 * R];
+#pragma unroll
+    for (int x = 0; x < 3 * R; ++x) ar.acc_zero(acc[x]);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_blocks; i += stride) {
+        typename A::El v[3][B];
+        const uint64_t* in[3] = {P, Q, S};
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int e = 0; e < B; ++e) v[k][e] = ld_el(ar, in[k], i * B + e);
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            const int pairs = B >> (s + 1);
+            typename A::Acc a3[3] = {acc[3 * s], acc[3 * s + 1], acc[3 * s + 2]};
+#pragma unroll
+            for (int j = 0; j < pairs; ++j) {
+                const typename A::El pp[2] = {v[0][2 * j], v[0][2 * j + 1]};
+                const typename A::El qq[2] = {v[1][2 * j], v[1][2 * j + 1]};
+                const typename A::El ss[2] = {v[2][2 * j], v[2][2 * j + 1]};
+                pqs_accumulate(ar, pp, qq, ss, a3);
+            }
+            acc[3 * s] = a3[0];
+            acc[3 * s + 1] = a3[1];
+            acc[3 * s + 2] = a3[2];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int j = 0; j < pairs; ++j) v[k][j] = ar.fold(v[k][2 * j], v[k][2 * j + 1], r[s]);
+        }
+        uint64_t* outp[3] = {Po, Qo, So};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            uint64_t o[N];
+            ar.to_words(v[k][0], o);
+            st_words<N>(outp[k] + i * N, o);
+        }
+    }
+    grid_reduce_finish<A, 3 * R>(ar, acc, partials, ticket, out);
+}
+
 // ---- all rounds of one P*Q + S sum-check in one cooperative launch, challenges known up front ----
 // Round 0 is the message of the tables as they are; round t >= 1 folds by challenges[t-1] and accumulates the next
 // message (the bodies of k_pqs_round / k_pqs_fold_round).  The CTAs meet at a ticket/flag barrier in device memory

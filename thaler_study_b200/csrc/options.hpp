@@ -31,6 +31,7 @@ namespace scb {
     X(mle_lb, 0)               /* MLE evaluation: index bits of the low (shared-memory) eq table; 0: default */             \
     X(mle_u, 0)                /* MLE evaluation: 1 = one group per thread-iteration */                                     \
     X(mle_fused, 1)            /* MLE evaluation as ONE launch (eq sub-tables built per CTA in shared memory) */            \
+    X(gkr_multi, 1)            /* GKR layer with challenges up front: up to 4 rounds per pass, no barriers (k_pqs_multi) */  \
     X(gkr_persist, 1)          /* GKR layer phases as one cooperative launch each */                                        \
     X(g4_kernel, 1)            /* 4-limb fused fold+message with a claim: 1 = 32-bit-limb carry chains, one point fewer (g4.cuh:    \
                                   measured best, 14.7 ms per 2^28 x 3 launch); 2 = radix-2^29 lazy carries (g29.cuh: 20.8 ms);   \
@@ -42,6 +43,7 @@ namespace scb {
     X(host_pack_min_vars, 22)  /* narrowing upload from 2^n entries */                                                      \
     X(host_pack_chunk_log2, 20)                                                                                             \
     X(host_pack_raw, 1)        /* device-side narrowing lane; 2: also from pageable memory (tests) */                       \
+    X(host_pack_raw_slots, 3)  /* chunks the device-side lane keeps in flight (1..8) */                                     \
     X(host_pack_wire, 21)      /* 21: three 21-bit entries per 64-bit word when p < 2^21; 32: uint32 */                     \
     X(host_pack_nt, 0)         /* streaming stores into the staging buffers */                                              \
     X(local_ranks, 1)          /* processes sharing this box's host cores (set by the sharded driver) */                    \
