@@ -523,13 +523,19 @@ def run_ours(args):
         # upload (profiles/r01_upload_ab.md; SCB_BENCH_E2E_UPLOAD=1 selects it anyway).
         one_call = (world == 1 or os.environ.get("SCB_BENCH_E2E_UPLOAD", "0") == "1") and os.environ.get("SCB_BENCH_E2E_PLAIN", "0") == "0"
 
+        split = {"upload_ms": 0.0, "prove_ms": 0.0}  # host clock of the last step's two parts (both block until done)
+
         def e2e_step(tables):
+            t0 = time.perf_counter()
             if one_call:
                 gg = T.ProductMLE.from_host_tables(F, v, tables)
             else:
                 hs = [T.DenseMultilinearExtension.from_evaluations_vec(F, v, h) for h in tables]  # cudaMemcpy H2D
                 gg = T.ProductMLE.new(hs)
-            return prove(gg), gg  # messages come back device -> host every round
+            t1 = time.perf_counter()
+            tr = prove(gg)  # messages come back device -> host every round
+            split["upload_ms"], split["prove_ms"] = (t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3
+            return tr, gg
 
         def time_e2e(tables, n_steps):
             e2e_step(tables)
@@ -571,7 +577,7 @@ def run_ours(args):
                           "chunks_narrowed_on_device": rc_.value,
                           "host_lane_wire_format": "three 21-bit entries per 64-bit word" if wire21 else "uint32",
                           "host_pack_threads_per_rank": min(32, T.get_option("host_pack_threads") or max(1, host_threads() // world))}
-        e2e = {"value": total_entries / (ems * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ems, "verified": e2e_ok,
+        e2e = {"value": total_entries / (ems * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ems, "verified": e2e_ok, "last_step_split_rank0": dict(split),
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": rounds * (K + 1) * E * n_gpus, "note": note}
         if upload:
             e2e["upload"] = upload

@@ -110,6 +110,53 @@ __device__ __forceinline__ void peer_exchange_sum(const A& ar, const PeerArg& pe
     }
 }
 
+// The same exchange done by a whole WARP (all 32 lanes of one warp call it with the rank's NP * N canonical words in
+// shared memory `v`; the totals are left there): the world * NP * N remote stores go out in parallel instead of one
+// after the other from a single thread (128 dependent-issue stores for 8 ranks x 16 grid sums were ~6 us of the ~12 us a
+// sharded pass spent exchanging), lane g raises / polls rank g's flag, lane x adds element x of every peer's row.
+template <class A, int NP>
+__device__ __forceinline__ void peer_exchange_warp(const A& ar, const PeerArg& peer, uint64_t* v) {
+    constexpr int N = A::N, W = NP * N;
+    static_assert(W <= 32 && NP <= 32, "one lane per word / per element");
+    const int lane = threadIdx.x & 31;
+    const int slot = (int)(peer.seq & 1);
+    for (uint32_t idx = lane; idx < peer.world * W; idx += 32) {
+        const uint32_t g = idx / W, i = idx % W;
+        st_sys(peer.win[g] + (slot * kMaxRanks + peer.rank) * kWinSumStride + i, v[i]);
+    }
+    __threadfence_system();
+    __syncwarp();
+    uint64_t* me = peer.win[peer.rank];
+    if ((uint32_t)lane < peer.world) {
+        st_sys(peer.win[lane] + kWinFlags + slot * kMaxRanks + peer.rank, peer.seq);
+        const uint64_t t0 = globaltimer_ns();
+        while (ld_sys(me + kWinFlags + slot * kMaxRanks + lane) != peer.seq) {
+            if (globaltimer_ns() - t0 > peer.timeout_ns) {
+                st_sys(peer.status, 1);
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane < NP) {
+        uint64_t a[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) a[i] = v[lane * N + i];
+        for (uint32_t g = 0; g < peer.world; ++g) {
+            if (g == peer.rank) continue;
+            const uint64_t* src = me + (slot * kMaxRanks + g) * kWinSumStride + lane * N;
+            uint64_t o[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) o[i] = ld_sys(src + i);
+            ar.to_words(ar.add(ar.from_words(a), ar.from_words(o)), a);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[lane * N + i] = a[i];
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------
 // block-wide reduction of NP accumulators; result valid in thread 0
 // ------------------------------------------------------------------------------------------
@@ -209,6 +256,26 @@ __device__ __forceinline__ void grid_reduce_finish(const A& ar, typename A::Acc 
         }
     }
     block_reduce<A, NP>(ar, acc, sm);
+    if constexpr (NP * A::N <= 32) {
+        if (peer != nullptr && peer->world > 1) {  // sharded: warp 0 exchanges the sums with the peer GPUs (CTA-uniform branch)
+            __syncthreads();  // sm is free again
+            if (threadIdx.x == 0) {
+#pragma unroll
+                for (int x = 0; x < NP; ++x) ar.to_words(ar.msg_final(acc[x], msg_k), sm + x * A::N);
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                peer_exchange_warp<A, NP>(ar, *peer, sm);
+                if (threadIdx.x < NP * A::N) out[threadIdx.x] = sm[threadIdx.x];
+                __syncwarp();
+                if (threadIdx.x == 0) {
+                    *ticket = 0;
+                    __threadfence_system();
+                }
+            }
+            return;
+        }
+    }
     if (threadIdx.x == 0) {
         uint64_t w[NP][A::N];
 #pragma unroll

@@ -702,17 +702,13 @@ __global__ void __launch_bounds__(kThreads, (K <= 2 ? 3 : 2))
                 }
                 if (peer.world > 1) {  // sharded prover: add the peer GPUs' sums of this pass (NVLink peer windows)
                     __syncthreads();
-                    if (threadIdx.x == 0) {
-                        uint64_t w[NG][1];
-#pragma unroll
-                        for (int i = 0; i < NG; ++i) w[i][0] = sm[NG + i];
+                    if (threadIdx.x < 32) {  // warp 0: stores to all peers in parallel, lane g polls rank g, lane i adds sum i
                         PeerArg pa = peer;
                         pa.seq += t;
-                        peer_exchange_sum<A, NG>(ar, pa, w);
-#pragma unroll
-                        for (int i = 0; i < NG; ++i)
-                            if (i < n_out) st_sys(&mb->evals[i], hi | w[i][0]);
+                        peer_exchange_warp<A, NG>(ar, pa, sm + NG);
+                        if ((int)threadIdx.x < n_out) st_sys(&mb->evals[threadIdx.x], hi | sm[NG + threadIdx.x]);
                     }
+                    __syncthreads();
                 }
             }
             if (finisher && threadIdx.x == 0) {
