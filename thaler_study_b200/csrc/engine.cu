@@ -747,7 +747,9 @@ static int eval_table_multi(Ctx* c, const FieldImpl& f, const Table& t, const ui
             constexpr int KTC = A::N == 1 ? 8 : 2;
             auto kern = k_mle_dot_multi<A, KTC>;
             RC_TRY(allow_smem(kern, ((size_t)KTC * 8 * N) << lb));
-            kern<<<grid_for(c, n), kThreads, smem, g_stream>>>(f.d, t.buf->ptr, lo->ptr + (((size_t)t0 << lb) * N), hi->ptr + (((size_t)t0 << (v - lb)) * N),
+            // every CTA first stages the low tables (up to 64 KB): few CTAs with long loops, so that the staging is amortised
+            // (a grid of 8 CTAs per SM spent 64 us per pass over an 8 MB table, the staging being 9x the table data per CTA)
+            kern<<<grid_for(c, n / 16, 1), kThreads, smem, g_stream>>>(f.d, t.buf->ptr, lo->ptr + (((size_t)t0 << lb) * N), hi->ptr + (((size_t)t0 << (v - lb)) * N),
                                                               lb, v, np, n, c->partials, c->ticket, d_out + (size_t)t0 * N);
         });
         LAUNCH_CHECK();

@@ -217,9 +217,20 @@ __global__ void __launch_bounds__(kThreads) k_pqs_multi(FieldDesc f, const uint6
         typename A::El v[3][B];
         const uint64_t* in[3] = {P, Q, S};
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < 3; ++k) {
+            if constexpr (N == 1 && B >= 4) {  // 256-bit loads: a thread's block is contiguous (8-byte loads would re-fetch each sector)
 #pragma unroll
-            for (int e = 0; e < B; ++e) v[k][e] = ld_el(ar, in[k], i * B + e);
+                for (int e = 0; e < B; e += 4) {
+                    uint64_t w[4];
+                    ld_words<4>(in[k] + (i * B + e), w);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[k][e + q] = ar.from_words(&w[q]);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < B; ++e) v[k][e] = ld_el(ar, in[k], i * B + e);
+            }
+        }
 #pragma unroll
         for (int s = 0; s < R; ++s) {
             const int pairs = B >> (s + 1);

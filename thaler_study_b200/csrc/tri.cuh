@@ -26,16 +26,16 @@ constexpr int kMmTile = 64;   // outputs per CTA: kMmTile (z) x kMmTile (x)
 constexpr int kMmK = 32;      // y values per shared-memory step
 
 // M[z][x] = sum_y B[z][y] * A[y][x];  A: Y x X (f1), B: Z x Y (f2), M: Z x X.  Dimensions are powers of two.
-// grid = (ceil(X/64), ceil(Z/64)); 256 threads, each a 4 x 4 block of outputs (strided by 16 for conflict-free
-// shared-memory reads).  Tiles smaller than 64 (small tables) are handled by bounds checks.
+// grid = (ceil(X/64), ceil(Z/64)); 256 threads, each a 4 x 4 block of outputs: four adjacent x (one 128-bit
+// shared-memory read per step) by four z strided by 16 (broadcast reads).  Tiles smaller than 64 (small tables) are handled by bounds checks.
 __global__ void __launch_bounds__(256) k_field_matmul_sp(FieldDesc f, const uint64_t* __restrict__ A, const uint64_t* __restrict__ B,
                                                         uint64_t* __restrict__ M, uint32_t X, uint32_t Y, uint32_t Z) {
-    __shared__ uint32_t sa[kMmK][kMmTile + 4];   // [y][x]
+    __shared__ __align__(16) uint32_t sa[kMmK][kMmTile + 4];   // [y][x]; rows are 272 B apart: 16-byte aligned
     __shared__ uint32_t sb[kMmTile][kMmK + 1];   // [z][y]
     const PolSP ar(f);
     const uint32_t c32 = (uint32_t)((1ull << 32) % ar.p);
     const uint32_t x0 = blockIdx.x * kMmTile, z0 = blockIdx.y * kMmTile;
-    const uint32_t tx = threadIdx.x & 15, tz = threadIdx.x >> 4;  // outputs x0 + tx + 16 i, z0 + tz + 16 j
+    const uint32_t tx = threadIdx.x & 15, tz = threadIdx.x >> 4;  // outputs x0 + 4 tx + i, z0 + tz + 16 j
     uint64_t acc[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -55,10 +55,10 @@ __global__ void __launch_bounds__(256) k_field_matmul_sp(FieldDesc f, const uint
 #pragma unroll 8
         for (uint32_t k = 0; k < kMmK; ++k) {
             uint32_t a[4], b[4];
+            const uint4 av = *reinterpret_cast<const uint4*>(&sa[k][4 * tx]);  // one 128-bit read: 16 lanes x 16 B contiguous
+            a[0] = av.x, a[1] = av.y, a[2] = av.z, a[3] = av.w;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = sa[k][tx + 16 * i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = sb[tz + 16 * j][k];
+            for (int j = 0; j < 4; ++j) b[j] = sb[tz + 16 * j][k];  // two distinct words per warp: broadcasts
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) k_field_matmul_sp(FieldDesc f, const uint
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const uint32_t x = x0 + tx + 16 * i, z = z0 + tz + 16 * j;
+            const uint32_t x = x0 + 4 * tx + i, z = z0 + tz + 16 * j;
             if (x < X && z < Z) {
                 const uint64_t t = (acc[j][i] & 0xffffffffull) + (acc[j][i] >> 32) * c32;  // < 2^61
                 M[(size_t)z * X + x] = ar.reduce_once(ar.redc(t));
