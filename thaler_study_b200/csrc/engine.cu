@@ -722,7 +722,7 @@ static int eval_table_multi(Ctx* c, const FieldImpl& f, const Table& t, const ui
     const uint32_t TC = N == 1 ? 8 : 2;
     uint32_t lb = v / 2;
     while (lb > 0 && ((size_t)TC * 8 * N << lb) > 64 * 1024) --lb;  // TC low tables in 64 KB of shared memory
-    if (v < 2 || lb < 1 || v - lb > cap_bits || t.p32) {
+    if (v < 4 || lb < 2 || v - lb > cap_bits || t.p32) {
         for (uint32_t i = 0; i < T; ++i) RC_TRY(eval_table(c, f, t, pts + (size_t)i * v * N, nullptr, d_out + (size_t)i * N));
         return SCB_OK;
     }
@@ -747,9 +747,8 @@ static int eval_table_multi(Ctx* c, const FieldImpl& f, const Table& t, const ui
             constexpr int KTC = A::N == 1 ? 8 : 2;
             auto kern = k_mle_dot_multi<A, KTC>;
             RC_TRY(allow_smem(kern, ((size_t)KTC * 8 * N) << lb));
-            // every CTA first stages the low tables (up to 64 KB): few CTAs with long loops, so that the staging is amortised
-            // (a grid of 8 CTAs per SM spent 64 us per pass over an 8 MB table, the staging being 9x the table data per CTA)
-            kern<<<grid_for(c, n / 16, 1), kThreads, smem, g_stream>>>(f.d, t.buf->ptr, lo->ptr + (((size_t)t0 << lb) * N), hi->ptr + (((size_t)t0 << (v - lb)) * N),
+            // every CTA first stages the low tables (up to 64 KB, so at most 3 CTAs fit an SM): one resident wave
+            kern<<<grid_for(c, n / 4, 3), kThreads, smem, g_stream>>>(f.d, t.buf->ptr, lo->ptr + (((size_t)t0 << lb) * N), hi->ptr + (((size_t)t0 << (v - lb)) * N),
                                                               lb, v, np, n, c->partials, c->ticket, d_out + (size_t)t0 * N);
         });
         LAUNCH_CHECK();

@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(kThreads) k_mle_dot_multi(FieldDesc f, const u
                                                             const uint64_t* __restrict__ hi_all, uint32_t lb, uint32_t v, uint32_t n_pts, uint64_t n,
                                                             uint64_t* partials, unsigned int* ticket, uint64_t* out) {
     constexpr int N = A::N;
+    constexpr int VEC = N == 1 ? 4 : 1;  // one-limb fields: four consecutive entries per 256-bit load (same row: lb >= 2)
     extern __shared__ uint64_t lo_sm[];
     const A ar(f);
     const uint64_t lo_words = ((uint64_t)n_pts << lb) * N;
@@ -169,10 +170,11 @@ __global__ void __launch_bounds__(kThreads) k_mle_dot_multi(FieldDesc f, const u
     for (int t = 0; t < TC; ++t) ar.acc_zero(acc[t]);
     const uint64_t mask = (1ull << lb) - 1;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint64_t w[N];
-        ld_words<N>(evals + i * N, w);
-        const typename A::Lz e = ar.lz(ar.from_words(w));
+    const uint64_t n_groups = n / VEC;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
+        uint64_t w[VEC * N];
+        ld_words<VEC * N>(evals + g * VEC * N, w);
+        const uint64_t i = g * VEC;
         const uint64_t il = i & mask, ih = i >> lb;
 #pragma unroll
         for (int t = 0; t < TC; ++t) {
@@ -180,7 +182,12 @@ __global__ void __launch_bounds__(kThreads) k_mle_dot_multi(FieldDesc f, const u
                 uint64_t hw[N];
 #pragma unroll
                 for (int q = 0; q < N; ++q) hw[q] = __ldg(hi_all + (((size_t)t << (v - lb)) + ih) * N + q);
-                const typename A::Lz m = ar.lz_mul(e, ar.lz(ar.from_words(lo_sm + (((size_t)t << lb) + il) * N)));
+                typename A::Lz m;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    const typename A::Lz me = ar.lz_mul(ar.lz(ar.from_words(w + e * N)), ar.lz(ar.from_words(lo_sm + (((size_t)t << lb) + il + e) * N)));
+                    m = e == 0 ? me : ar.lz_add(m, me);
+                }
                 ar.acc_add(acc[t], ar.lz_mul(m, ar.lz(ar.from_words(hw))));
             }
         }
