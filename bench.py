@@ -52,7 +52,8 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="which curve is the headline at N>1")
     ap.add_argument("--cpu-vars", type=int, default=24, help="log2 table size of the bounded sample in the cpu_baseline leg")
     ap.add_argument("--ref-vars", type=int, default=0, help="--impl reference: log2 table size per step (0 = the workload's own size if it fits)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-warmup", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="N>1: skip the second (strong-scaling) curve")
@@ -537,16 +538,28 @@ def run_ours(args):
             split["upload_ms"], split["prove_ms"] = (t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3
             return tr, gg
 
-        def time_e2e(tables, n_steps):
-            e2e_step(tables)
+        step_log = {}
+
+        def time_e2e(tables, n_steps, n_warm=1, tag="pinned"):
+            warm = []
+            for _ in range(max(1, n_warm)):
+                tw = time.perf_counter()
+                e2e_step(tables)
+                warm.append(round((time.perf_counter() - tw) * 1e3, 2))
             barrier()
             t0 = time.perf_counter()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
+            per = []
+            tr = gg = None
             for _ in range(n_steps):
+                tr = gg = None  # the previous step's handles are dropped before the next upload, as a caller's loop would
+                ts = time.perf_counter()
                 tr, gg = e2e_step(tables)
+                per.append(round((time.perf_counter() - ts) * 1e3, 2))
             b.record()
             barrier()
+            step_log[tag] = {"warmup_ms": warm, "timed_ms": per}
             wall = (time.perf_counter() - t0) / n_steps
             ems = max(a.elapsed_time(b) / n_steps, wall * 1e3)
             if world > 1:
@@ -555,7 +568,7 @@ def run_ours(args):
                 ems = float(t.item())
             return ems, all_true(verify(tr, gg, v))
 
-        ems, e2e_ok = time_e2e(host, args.e2e_steps)
+        ems, e2e_ok = time_e2e(host, args.e2e_steps, args.e2e_warmup)
         rounds = v + lg
         h2d = K * (1 << v) * E * n_gpus
         note = "scb_mle_from_host x%d (pinned host tables, H2D) + Prover::new + all rounds + Fiat-Shamir, per step" % K
@@ -577,7 +590,8 @@ def run_ours(args):
                           "chunks_narrowed_on_device": rc_.value,
                           "host_lane_wire_format": "three 21-bit entries per 64-bit word" if wire21 else "uint32",
                           "host_pack_threads_per_rank": min(32, T.get_option("host_pack_threads") or max(1, host_threads() // world))}
-        e2e = {"value": total_entries / (ems * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ems, "verified": e2e_ok, "last_step_split_rank0": dict(split),
+        e2e = {"value": total_entries / (ems * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ems, "steps": args.e2e_steps, "warmup": max(1, args.e2e_warmup),
+               "step_ms_rank0": step_log["pinned"], "verified": e2e_ok, "last_step_split_rank0": dict(split),
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": rounds * (K + 1) * E * n_gpus, "note": note}
         if upload:
             e2e["upload"] = upload
@@ -585,8 +599,8 @@ def run_ours(args):
         # and is skipped, the host lane stages through the library's pinned buffers
         if world == 1 and one_call:
             pageable = [np.array(h, copy=True) for h in host]
-            pms_, pok = time_e2e(pageable, max(1, args.e2e_steps - 1))
-            e2e["pageable_host_tables"] = {"value": total_entries / (pms_ * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": pms_, "verified": pok,
+            pms_, pok = time_e2e(pageable, max(1, args.e2e_steps - 1), 2, "pageable")
+            e2e["pageable_host_tables"] = {"value": total_entries / (pms_ * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": pms_, "verified": pok, "step_ms_rank0": step_log["pageable"],
                                            "note": "same call with the tables in pageable memory (what `Vec<F>::as_ptr()` gives a Rust shim)"}
             del pageable
         # The drop-in through the TRAIT ONLY: exactly the calls an unmodified sum_check_protocol::Prover<F, GpuPoly> and
