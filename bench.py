@@ -693,12 +693,21 @@ def generic_roofline(T, torch, F, g, v, K, p, ms, steps, res_stats, world):
     kname = {0: "k_fold_round_sp<3,in=u64,out=u32>", 1: "k_fold_round<PolG1,3>", 4: "fused fold+message kernel of the 4-limb policy (option g4_kernel=%d)" % T.get_option("g4_kernel")}[F.policy] \
         if (packed or F.policy != 0) else "k_fold_round<PolSP,3>"
     tkey = {0: "k_fold_round_sp", 1: "k_fold_round_g1", 4: "k_fold_round_g4"}[F.policy]
-    # integer roofline: modmuls per launch x IMAD.WIDE per modmul / measured IMAD.WIDE peak
-    imad_peak = 17.9e12  # profiles/r01_imad_peak.jsonl (IMAD.WIDE.U32, full rate)
-    imads_per_mul = {0: 3, 1: 11, 4: 128}[F.policy]
+    # integer roofline: modmuls per launch x 32x32->64 multiply-adds per modmul / their measured issue rate.
+    # A wide multiply-add (IMAD.WIDE.U32, with or without carry, IMAD.HI) issues once per 4 cycles per SM sub-partition on
+    # the fmaheavy pipe: 148 SMs x 4 x 32 lanes / 4 cycles x 1.965 GHz = 9.31 T/s (scripts/mont29_bench.cu under ncu:
+    # fmaheavy 91-95 % active at 0.24 warp instructions per cycle; profiles/r02_mont29.md).  Round 1-2 divided by 17.9 T/s,
+    # which was the rate of IADD3 pairs -- ptxas had hoisted that microbenchmark's loop-invariant product.
+    imad_peak = 9.31e12
+    imads_per_mul = {0: 2.5, 1: 10, 4: 128}[F.policy]  # wide multiply-adds (a plain 32-bit IMAD counts one half)
     modmuls_launch = (2 * K + (K + 1) * (K - 1)) * (1 << v) / 4.0  # fold K per output + message at X = 0..K
-    g4_on = F.policy == 4 and T.get_option("g4_kernel") != 0
+    g4_mode = T.get_option("g4_kernel") if F.policy == 4 else 0
+    g4_on = g4_mode != 0
     modmuls_executed = ((2 * K + K * (K - 1)) if g4_on else (2 * K + (K + 1) * (K - 1))) * (1 << v) / 4.0  # g4.cuh skips one point
+    wide_executed = modmuls_executed * imads_per_mul
+    if g4_mode == 3 and K >= 2:  # last product of each point unreduced (64), p = 1 mod 2^32: 120 per reduced product
+        red = 120 if (p & 0xFFFFFFFF) == 1 and T.get_option("g4_p0one") else 128
+        wide_executed = ((2 * K + K * (K - 2)) * red + K * 64) * (1 << v) / 4.0
     modmuls_proof = (K * K + K - 1) * float(1 << v)
     t_int_launch = modmuls_launch * imads_per_mul / imad_peak
     t_hbm_launch = alg_bytes / (peak * 1e9)
@@ -708,6 +717,7 @@ def generic_roofline(T, torch, F, g, v, K, p, ms, steps, res_stats, world):
              "achieved": achieved, "frac": achieved / peak, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
              "traffic": ncu_traffic(tkey, v, K, p),
              "modmuls_per_launch": modmuls_launch, "modmuls_executed_per_launch": modmuls_executed, "imad_wide_per_modmul": imads_per_mul, "imad_wide_peak_per_s": imad_peak,
+             "imad_wide_executed_per_launch": wide_executed, "frac_of_fmaheavy_issue_peak": wide_executed / imad_peak / (kms * 1e-3),
              "t_integer_bound_ms": t_int_launch * 1e3, "t_hbm_bound_ms": t_hbm_launch * 1e3,
              "frac_of_slower_bound": max(t_int_launch, t_hbm_launch) / (kms * 1e-3)}
     proof = {"proof_bytes_moved": proof_bytes, "proof_frac_of_hbm_roofline": (proof_bytes / (ms * 1e-3) / 1e9) / peak,
@@ -719,7 +729,8 @@ def generic_roofline(T, torch, F, g, v, K, p, ms, steps, res_stats, world):
             "share_of_step": kms / ms,
             "binding_roofline": "integer (IMAD.WIDE)" if int_bound else "hbm",
             "note": "contract fields describe the HBM side; for this policy the integer pipe binds -- see frac_of_slower_bound" if int_bound else None,
-            "integer": {k: alone[k] for k in ("modmuls_per_launch", "modmuls_executed_per_launch", "imad_wide_per_modmul", "imad_wide_peak_per_s", "t_integer_bound_ms", "t_hbm_bound_ms", "frac_of_slower_bound")}}
+            "integer": {k: alone[k] for k in ("modmuls_per_launch", "modmuls_executed_per_launch", "imad_wide_per_modmul", "imad_wide_peak_per_s", "imad_wide_executed_per_launch",
+                                             "frac_of_fmaheavy_issue_peak", "t_integer_bound_ms", "t_hbm_bound_ms", "frac_of_slower_bound")}}
     if world == 1 and res_stats["launches"] >= steps and res_stats["last_rounds"] > 0:
         res_ms = res_stats["total_ms"] / steps
         roof["resident_kernel"] = {"kernel_ms": res_ms, "rounds_last_launch": res_stats["last_rounds"], "share_of_step": res_ms / ms,

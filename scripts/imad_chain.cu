@@ -1,7 +1,11 @@
 // imad_chain.cu -- issue rates of the multiply-add forms a multi-limb Montgomery product can be built from (B200).
 // Round 1 measured IMAD.WIDE.U32 at full rate (17.9 T/s) and built the 4-limb product from mad.lo.cc / madc.hi.cc
 // pairs, which ptxas fuses into IMAD.WIDE.U32.X with a predicate carry in and out.  This bench separates:
-//   wide        IMAD.WIDE.U32 with a 64-bit addend, no carry           (the radix-2^29 lazy-carry product)
+//   wide        mad.wide.u32 with a 64-bit addend and LOOP-INVARIANT operands: ptxas hoists the product out of the loop and
+//               what is timed is IADD3 / IADD3.X pairs -- this line is NOT an IMAD.WIDE rate (round 2 misread it as one)
+//   wide_var    IMAD.WIDE.U32 with a 64-bit addend, no carry, multiplicand changing every iteration (the low word of the
+//               neighbouring accumulator): the real issue rate of the instruction -- one warp instruction per 4 cycles per
+//               SM sub-partition, the same as the carry forms below (ncu: fmaheavy pipe 91-95 % active, profiles/r02_mont29_ncu.md)
 //   wide_cout   mad.lo.cc + madc.hi (carry out of the low half only)
 //   wide_x      madc.lo.cc + madc.hi.cc chains of 4 pairs, carry in AND out (round 1's chain8)
 //   add64       add.cc + addc (64-bit add on the ALU pipe), shf (funnel shift), lop3
@@ -40,6 +44,8 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t a, uint32_t b) 
 #pragma unroll
             for (int i = 0; i < ILP; ++i) {
                 if (MODE == 0) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(x[i]), "r"(a));
+                if (MODE == 7) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"((uint32_t)w[(i + 1) % ILP]), "r"(a));
+                if (MODE == 8) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"((uint32_t)w[(i + 1) % ILP]), "r"((uint32_t)w[(i + 3) % ILP]));
                 if (MODE == 1) asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(x[i]), "+r"(y[i]) : "r"(z[i]), "r"(a));
                 if (MODE == 3) asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(x[i]), "+r"(y[i]) : "r"(a), "r"(b));
                 if (MODE == 4) asm volatile("shf.r.wrap.b32 %0, %0, %1, 29;" : "+r"(x[i]) : "r"(y[i]));
@@ -85,7 +91,9 @@ int main() {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     uint32_t* d;
     cudaMalloc(&d, (size_t)sms * 8 * 256 * 4);
-    run<0>("wide: mad.wide.u32 64-bit addend, no carry (per product)", 1, sms, d);
+    run<0>("wide: mad.wide.u32 with loop-invariant operands -- hoisted by ptxas, times IADD3 pairs, NOT a multiply rate", 1, sms, d);
+    run<7>("wide_var: IMAD.WIDE.U32 64-bit addend, no carry, register x constant, multiplicand changes every iteration (per product)", 1, sms, d);
+    run<8>("wide_var_rr: the same, register x register (per product)", 1, sms, d);
     run<1>("wide_cout: mad.lo.cc + madc.hi (per product)", 1, sms, d);
     run<2>("wide_x: carry chain of 4 mad pairs, carry in and out (per product)", 1, sms, d);
     run<3>("add64: add.cc + addc (per 64-bit add)", 1, sms, d);

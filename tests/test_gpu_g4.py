@@ -1,5 +1,6 @@
-"""The second-generation 4-limb kernel (csrc/g4.cuh: one point fewer thanks to the claim, leading coefficient instead
-of the highest point, lazy 288-bit sums, leaner carry chains) against the C oracle and against round 1's kernel."""
+"""The 4-limb kernels of csrc/g4.cuh (one point fewer thanks to the claim, leading coefficient instead of the highest
+point, lazy sums, leaner carry chains; fourth generation: unreduced last products in 544-bit shared-memory accumulators,
+p = 1 (mod 2^32) variant) and csrc/g29.cuh against the C oracle and against round 1's kernel."""
 import random
 
 import numpy as np
@@ -34,12 +35,16 @@ def test_g4_kernel_matches_oracle_and_first_generation(p):
             f_c = [cf.fix_variable(t, cf.to_mont([r])) for t in tabs_c[:K]]
             want = cf.from_mont(cf.product_round_evals(f_c, K + 1))
             claim = (want[0] + want[1]) % p
-            for flag in (2, 1, 0):  # radix-2^29 lazy carries (g29.cuh), 32-bit-limb chains (g4.cuh), round 1's kernel
+            # wide accumulators (generic / p = 1 mod 2^32 variant), radix-2^29 lazy carries (g29.cuh), 32-bit-limb chains, round 1's kernel
+            for flag, p0one in ((3, 1), (3, 0), (2, 1), (1, 1), (0, 1)):
                 T.set_option("g4_kernel", flag)
+                T.set_option("g4_p0one", p0one)
                 g_new, ev_new = g.fix_and_round_evals(r, claim=claim)
-                assert ev_new == want, (v, K, flag)
+                assert ev_new == want, (v, K, flag, p0one)
                 for k in range(K):
                     assert np.array_equal(g_new.table(k).to_evaluations_mont(), f_c[k]), (v, K, flag)
+                # Prover::new's pass (no claim): k_round_evals_g4w / k_round_evals_g29 / k_round_evals
+                assert g_new.round_evals() == want, (v, K, flag, p0one)
             _, ev_plain = g.fix_and_round_evals(r)
             assert ev_plain == want, (v, K)
     T.reset_options()
@@ -59,12 +64,15 @@ def test_g4_kernel_extreme_values(p):
         for r in (p - 1, 0, 1, (p + 1) // 2):
             of = og.fix_variables([r])
             want = of.round_evals()
-            for flag in (2, 1):
+            for flag, p0one in ((3, 1), (3, 0), (2, 1), (1, 1)):
                 T.set_option("g4_kernel", flag)
+                T.set_option("g4_p0one", p0one)
                 g2, ev = g.fix_and_round_evals(r, claim=(want[0] + want[1]) % p)
-                assert ev == want, (K, r, flag)
+                assert ev == want, (K, r, flag, p0one)
+                assert g2.round_evals() == want, (K, r, flag, p0one)
                 for k in range(K):
                     assert g2.table(k).to_evaluations() == of.tables[k].evals
+    T.reset_options()
 
 
 @pytest.mark.parametrize("p", [BLS, BN254], ids=pid)
@@ -79,7 +87,7 @@ def test_transcripts_through_the_g4_kernel(p):
         og = O.ProductMLE(OF, [O.DenseMLE(OF, v, t) for t in vals])
         want = O.generate_transcript(OF, O.Prover(og))
         outs = []
-        for flag in (2, 1, 0):
+        for flag in (3, 2, 1, 0):
             T.set_option("g4_kernel", flag)
             g = T.ProductMLE.new([T.DenseMultilinearExtension.from_evaluations_vec(F, v, t) for t in vals])
             T.launch_count(reset=True)

@@ -1198,7 +1198,7 @@ static int round_evals_impl(const scb_poly* p, uint32_t n_points, uint64_t* h_ou
         CU_TRY(cudaMemcpyAsync(d_out, c->d_scratch, (size_t)8 * N * n_points, cudaMemcpyDeviceToDevice, g_stream));
         return SCB_OK;
     }
-    if ((p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) && p->f->policy == POL_G4 && opt(OPT_g4_kernel) >= 2 && g29_supported(p->f->d) &&
+    if ((p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) && p->f->policy == POL_G4 && opt(OPT_g4_kernel) == 2 && g29_supported(p->f->d) &&
         p->t[0].nv >= 1) {
         // 4-limb fields: the message pass in radix-2^29 lazy-carry arithmetic (g29.cuh); sums at 0, inf, 2..K-1, 1
         const FieldImpl& f = *p->f;
@@ -1220,6 +1220,28 @@ static int round_evals_impl(const scb_poly* p, uint32_t n_points, uint64_t* h_ou
             const Fe fix = f.h.from_u64(1ull << (5 * (K - 1)));
             for (uint32_t x = 0; x <= K; ++x) S[x] = f.h.mul(S[x], fix);
         }
+        g4_rebuild_evals(f.h, K, S[K], S, ev);
+        for (uint32_t x = 0; x < n_points; ++x) f.h.store(ev[x], h_out + (size_t)x * N);
+        return SCB_OK;
+    }
+    if ((p->kind == SCB_POLY_PRODUCT || p->kind == SCB_POLY_MATMUL_G) && p->f->policy == POL_G4 && opt(OPT_g4_kernel) == 3 &&
+        g4w_supported(p->f->d, (int)p->t.size()) && p->t[0].nv >= 1) {
+        // 4-limb fields: the message pass with unreduced last products (k_round_evals_g4w); sums at 0, inf, 2..K-1, 1
+        const FieldImpl& f = *p->f;
+        const uint32_t K = (uint32_t)p->t.size();
+        const uint64_t* in[kMaxTables];
+        for (uint32_t k = 0; k < K; ++k) in[k] = p->t[k].buf->ptr;
+        const cudaError_t le = launch_round_evals_g4w((int)K, opt(OPT_g4_p0one) != 0 && g4_p0one(f.d), (int)opt(OPT_bps), c->sms, g_stream, f.d, in,
+                                                      p->t[0].len() / 2, c->partials, c->ticket, c->h_res, peer_arg(c), kMaxGrid);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (le != cudaSuccess) {
+            set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(le), __FILE__, __LINE__);
+            return SCB_ECUDA;
+        }
+        CU_TRY(cudaStreamSynchronize(g_stream));
+        RC_TRY(peers_check(c));
+        Fe S[kMaxPts + 1], ev[kMaxPts + 1];
+        for (uint32_t x = 0; x <= K; ++x) f.h.load(c->h_res + (size_t)x * N, S[x]);
         g4_rebuild_evals(f.h, K, S[K], S, ev);
         for (uint32_t x = 0; x < n_points; ++x) f.h.store(ev[x], h_out + (size_t)x * N);
         return SCB_OK;
@@ -1330,11 +1352,15 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
             in[k] = p->t[k].buf->ptr;
             o[k] = q->t[k].buf->ptr;
         }
-        // option g4_kernel: 2 (default) = radix-2^29 lazy-carry arithmetic (g29.cuh) where the modulus allows, 1 = the
-        // 32-bit-limb carry-chain kernel (g4.cuh)
-        const bool use29 = opt(OPT_g4_kernel) >= 2 && g29_supported(f.d);
+        // option g4_kernel: 3 (default) = carry chains with unreduced last products (k_fold_round_g4w), 1 = carry chains
+        // (k_fold_round_g4), 2 = radix-2^29 lazy-carry arithmetic (g29.cuh) where the modulus allows
+        const bool use29 = opt(OPT_g4_kernel) == 2 && g29_supported(f.d);
+        const bool usew = opt(OPT_g4_kernel) == 3 && g4w_supported(f.d, (int)K);
         cudaError_t le;
-        if (use29) {
+        if (usew) {
+            le = launch_fold_round_g4w((int)K, opt(OPT_g4_p0one) != 0 && g4_p0one(f.d), (int)opt(OPT_bps), c->sms, g_stream, f.d, in, o, elem_arg(f, r),
+                                       p->t[0].len() / 4, c->partials, c->ticket, c->h_res, peer_arg(c), kMaxGrid);
+        } else if (use29) {
             Fe rr, r5;
             f.h.load(r, rr);
             r5 = f.h.mul(rr, f.h.from_u64(32));  // r * 2^5: the fold's product divides by 2^261 instead of 2^256

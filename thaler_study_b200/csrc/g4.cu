@@ -150,6 +150,91 @@ cudaError_t launch_fold_round_g29(int K, int minb, int blocks_per_sm_cap, int sm
     }
 }
 
+// ---- fourth generation: wide accumulators in shared memory (k_fold_round_g4w / k_round_evals_g4w)
+// nb_cached: the caller's per-kernel static (kernels that differ only in a bool template argument share a function TYPE,
+// so a static in here would be shared between them and the second one would never get its shared-memory attribute)
+template <class Kern>
+static cudaError_t wide_grid(Kern kern, int& nb_cached, size_t smem, int blocks_per_sm_cap, int sms, uint64_t items, int max_grid, int* grid_out) {
+    if (nb_cached == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess || nb < 1) nb = 1;
+        nb_cached = nb;
+    }
+    int nb = nb_cached;
+    if (blocks_per_sm_cap > 0 && blocks_per_sm_cap < nb) nb = blocks_per_sm_cap;
+    uint64_t want = (items + kThreads - 1) / kThreads, cap = (uint64_t)sms * nb;
+    if (cap > (uint64_t)max_grid) cap = max_grid;
+    if (want < 1) want = 1;
+    *grid_out = (int)(want < cap ? want : cap);
+    return cudaSuccess;
+}
+template <int K, bool P0ONE>
+static cudaError_t launch_kw(int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in, uint64_t* const* outp,
+                             const ElemArg& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid) {
+    auto kern = g4::k_fold_round_g4w<K, P0ONE>;
+    const size_t smem = g4::wacc_smem_bytes(g4::n_sums(K));
+    static int nb_cached = 0;
+    int grid = 1;
+    const cudaError_t e = wide_grid(kern, nb_cached, smem, blocks_per_sm_cap, sms, n_quads, max_grid, &grid);
+    if (e != cudaSuccess) return e;
+    TabsIn<K> ti;
+    TabsOut<K> to;
+    for (int k = 0; k < K; ++k) {
+        ti.p[k] = in[k];
+        to.p[k] = outp[k];
+    }
+    kern<<<grid, kThreads, smem, stream>>>(f, ti, to, r, n_quads, partials, ticket, res, pa);
+    return cudaGetLastError();
+}
+template <int K, bool P0ONE>
+static cudaError_t launch_rw(int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in, uint64_t n_pairs,
+                             uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid) {
+    auto kern = g4::k_round_evals_g4w<K, P0ONE>;
+    const size_t smem = g4::wacc_smem_bytes(g4::n_sums(K) + 1);
+    static int nb_cached = 0;
+    int grid = 1;
+    const cudaError_t e = wide_grid(kern, nb_cached, smem, blocks_per_sm_cap, sms, n_pairs, max_grid, &grid);
+    if (e != cudaSuccess) return e;
+    TabsIn<K> ti;
+    for (int k = 0; k < K; ++k) ti.p[k] = in[k];
+    kern<<<grid, kThreads, smem, stream>>>(f, ti, n_pairs, partials, ticket, res, pa);
+    return cudaGetLastError();
+}
+bool g4w_supported(const FieldDesc& f, int K) { return f.n == 4 && f.bits <= 255 && K >= 2 && K <= 4; }
+bool g4_p0one(const FieldDesc& f) { return (uint32_t)f.p[0] == 1u; }
+
+cudaError_t launch_fold_round_g4w(int K, bool p0one, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
+                                  uint64_t* const* outp, const ElemArg& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res,
+                                  const PeerArg& pa, int max_grid) {
+#define SCB_KW(KK)                                                                                                                          \
+    case KK:                                                                                                                                \
+        return p0one ? launch_kw<KK, true>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid)   \
+                     : launch_kw<KK, false>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid);
+    switch (K) {
+        SCB_KW(2)
+        SCB_KW(3)
+        SCB_KW(4)
+        default: return cudaErrorInvalidValue;
+    }
+#undef SCB_KW
+}
+cudaError_t launch_round_evals_g4w(int K, bool p0one, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
+                                   uint64_t n_pairs, uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid) {
+#define SCB_RW(KK)                                                                                                                  \
+    case KK:                                                                                                                        \
+        return p0one ? launch_rw<KK, true>(blocks_per_sm_cap, sms, stream, f, in, n_pairs, partials, ticket, res, pa, max_grid)    \
+                     : launch_rw<KK, false>(blocks_per_sm_cap, sms, stream, f, in, n_pairs, partials, ticket, res, pa, max_grid);
+    switch (K) {
+        SCB_RW(2)
+        SCB_RW(3)
+        SCB_RW(4)
+        default: return cudaErrorInvalidValue;
+    }
+#undef SCB_RW
+}
+
 cudaError_t launch_fold_round_g4(int K, int minb, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
                                  uint64_t* const* outp, const ElemArg& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res,
                                  const PeerArg& pa, int max_grid) {

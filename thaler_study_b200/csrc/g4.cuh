@@ -85,11 +85,38 @@ __device__ __forceinline__ void store8(const W8& a, uint64_t* l) {
     for (int i = 0; i < 4; ++i) l[i] = (uint64_t)a.w[2 * i] | ((uint64_t)a.w[2 * i + 1] << 32);
 }
 
-struct Arith {
+// the second reduction chain of a row when p = 1 (mod 2^32): word 0 receives m * 1 as a plain add (E0 + m = 0 mod 2^32,
+// only its carry matters), the other three products as in chain().  Two asm blocks, and the carry re-enters the second
+// through `add.cc c, 0xffffffff` -- the shape of chain_fix -- because ptxas only fuses mad.lo.cc / madc.hi.cc pairs into
+// IMAD.WIDE.U32.X when the chain starts that way (with add.cc, addc.cc in front it emits IMAD.X + IMAD.HI.U32.X pairs).
+__device__ __forceinline__ void chain_p0one(uint32_t* t, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t m) {
+    uint32_t c;
+    asm("add.cc.u32      %0, %0, %3;\n\t"
+        "addc.cc.u32     %1, %1, 0;\n\t"
+        "addc.u32        %2, 0, 0;\n\t"
+        : "+r"(t[0]), "+r"(t[1]), "=r"(c)
+        : "r"(m));
+    asm("add.cc.u32      %7, %7, 0xffffffff;\n\t"
+        "madc.lo.cc.u32  %0, %8, %11, %0;\n\t"
+        "madc.hi.cc.u32  %1, %8, %11, %1;\n\t"
+        "madc.lo.cc.u32  %2, %9, %11, %2;\n\t"
+        "madc.hi.cc.u32  %3, %9, %11, %3;\n\t"
+        "madc.lo.cc.u32  %4, %10, %11, %4;\n\t"
+        "madc.hi.cc.u32  %5, %10, %11, %5;\n\t"
+        "addc.u32        %6, %6, 0;\n\t"
+        : "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(c)
+        : "r"(x1), "r"(x2), "r"(x3), "r"(m));
+}
+
+// P0ONE: the modulus is 1 modulo 2^32 (every field whose two-adicity is at least 32 -- BLS12-381 Fr is one): then
+// n0 = -p^-1 = -1 (mod 2^32), so m = -E[0] needs no multiplication and m * p[0] = m is an addition: 120 instead of 128
+// wide multiply-adds per product.  The host picks the variant from the modulus (g4.cu).
+template <bool P0ONE = false>
+struct ArithT {
     uint32_t p[8];
     uint32_t n0;
 
-    __device__ __forceinline__ explicit Arith(const FieldDesc& f) {
+    __device__ __forceinline__ explicit ArithT(const FieldDesc& f) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             p[2 * i] = (uint32_t)f.p[i];
@@ -114,12 +141,19 @@ struct Arith {
                 chain_fix(E[0], orphan, O, a.w[1], a.w[3], a.w[5], a.w[7], b.w[i]);
             }
             chain(E, a.w[0], a.w[2], a.w[4], a.w[6], b.w[i]);
-            const uint32_t m = E[0] * n0;
-            chain(O, p[1], p[3], p[5], p[7], m);
-            chain(E, p[0], p[2], p[4], p[6], m);  // E[0] becomes 0
-            // E[0] is dead from here on; OR-ing it into a sink keeps the low half of its product alive, so ptxas emits
-            // ONE full-rate IMAD.WIDE for the pair instead of IMAD + half-rate IMAD.HI (the carry is all that is needed)
-            sink |= E[0];
+            if constexpr (P0ONE) {
+                const uint32_t m = E[0] * n0;  // n0 = 0xffffffff; written as the product because ptxas stops fusing the
+                                               // mad.lo / mad.hi pairs below into IMAD.WIDE when m is a plain negation
+                chain(O, p[1], p[3], p[5], p[7], m);
+                chain_p0one(E, p[2], p[4], p[6], m);  // E[0] becomes 0
+            } else {
+                const uint32_t m = E[0] * n0;
+                chain(O, p[1], p[3], p[5], p[7], m);
+                chain(E, p[0], p[2], p[4], p[6], m);  // E[0] becomes 0
+                // E[0] is dead from here on; OR-ing it into a sink keeps the low half of its product alive, so ptxas emits
+                // ONE IMAD.WIDE for the pair instead of IMAD + IMAD.HI (the carry is all that is needed)
+                sink |= E[0];
+            }
         }
         A0[16] |= sink;  // always zero
         // window after row 7: E = A0 + 8, O = A1 + 8, orphan = A1[7];  t = orphan + E + (O << 32)
@@ -135,6 +169,43 @@ struct Arith {
             : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]), "=r"(lo[4]), "=r"(lo[5]), "=r"(lo[6]), "=r"(lo[7]), "=r"(top)
             : "r"(A0[8]), "r"(A0[9]), "r"(A0[10]), "r"(A0[11]), "r"(A0[12]), "r"(A0[13]), "r"(A0[14]), "r"(A0[15]), "r"(A0[16]),
               "r"(A1[7]), "r"(A1[8]), "r"(A1[9]), "r"(A1[10]), "r"(A1[11]), "r"(A1[12]), "r"(A1[13]), "r"(A1[14]), "r"(A1[15]));
+    }
+    // a * b as a plain 512-bit integer (no reduction): 64 wide multiply-adds in the same even/odd two-accumulator layout
+    // (A0[k] holds word k, A1[k] word k + 1; a row's chain ends in a word no earlier row has touched, so its carry-out
+    // word cannot overflow), then one 16-word add joins the two.
+    __device__ __forceinline__ void mul_wide(uint32_t (&t)[16], const W8& a, const W8& b) const {
+        uint32_t A0[18], A1[18];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) A0[i] = A1[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t* E = (i & 1) ? A1 + (i - 1) : A0 + i;
+            uint32_t* O = (i & 1) ? A0 + (i + 1) : A1 + i;
+            chain(O, a.w[1], a.w[3], a.w[5], a.w[7], b.w[i]);
+            chain(E, a.w[0], a.w[2], a.w[4], a.w[6], b.w[i]);
+        }
+        t[0] = A0[0];
+        asm("add.cc.u32  %0, %15, %30;\n\t"
+            "addc.cc.u32 %1, %16, %31;\n\t"
+            "addc.cc.u32 %2, %17, %32;\n\t"
+            "addc.cc.u32 %3, %18, %33;\n\t"
+            "addc.cc.u32 %4, %19, %34;\n\t"
+            "addc.cc.u32 %5, %20, %35;\n\t"
+            "addc.cc.u32 %6, %21, %36;\n\t"
+            "addc.cc.u32 %7, %22, %37;\n\t"
+            "addc.cc.u32 %8, %23, %38;\n\t"
+            "addc.cc.u32 %9, %24, %39;\n\t"
+            "addc.cc.u32 %10, %25, %40;\n\t"
+            "addc.cc.u32 %11, %26, %41;\n\t"
+            "addc.cc.u32 %12, %27, %42;\n\t"
+            "addc.cc.u32 %13, %28, %43;\n\t"
+            "addc.u32    %14, %29, %44;\n\t"
+            : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]),
+              "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+            : "r"(A0[1]), "r"(A0[2]), "r"(A0[3]), "r"(A0[4]), "r"(A0[5]), "r"(A0[6]), "r"(A0[7]), "r"(A0[8]), "r"(A0[9]), "r"(A0[10]), "r"(A0[11]),
+              "r"(A0[12]), "r"(A0[13]), "r"(A0[14]), "r"(A0[15]),
+              "r"(A1[0]), "r"(A1[1]), "r"(A1[2]), "r"(A1[3]), "r"(A1[4]), "r"(A1[5]), "r"(A1[6]), "r"(A1[7]), "r"(A1[8]), "r"(A1[9]), "r"(A1[10]),
+              "r"(A1[11]), "r"(A1[12]), "r"(A1[13]), "r"(A1[14]));
     }
     // (lo, top) < 2p  ->  canonical
     __device__ __forceinline__ W8 reduce_once(const uint32_t (&lo)[8], uint32_t top) const {
@@ -181,6 +252,7 @@ struct Arith {
     // t0 + r * (t1 - t0), canonical
     __device__ __forceinline__ W8 fold(const W8& t0, const W8& t1, const W8& r) const { return add(t0, mul(diff_lazy(t1, t0), r)); }
 };
+using Arith = ArithT<false>;
 
 __device__ __forceinline__ void acc_zero(W9& a) {
 #pragma unroll
@@ -275,6 +347,184 @@ __global__ void __launch_bounds__(kThreads, MINB)
         const W8 r2 = load8(f.r2);
         const W8 hr = ar.mul(hi, r2);
         const W8 s = ar.add(ar.mul(ar.mul(lo, r2), one_int), hr);
+        uint64_t l[4];
+        store8(s, l);
+        fin[x] = A.from_words(l);
+    }
+    grid_reduce_finish<PolGN<4>, NS>(A, fin, partials, ticket, out, 0, &peer);
+}
+
+// ------------------------------------------------------------------------------------------------ wide accumulators (r2b)
+// Fourth generation.  Measured on B200 (scripts/mont29_bench.cu, profiles/r02_mont29.md): a 32 x 32 -> 64-bit multiply-add
+// (IMAD.WIDE.U32, with or without carry) issues once per 4 cycles per SM sub-partition on the fmaheavy pipe, and these
+// kernels run with that pipe 85-95 % busy -- so the only way to be faster is to issue fewer of them:
+//   * the LAST product of every message point is not reduced at all: its 512-bit integer value prod * fac goes into a
+//     544-bit accumulator (64 wide multiply-adds instead of 128), and each thread does ONE Montgomery reduction per
+//     accumulator at the end (REDC is linear: sum REDC(x_i) = REDC(sum x_i) mod p);
+//   * moduli with p = 1 (mod 2^32) skip the n0 multiplication and the p[0] column of every reduction (ArithT<true>).
+// The accumulators (17 words each) would not fit the 128-register budget of two resident CTAs per SM, so they live in
+// shared memory: 5 x 128-bit per thread and sum, 80-byte stride (bank-conflict-free for 128-bit accesses), read, added to
+// and written back once per product.  K >= 2 (K = 1 has no product to defer; the host keeps k_fold_round_g4 for it).
+constexpr int kWaccQuads = 5;  // 128-bit words per accumulator slot (17 of the 20 32-bit words used)
+__host__ __device__ constexpr size_t wacc_smem_bytes(int n_sums) { return (size_t)n_sums * kWaccQuads * 16 * kThreads; }
+
+__device__ __forceinline__ uint4* wacc_slot(uint4* base, int x) { return base + ((size_t)x * kThreads + threadIdx.x) * kWaccQuads; }
+__device__ __forceinline__ void wacc_zero(uint4* slot) {
+#pragma unroll
+    for (int q = 0; q < kWaccQuads; ++q) slot[q] = make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void wacc_add(uint4* slot, const uint32_t (&t)[16]) {
+    uint4 a0 = slot[0], a1 = slot[1], a2 = slot[2], a3 = slot[3];
+    uint32_t a16 = slot[4].x;
+    asm("add.cc.u32  %0, %0, %17;\n\t"
+        "addc.cc.u32 %1, %1, %18;\n\t"
+        "addc.cc.u32 %2, %2, %19;\n\t"
+        "addc.cc.u32 %3, %3, %20;\n\t"
+        "addc.cc.u32 %4, %4, %21;\n\t"
+        "addc.cc.u32 %5, %5, %22;\n\t"
+        "addc.cc.u32 %6, %6, %23;\n\t"
+        "addc.cc.u32 %7, %7, %24;\n\t"
+        "addc.cc.u32 %8, %8, %25;\n\t"
+        "addc.cc.u32 %9, %9, %26;\n\t"
+        "addc.cc.u32 %10, %10, %27;\n\t"
+        "addc.cc.u32 %11, %11, %28;\n\t"
+        "addc.cc.u32 %12, %12, %29;\n\t"
+        "addc.cc.u32 %13, %13, %30;\n\t"
+        "addc.cc.u32 %14, %14, %31;\n\t"
+        "addc.cc.u32 %15, %15, %32;\n\t"
+        "addc.u32    %16, %16, 0;\n\t"
+        : "+r"(a0.x), "+r"(a0.y), "+r"(a0.z), "+r"(a0.w), "+r"(a1.x), "+r"(a1.y), "+r"(a1.z), "+r"(a1.w), "+r"(a2.x), "+r"(a2.y), "+r"(a2.z),
+          "+r"(a2.w), "+r"(a3.x), "+r"(a3.y), "+r"(a3.z), "+r"(a3.w), "+r"(a16)
+        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]),
+          "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]));
+    slot[0] = a0;
+    slot[1] = a1;
+    slot[2] = a2;
+    slot[3] = a3;
+    slot[4].x = a16;
+}
+// T = C0 + C1 2^256 + C2 2^512 (sum of products of Montgomery-form factors)  ->  REDC(T) = T / R mod p, canonical:
+// C0 / R = montmul(C0, 1),  C1 2^256 / R = C1 (an arbitrary 256-bit integer: montmul(montmul(C1, R^2), 1) brings it below p),
+// C2 2^512 / R = C2 R = montmul(C2, R^2).  Once per thread and accumulator.
+template <bool P0ONE>
+__device__ __forceinline__ W8 wacc_reduce(const ArithT<P0ONE>& ar, const FieldDesc& f, const uint4* slot) {
+    W8 c0, c1, c2, one_int;
+    const uint4 a0 = slot[0], a1 = slot[1], a2 = slot[2], a3 = slot[3];
+    c0.w[0] = a0.x, c0.w[1] = a0.y, c0.w[2] = a0.z, c0.w[3] = a0.w, c0.w[4] = a1.x, c0.w[5] = a1.y, c0.w[6] = a1.z, c0.w[7] = a1.w;
+    c1.w[0] = a2.x, c1.w[1] = a2.y, c1.w[2] = a2.z, c1.w[3] = a2.w, c1.w[4] = a3.x, c1.w[5] = a3.y, c1.w[6] = a3.z, c1.w[7] = a3.w;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) c2.w[q] = one_int.w[q] = 0;
+    c2.w[0] = slot[4].x;
+    one_int.w[0] = 1;
+    const W8 r2 = load8(f.r2);
+    const W8 x0 = ar.mul(c0, one_int);
+    const W8 x1 = ar.mul(ar.mul(c1, r2), one_int);
+    const W8 x2 = ar.mul(c2, r2);
+    return ar.add(ar.add(x0, x1), x2);
+}
+
+// Fused fold + message with a claim (as k_fold_round_g4): sums S_0, S_inf, S_2 .. S_{K-1}, canonical.
+template <int K, bool P0ONE>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_fold_round_g4w(FieldDesc f, TabsIn<K> in, TabsOut<K> outp, ElemArg rarg, uint64_t n_quads, uint64_t* partials, unsigned int* ticket,
+                     uint64_t* out, PeerArg peer) {
+    static_assert(K >= 2, "K = 1 has no product to defer");
+    constexpr int NS = n_sums(K);
+    extern __shared__ uint4 wacc[];
+    const ArithT<P0ONE> ar(f);
+    const W8 r = load8(rarg.w);
+#pragma unroll
+    for (int x = 0; x < NS; ++x) wacc_zero(wacc_slot(wacc, x));
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_quads; i += stride) {
+        W8 prod[NS];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            uint64_t w[16];
+            ld_words<16>(in.p[k] + i * 16, w);
+            const W8 u0 = ar.fold(load8(w), load8(w + 4), r);
+            const W8 u1 = ar.fold(load8(w + 8), load8(w + 12), r);
+            uint64_t o[8];
+            store8(u0, o);
+            store8(u1, o + 4);
+            st_words<8>(outp.p[k] + i * 8, o);
+            W8 fac[NS];
+            fac[0] = u0;
+            fac[1] = ar.sub(u1, u0);
+#pragma unroll
+            for (int x = 2; x < NS; ++x) fac[x] = ar.add(x == 2 ? u1 : fac[x - 1], fac[1]);
+#pragma unroll
+            for (int x = 0; x < NS; ++x) {
+                if (k == 0) {
+                    prod[x] = fac[x];
+                } else if (k < K - 1) {
+                    prod[x] = ar.mul(prod[x], fac[x]);
+                } else {  // last factor: the plain 512-bit product into the wide accumulator
+                    uint32_t t[16];
+                    ar.mul_wide(t, prod[x], fac[x]);
+                    wacc_add(wacc_slot(wacc, x), t);
+                }
+            }
+        }
+    }
+    const PolGN<4> A(f);
+    typename PolGN<4>::Acc fin[NS];
+#pragma unroll
+    for (int x = 0; x < NS; ++x) {
+        const W8 s = wacc_reduce<P0ONE>(ar, f, wacc_slot(wacc, x));
+        uint64_t l[4];
+        store8(s, l);
+        fin[x] = A.from_words(l);
+    }
+    grid_reduce_finish<PolGN<4>, NS>(A, fin, partials, ticket, out, 0, &peer);
+}
+
+// Round-0 message (Prover::new's pass: sum-check-protocol/src/lib.rs:88-97 with G::to_univariate,
+// matrix-multiplication/src/lib.rs:110-122, generalised to K tables) in the same arithmetic.  No claim exists yet, so
+// X = 1 is summed too: K + 1 sums in the order S_0, S_inf, S_2 .. S_{K-1}, S_1 (the host rebuilds g(0..K), engine.cu).
+// One hypercube pair of every table per thread-iteration; 64 K + 64 instead of 128 K wide multiply-adds per point.
+template <int K, bool P0ONE>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_round_evals_g4w(FieldDesc f, TabsIn<K> in, uint64_t n_pairs, uint64_t* partials, unsigned int* ticket, uint64_t* out, PeerArg peer) {
+    static_assert(K >= 2, "K = 1 has no product to defer");
+    constexpr int NS = n_sums(K) + 1;
+    extern __shared__ uint4 wacc[];
+    const ArithT<P0ONE> ar(f);
+#pragma unroll
+    for (int x = 0; x < NS; ++x) wacc_zero(wacc_slot(wacc, x));
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += stride) {
+        W8 prod[NS];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            uint64_t w[8];
+            ld_words<8>(in.p[k] + i * 8, w);
+            const W8 lo = load8(w), hi = load8(w + 4);
+            W8 fac[NS];
+            fac[0] = lo;
+            fac[NS - 1] = hi;
+            fac[1] = ar.sub(hi, lo);
+#pragma unroll
+            for (int x = 2; x < NS - 1; ++x) fac[x] = ar.add(x == 2 ? hi : fac[x - 1], fac[1]);
+#pragma unroll
+            for (int x = 0; x < NS; ++x) {
+                if (k == 0) {
+                    prod[x] = fac[x];
+                } else if (k < K - 1) {
+                    prod[x] = ar.mul(prod[x], fac[x]);
+                } else {
+                    uint32_t t[16];
+                    ar.mul_wide(t, prod[x], fac[x]);
+                    wacc_add(wacc_slot(wacc, x), t);
+                }
+            }
+        }
+    }
+    const PolGN<4> A(f);
+    typename PolGN<4>::Acc fin[NS];
+#pragma unroll
+    for (int x = 0; x < NS; ++x) {
+        const W8 s = wacc_reduce<P0ONE>(ar, f, wacc_slot(wacc, x));
         uint64_t l[4];
         store8(s, l);
         fin[x] = A.from_words(l);

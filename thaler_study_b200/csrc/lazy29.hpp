@@ -146,6 +146,76 @@ L29_HD L9 mont(const Desc29& d, const L9& a, const L9& b) {
     return carry_cols(t);
 }
 
+// ---------------------------------------------------------------------------------------------- product scanning (r2b)
+// The same product with the two phases separated: first all 81 partial products into 17 independent 64-bit columns
+// (no instruction waits on another column), then the Montgomery reduction column by column.  Step k makes column k a
+// multiple of 2^29 by adding m_k p (m_k from the low word of the column) and hands its upper bits to column k + 1.
+// P0ONE: moduli with p = 1 (mod 2^29) (every field with 2-adicity >= 29, BLS12-381 Fr among them): n0 = -1, so
+// m_k = -c_k mod 2^29 without a multiplication.
+// Column bound: 9 (A B) from the products + 9 2^58 from the reduction + a carry below 2^36, A B <= 2^60.2 as above.
+// The result occupies columns 9 .. 16 (column 17 of a 9 x 9 product is empty): eight 64-bit columns out.
+template <bool P0ONE>
+L29_HD void mont_ps_cols(const Desc29& d, const L9& a, const L9& b, uint64_t (&out)[NL - 1]) {
+    uint64_t c[2 * NL - 1];
+#pragma unroll
+    for (int k = 0; k < 2 * NL - 1; ++k) c[k] = 0;
+#pragma unroll
+    for (int i = 0; i < NL; ++i)
+#pragma unroll
+        for (int j = 0; j < NL; ++j) c[i + j] += (uint64_t)a.l[j] * b.l[i];
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+        const uint32_t lo = (uint32_t)c[k];
+        const uint32_t m = P0ONE ? ((0u - lo) & M29) : ((lo * d.n0) & M29);
+#pragma unroll
+        for (int j = 0; j < NL; ++j) c[k + j] += (uint64_t)m * (P0ONE && j == 0 ? 1u : d.p[j]);
+        if (k + 1 < 2 * NL - 1) c[k + 1] += c[k] >> 29;
+    }
+#pragma unroll
+    for (int j = 0; j < NL - 1; ++j) out[j] = c[NL + j];
+}
+// eight columns -> nine limbs, carries rippled (limbs below 2^29, the top limb takes the rest)
+L29_HD L9 carry_cols8(uint64_t (&t)[NL - 1]) {
+    L9 r;
+#pragma unroll
+    for (int j = 0; j < NL - 2; ++j) {
+        r.l[j] = (uint32_t)t[j] & M29;
+        t[j + 1] += t[j] >> 29;
+    }
+    r.l[NL - 2] = (uint32_t)t[NL - 2] & M29;
+    r.l[NL - 1] = (uint32_t)(t[NL - 2] >> 29);
+    return r;
+}
+// eight columns -> nine limbs without a carry chain: every column is cut into its three 29-bit digits and limb j takes
+// digit 0 of column j, digit 1 of column j - 1 and digit 2 of column j - 2.  Limbs below 2^30 + 2^6 (not normalised):
+// fine as an operand of another product (9 2^60.02 + 9 2^58 < 2^64), not for limb-wise sums.
+L29_HD L9 split_cols8(const uint64_t (&t)[NL - 1]) {
+    uint32_t d0[NL - 1], d1[NL - 1], d2[NL - 1];
+#pragma unroll
+    for (int j = 0; j < NL - 1; ++j) {
+        d0[j] = (uint32_t)t[j] & M29;
+        d1[j] = (uint32_t)(t[j] >> 29) & M29;
+        d2[j] = (uint32_t)(t[j] >> 58);
+    }
+    L9 r;
+#pragma unroll
+    for (int j = 0; j < NL - 1; ++j) r.l[j] = d0[j] + (j >= 1 ? d1[j - 1] : 0u) + (j >= 2 ? d2[j - 2] : 0u);
+    r.l[NL - 1] = (uint32_t)(t[NL - 2] >> 29) + d2[NL - 3];  // digit 1 of the last column unmasked: it takes what is above
+    return r;
+}
+template <bool P0ONE>
+L29_HD L9 mont_ps(const Desc29& d, const L9& a, const L9& b) {
+    uint64_t t[NL - 1];
+    mont_ps_cols<P0ONE>(d, a, b, t);
+    return carry_cols8(t);
+}
+template <bool P0ONE>
+L29_HD L9 mont_ps_par(const Desc29& d, const L9& a, const L9& b) {
+    uint64_t t[NL - 1];
+    mont_ps_cols<P0ONE>(d, a, b, t);
+    return split_cols8(t);
+}
+
 // ---------------------------------------------------------------------------------------------- host set-up
 // p as four little-endian 64-bit limbs.  False if the modulus is outside the range the bounds above were derived for
 // (the caller then keeps the 32-bit-limb kernel).

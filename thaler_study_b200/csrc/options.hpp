@@ -33,9 +33,10 @@ namespace scb {
     X(mle_fused, 1)            /* MLE evaluation as ONE launch (eq sub-tables built per CTA in shared memory) */            \
     X(gkr_multi, 1)            /* GKR layer with challenges up front: up to 4 rounds per pass, no barriers (k_pqs_multi) */  \
     X(gkr_persist, 1)          /* GKR layer phases as one cooperative launch each */                                        \
-    X(g4_kernel, 1)            /* 4-limb fused fold+message with a claim: 1 = 32-bit-limb carry chains, one point fewer (g4.cuh:    \
-                                  measured best, 14.7 ms per 2^28 x 3 launch); 2 = radix-2^29 lazy carries (g29.cuh: 20.8 ms);   \
-                                  0 = round 1's kernel (18.2 ms) */                                                            \
+    X(g4_kernel, 3)            /* 4-limb fused fold+message with a claim: 3 = carry chains + unreduced last products in 544-bit        \
+                                  shared-memory accumulators, round 0 included (g4.cuh, K >= 2); 1 = carry chains, one point fewer      \
+                                  (14.7 ms per 2^28 x 3 launch); 2 = radix-2^29 lazy carries (g29.cuh: 20.8 ms); 0 = round 1's (18.2 ms) */ \
+    X(g4_p0one, 1)             /* g4_kernel 3: use the p = 1 (mod 2^32) variant when the modulus allows (0: always the generic one) */   \
     X(g4_blocks, 2)            /* 4-limb kernels: variant compiled for 2 or 3 resident CTAs per SM */                       \
     X(tri_tiled, 1)            /* triangle x-phase as a shared-memory tiled field matmul */                                 \
     X(host_pack, 1)            /* narrowing upload of host tables (upload_engine.inc) */                                    \
