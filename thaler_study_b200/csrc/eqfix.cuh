@@ -227,6 +227,21 @@ __global__ void __launch_bounds__(kThreads) k_mle_eval_fused(FieldDesc f, PointA
     uint64_t* const t1 = eq_sm + ((size_t)N << LB);
     uint64_t* const t2 = t1 + ((size_t)N << SUB);
     uint64_t* const t3 = t2 + ((size_t)N << SUB);
+    const int lane = threadIdx.x & 31;
+    const uint64_t n_rows = 1ull << (v_local - LB);
+    const uint64_t n_warps = (uint64_t)gridDim.x * (kThreads / 32);
+    // one-limb fields: the loads of a warp's first row are issued BEFORE the eq tables are built, and every later row is
+    // loaded while the previous one is multiplied (register double buffer) -- at 2^24 entries a warp only sees ~7 rows, so
+    // a load-wait-compute chain per row left the kernel latency-bound (38 us for a 21 us read)
+    constexpr int JL1 = A::N == 1 ? (1 << LB) / 128 : 1;  // 256-bit loads per lane per row
+    uint64_t wn[JL1][4];
+    uint64_t row_n = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    if constexpr (N == 1) {
+        if (row_n < n_rows) {
+#pragma unroll
+            for (int j = 0; j < JL1; ++j) ld_words<4>(evals + ((row_n << LB) + (size_t)(j * 32 + lane) * 4), wn[j]);
+        }
+    }
     {  // thread group g (64 threads) doubles table g: g = 0 the low table, 1..3 the high sub-tables
         const uint32_t g = threadIdx.x >> 6, tid = threadIdx.x & 63;
         uint64_t* const tg = g == 0 ? eq_sm : (g == 1 ? t1 : (g == 2 ? t2 : t3));
@@ -253,18 +268,22 @@ __global__ void __launch_bounds__(kThreads) k_mle_eval_fused(FieldDesc f, PointA
     }
     typename A::Acc acc[1];
     ar.acc_zero(acc[0]);
-    const int lane = threadIdx.x & 31;
-    const uint64_t n_rows = 1ull << (v_local - LB);
-    const uint64_t n_warps = (uint64_t)gridDim.x * (kThreads / 32);
     const uint64_t m1 = (1ull << b1) - 1, m2 = (1ull << b2) - 1;
     for (uint64_t row = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); row < n_rows; row += n_warps) {
         const uint64_t* src = evals + ((row << LB) * N);
         typename A::Lz s;
         if constexpr (N == 1) {
-            constexpr int JL = (1 << LB) / 128;  // 256-bit loads per lane per row
+            constexpr int JL = JL1;
             uint64_t w[JL][4];
 #pragma unroll
-            for (int j = 0; j < JL; ++j) ld_words<4>(src + (size_t)(j * 32 + lane) * 4, w[j]);
+            for (int j = 0; j < JL; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) w[j][e] = wn[j][e];
+            row_n = row + n_warps;
+            if (row_n < n_rows) {
+#pragma unroll
+                for (int j = 0; j < JL; ++j) ld_words<4>(evals + ((row_n << LB) + (size_t)(j * 32 + lane) * 4), wn[j]);
+            }
 #pragma unroll
             for (int j = 0; j < JL; ++j)
 #pragma unroll
