@@ -23,9 +23,11 @@ from oracle.coracle import CField  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--resident", action="store_true")
 ap.add_argument("--variants", action="store_true", help="also the cp.async / TMA variants of the pair kernels")
+ap.add_argument("--only-g4", action="store_true", help="only the 4-limb kernels, every generation")
 a = ap.parse_args()
 
 BLS = O.BLS12_381_FR.p
+BN254 = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 checks = 0
 
 
@@ -78,7 +80,19 @@ def main():
         T.set_option("tail_vars", 0)
     variants = [{}]
     if a.variants:
-        variants += [{"pair_stage": 1}, {"grid_tma": 1}, {"grid_pf": 0}, {"pairs": 0}, {"packed": 0}, {"g4_kernel": 0}]
+        variants += [{"pair_stage": 1}, {"grid_tma": 1}, {"grid_pf": 0}, {"pairs": 0}, {"packed": 0}, {"g4_kernel": 0}, {"g4_kernel": 1}, {"g4_p0one": 0}]
+    if a.only_g4:  # the 4-limb kernels alone: wide accumulators (p = 1 mod 2^32 variant and generic), carry chains, radix 2^29
+        for var in ({}, {"g4_p0one": 0}, {"g4_kernel": 1}, {"g4_kernel": 2}):
+            for k_, v_ in var.items():
+                T.set_option(k_, v_)
+            tag = ",".join(f"{k}={v}" for k, v in var.items()) or "default"
+            for p, v, K in ((BLS, 11, 3), (BLS, 7, 2), (BLS, 9, 4), (BN254, 10, 3)):
+                product_case(p, v, K, f"[{tag}] p{p.bit_length()} v{v} K{K}")
+            T.reset_options()
+            T.set_option("pair_resident", 0)
+            T.set_option("tail_vars", 0)
+        print(f"sanitize_run (4-limb only): {checks} checks passed")
+        sys.exit(0)
     for var in variants:
         for k_, v_ in var.items():
             T.set_option(k_, v_)
@@ -86,7 +100,7 @@ def main():
         for p, v, K in ((1572869, 13, 3), (1572869, 9, 4), (389, 10, 2), (5, 8, 3), (0xFFFFFFFF00000001, 11, 3), (BLS, 11, 3), (BLS, 7, 2)):
             product_case(p, v, K, f"[{tag}] p{p.bit_length()} v{v} K{K}")
         for k_ in var:
-            T.set_option(k_, {"grid_pf": 1, "pairs": 1, "packed": 1, "g4_kernel": 1}.get(k_, 0))
+            T.set_option(k_, {"grid_pf": 1, "pairs": 1, "packed": 1, "g4_kernel": 3, "g4_p0one": 1}.get(k_, 0))
     # matmul G::new (relabel / eq-table fixes), triangle (tiled matmul + folds), GKR W
     OF, F = O.FP1572869, T.Field(1572869)
     rnd = random.Random(3)

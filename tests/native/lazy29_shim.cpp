@@ -41,4 +41,16 @@ void l29_mont(const Desc29* d, const uint32_t* a, const uint32_t* b, uint32_t* o
     L9 r = carry_cols(t);
     for (int j = 0; j < NL; ++j) out[j] = r.l[j];
 }
+// product-scanning forms: mode bit 0 = p0one variant, bit 1 = digit-split instead of rippled carries
+void l29_mont_ps(const Desc29* d, const uint32_t* a, const uint32_t* b, int mode, uint32_t* out, uint64_t* max_col) {
+    L9 x, y;
+    for (int j = 0; j < NL; ++j) { x.l[j] = a[j]; y.l[j] = b[j]; }
+    uint64_t t[NL - 1];
+    if (mode & 1) mont_ps_cols<true>(*d, x, y, t); else mont_ps_cols<false>(*d, x, y, t);
+    uint64_t m = 0;
+    for (int j = 0; j < NL - 1; ++j) m = t[j] > m ? t[j] : m;
+    *max_col = m;
+    L9 r = (mode & 2) ? split_cols8(t) : carry_cols8(t);
+    for (int j = 0; j < NL; ++j) out[j] = r.l[j];
+}
 }

@@ -109,3 +109,28 @@ def test_mont_and_lazy_difference(lib, p):
     assert val(out) % p == val(nrm) * val(big) * rinv % p
     worst = max(worst, mc.value)
     assert worst < 0.76 * 2**64, worst / 2**64  # 9 (2^29 2^31 + 2^58) + carries = 0.70 * 2^64: the columns never wrap
+
+
+@pytest.mark.parametrize("p", [BLS, BN254, P255])
+def test_product_scanning_forms(lib, p):
+    """mont_ps / mont_ps_par (scripts/mont29_bench.cu measures them on the GPU): same value as the interleaved form,
+    the digit-split result with limbs below 2^30 + 2^6, and the p = 1 (mod 2^29) variant wherever the modulus allows."""
+    d = desc(lib, p)
+    rnd = random.Random(5)
+    rinv = pow(1 << 261, -1, p)
+    modes = [0, 2] + ([1, 3] if p % (1 << 29) == 1 else [])
+    cases = [(0, 0), (p - 1, p - 1), (1, p - 1)] + [(rnd.randrange(p), rnd.randrange(p)) for _ in range(200)]
+    for a, b in cases:
+        for mode in modes:
+            out, mc = (C.c_uint32 * 9)(), C.c_uint64()
+            lib.l29_mont_ps(C.byref(d), arr(limbs_of(a)), arr(limbs_of(b)), mode, out, C.byref(mc))
+            v = val(out)
+            assert v % p == a * b * rinv % p and v < a * b // (1 << 261) + p + 1, (mode, a, b)
+            if mode & 2:
+                assert all(l < (1 << 30) + (1 << 6) for l in list(out)[:8])
+                # a digit-split result is a valid operand of the next product
+                out2 = (C.c_uint32 * 9)()
+                lib.l29_mont_ps(C.byref(d), out, arr(limbs_of(b)), mode, out2, C.byref(mc))
+                assert val(out2) % p == v * b * rinv % p and mc.value < 0.9 * 2**64
+            else:
+                assert all(l <= M29 for l in list(out)[:8])
