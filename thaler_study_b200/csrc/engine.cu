@@ -656,6 +656,17 @@ static int eval_table_fused(Ctx* c, const FieldImpl& f, const Table& t, const ui
     PointArg pa;
     std::memset(&pa, 0, sizeof pa);
     std::memcpy(pa.w, bitpt, (size_t)8 * N * v_total);
+    if (f.policy == POL_G4 && opt(OPT_g4_kernel) == 3 && f.d.bits <= 255) {
+        // 4-limb fields: the same launch with unreduced products in 544-bit register accumulators (g4_mle.cuh)
+        const cudaError_t le = launch_mle_eval_fused_g4(opt(OPT_g4_p0one) != 0 && g4_p0one(f.d), c->sms, g_stream, f.d, pa, t.buf->ptr, t.nv, v_total, row0,
+                                                        c->partials, c->ticket, res, peer_arg(c), kMaxGrid);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (le != cudaSuccess) {
+            set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(le), __FILE__, __LINE__);
+            return SCB_ECUDA;
+        }
+        return SCB_OK;
+    }
     DISPATCH_POLICY(f.policy, {
         auto kern = k_mle_eval_fused<A>;
         constexpr size_t smem = MleFusedCfg<A>::smem_bytes;

@@ -4,6 +4,7 @@
 
 #include "g4.cuh"
 #include "g29.cuh"
+#include "g4_mle.cuh"
 #include "g4_launch.hpp"
 
 namespace scb {
@@ -233,6 +234,26 @@ cudaError_t launch_round_evals_g4w(int K, bool p0one, int blocks_per_sm_cap, int
         default: return cudaErrorInvalidValue;
     }
 #undef SCB_RW
+}
+
+// ---- MLE evaluation of a 4-limb table with unreduced products (g4_mle.cuh)
+template <bool P0ONE>
+static cudaError_t launch_mle(int sms, cudaStream_t stream, const FieldDesc& f, const PointArg& pt, const uint64_t* evals, uint32_t v_local, uint32_t v_total,
+                              uint64_t row0, uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid) {
+    auto kern = g4::k_mle_eval_fused_g4<P0ONE>;
+    constexpr size_t smem = MleFusedCfg<PolGN<4>>::smem_bytes;
+    static int nb_cached = 0;
+    int grid = 1;
+    const uint64_t n_rows = (1ull << v_local) >> MleFusedCfg<PolGN<4>>::LB;
+    const cudaError_t e = wide_grid(kern, nb_cached, smem, 0, sms, n_rows * 32, max_grid, &grid);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kThreads, smem, stream>>>(f, pt, evals, v_local, v_total, row0, partials, ticket, res, pa);
+    return cudaGetLastError();
+}
+cudaError_t launch_mle_eval_fused_g4(bool p0one, int sms, cudaStream_t stream, const FieldDesc& f, const PointArg& pt, const uint64_t* evals, uint32_t v_local,
+                                     uint32_t v_total, uint64_t row0, uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid) {
+    return p0one ? launch_mle<true>(sms, stream, f, pt, evals, v_local, v_total, row0, partials, ticket, res, pa, max_grid)
+                 : launch_mle<false>(sms, stream, f, pt, evals, v_local, v_total, row0, partials, ticket, res, pa, max_grid);
 }
 
 cudaError_t launch_fold_round_g4(int K, int minb, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,

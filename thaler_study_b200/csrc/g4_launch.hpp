@@ -4,6 +4,7 @@
 
 #include <cstdint>
 
+#include "eqfix.cuh"
 #include "kernels.cuh"
 
 namespace scb {
@@ -42,5 +43,10 @@ cudaError_t launch_fold_round_g4w(int K, bool p0one, int blocks_per_sm_cap, int 
                                   const PeerArg& pa, int max_grid);
 cudaError_t launch_round_evals_g4w(int K, bool p0one, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
                                    uint64_t n_pairs, uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid);
+
+// MLE evaluation of a 4-limb table in one launch with unreduced products (g4_mle.cuh); arguments as k_mle_eval_fused.
+// Needs f.bits <= 255 (the unreduced sums are sized on p < 2^255).
+cudaError_t launch_mle_eval_fused_g4(bool p0one, int sms, cudaStream_t stream, const FieldDesc& f, const PointArg& pt, const uint64_t* evals, uint32_t v_local,
+                                     uint32_t v_total, uint64_t row0, uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid);
 
 }  // namespace scb
