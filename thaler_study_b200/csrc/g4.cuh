@@ -424,8 +424,8 @@ __device__ __forceinline__ W8 wacc_reduce(const ArithT<P0ONE>& ar, const FieldDe
 }
 
 // Fused fold + message with a claim (as k_fold_round_g4): sums S_0, S_inf, S_2 .. S_{K-1}, canonical.
-template <int K, bool P0ONE>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int K, bool P0ONE, int MINB = 2>
+__global__ void __launch_bounds__(kThreads, MINB)
     k_fold_round_g4w(FieldDesc f, TabsIn<K> in, TabsOut<K> outp, ElemArg rarg, uint64_t n_quads, uint64_t* partials, unsigned int* ticket,
                      uint64_t* out, PeerArg peer) {
     static_assert(K >= 2, "K = 1 has no product to defer");
@@ -483,8 +483,8 @@ __global__ void __launch_bounds__(kThreads, 2)
 // matrix-multiplication/src/lib.rs:110-122, generalised to K tables) in the same arithmetic.  No claim exists yet, so
 // X = 1 is summed too: K + 1 sums in the order S_0, S_inf, S_2 .. S_{K-1}, S_1 (the host rebuilds g(0..K), engine.cu).
 // One hypercube pair of every table per thread-iteration; 64 K + 64 instead of 128 K wide multiply-adds per point.
-template <int K, bool P0ONE>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int K, bool P0ONE, int MINB = 2>
+__global__ void __launch_bounds__(kThreads, MINB)
     k_round_evals_g4w(FieldDesc f, TabsIn<K> in, uint64_t n_pairs, uint64_t* partials, unsigned int* ticket, uint64_t* out, PeerArg peer) {
     static_assert(K >= 2, "K = 1 has no product to defer");
     constexpr int NS = n_sums(K) + 1;

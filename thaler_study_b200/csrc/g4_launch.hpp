@@ -36,6 +36,7 @@ cudaError_t launch_round_evals_g29(int K, int blocks_per_sm_cap, int sms, cudaSt
 // 544-bit shared-memory accumulators; p0one selects the variant for moduli that are 1 modulo 2^32 (g4_p0one).  K = 2..4.
 // launch_fold_round_g4w: sums S_0, S_inf, S_2 .. S_{K-1} like launch_fold_round_g4; launch_round_evals_g4w: K + 1 sums in
 // the order S_0, S_inf, S_2 .. S_{K-1}, S_1 (no claim in round 0).
+extern int g_g4w_minb;  // 1: K = 3, p = 1 (mod 2^32) kernels compiled for one resident CTA per SM (option g4_blocks = 1; measured variant)
 bool g4w_supported(const FieldDesc& f, int K);
 bool g4_p0one(const FieldDesc& f);
 cudaError_t launch_fold_round_g4w(int K, bool p0one, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
