@@ -705,9 +705,11 @@ def generic_roofline(T, torch, F, g, v, K, p, ms, steps, res_stats, world):
     g4_on = g4_mode != 0
     modmuls_executed = ((2 * K + K * (K - 1)) if g4_on else (2 * K + (K + 1) * (K - 1))) * (1 << v) / 4.0  # g4.cuh skips one point
     wide_executed = modmuls_executed * imads_per_mul
-    if g4_mode == 3 and K >= 2:  # last product of each point unreduced (64), p = 1 mod 2^32: 120 per reduced product
-        red = 120 if (p & 0xFFFFFFFF) == 1 and T.get_option("g4_p0one") else 128
-        wide_executed = ((2 * K + K * (K - 2)) * red + K * 64) * (1 << v) / 4.0
+    if g4_mode == 3 and K >= 2:
+        # last product of each point unreduced (64); p = 1 mod 2^32: 120 per reduced product; folds with the pass's table: 80 / 78
+        p0one = (p & 0xFFFFFFFF) == 1 and T.get_option("g4_p0one")
+        red, fold = (120, 78) if p0one else (128, 80)
+        wide_executed = (2 * K * fold + K * (K - 2) * red + K * 64) * (1 << v) / 4.0
     modmuls_proof = (K * K + K - 1) * float(1 << v)
     t_int_launch = modmuls_launch * imads_per_mul / imad_peak
     t_hbm_launch = alg_bytes / (peak * 1e9)

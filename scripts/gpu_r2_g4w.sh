@@ -1,8 +1,8 @@
 #!/bin/bash
-# round 2: fourth-generation 4-limb kernels (wide accumulators, p = 1 mod 2^32 variant) -- parity, then the BLS12-381 Fr proof
+# round 2: fourth-generation 4-limb kernels (wide accumulators, p = 1 mod 2^32 variant, fixed-multiplier folds) -- parity, then the BLS12-381 Fr proof
 set -u
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_g4.py tests/test_gpu_trait_path.py -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r2w_pytest_g4.log
+timeout 1200 python -m pytest tests/test_gpu_g4.py tests/test_gpu_trait_path.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r2w_pytest_g4.log
 tail -4 gpurun_out/r2w_pytest_g4.log
 BLS=52435875175126190479447740508185965837690552500527637822603658699938581184513
 for cfg in "3 1" "3 0" "1 1"; do set -- $cfg
@@ -15,4 +15,3 @@ try:
 except Exception as e: print("failed",e)
 PY
 done
-cd scripts && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/imad_chain imad_chain.cu 2>/dev/null && /tmp/imad_chain > ../gpurun_out/r2w_imad_chain.jsonl; cat ../gpurun_out/r2w_imad_chain.jsonl | cut -c1-200

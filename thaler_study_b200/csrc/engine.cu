@@ -1371,7 +1371,21 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
         cudaError_t le;
         if (usew) {
             g_g4w_minb = opt(OPT_g4_blocks) == 1 ? 1 : 2;
-            le = launch_fold_round_g4w((int)K, opt(OPT_g4_p0one) != 0 && g4_p0one(f.d), (int)opt(OPT_bps), c->sms, g_stream, f.d, in, o, elem_arg(f, r),
+            // fold table of the challenge: t[i] = r 2^(32 i + 64) mod p as plain integers (64 + 7 x 32 modular doublings)
+            g4::FoldTab ft;
+            {
+                Fe rr;
+                f.h.load(r, rr);
+                Fe x = f.h.from_mont(rr);
+                for (int i = 0; i < 8; ++i) {
+                    for (int s = 0; s < (i == 0 ? 64 : 32); ++s) x = f.h.double_raw(x);
+                    for (int q = 0; q < 4; ++q) {
+                        ft.t[i][2 * q] = (uint32_t)x.l[q];
+                        ft.t[i][2 * q + 1] = (uint32_t)(x.l[q] >> 32);
+                    }
+                }
+            }
+            le = launch_fold_round_g4w((int)K, opt(OPT_g4_p0one) != 0 && g4_p0one(f.d), (int)opt(OPT_bps), c->sms, g_stream, f.d, in, o, ft,
                                        p->t[0].len() / 4, c->partials, c->ticket, c->h_res, peer_arg(c), kMaxGrid);
         } else if (use29) {
             Fe rr, r5;

@@ -173,7 +173,7 @@ static cudaError_t wide_grid(Kern kern, int& nb_cached, size_t smem, int blocks_
 }
 template <int K, bool P0ONE, int MINB = 2>
 static cudaError_t launch_kw(int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in, uint64_t* const* outp,
-                             const ElemArg& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid) {
+                             const g4::FoldTab& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid) {
     auto kern = g4::k_fold_round_g4w<K, P0ONE, MINB>;
     const size_t smem = g4::wacc_smem_bytes(g4::n_sums(K));
     static int nb_cached = 0;
@@ -208,7 +208,7 @@ bool g4_p0one(const FieldDesc& f) { return (uint32_t)f.p[0] == 1u; }
 
 int g_g4w_minb = 2;  // experiment: 1 = the K = 3 kernels compiled for one resident CTA per SM (255 registers)
 cudaError_t launch_fold_round_g4w(int K, bool p0one, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
-                                  uint64_t* const* outp, const ElemArg& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res,
+                                  uint64_t* const* outp, const g4::FoldTab& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res,
                                   const PeerArg& pa, int max_grid) {
     if (g_g4w_minb == 1 && K == 3 && p0one) return launch_kw<3, true, 1>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid);
 #define SCB_KW(KK)                                                                                                                          \

@@ -27,6 +27,7 @@
 #pragma once
 #include <cstdint>
 
+#include "g4_types.hpp"
 #include "kernels.cuh"
 
 namespace scb {
@@ -207,6 +208,54 @@ struct ArithT {
               "r"(A1[0]), "r"(A1[1]), "r"(A1[2]), "r"(A1[3]), "r"(A1[4]), "r"(A1[5]), "r"(A1[6]), "r"(A1[7]), "r"(A1[8]), "r"(A1[9]), "r"(A1[10]),
               "r"(A1[11]), "r"(A1[12]), "r"(A1[13]), "r"(A1[14]));
     }
+    // r * d * 2^-0 for the FIXED r of a fold pass, d any 256-bit integer congruent to the Montgomery-form difference:
+    // d = sum_i d_i 2^(32 i), so r d = sum_i d_i (r 2^(32 i)); with the table t[i] = r 2^(32 i + 64) mod p the eight
+    // rows d_i * t[i] all land on the SAME words (64 multiply-adds, a value below 2^35 p), and two Montgomery word
+    // steps (16, or 14 when p = 1 mod 2^32) divide the 2^64 out again: 80 / 78 multiply-adds instead of 128 / 120, result
+    // below p (1 + 2^-29), unreduced (lo, top).  Same even/odd layout as mul_raw: A0[k] holds word k, A1[k] word k + 1.
+    __device__ __forceinline__ void mul_fixed_raw(uint32_t (&lo)[8], uint32_t& top, const FoldTab& ft, const W8& d) const {
+        uint32_t A0[12], A1[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) A0[i] = A1[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            chain(A1, ft.t[i][1], ft.t[i][3], ft.t[i][5], ft.t[i][7], d.w[i]);
+            chain(A0, ft.t[i][0], ft.t[i][2], ft.t[i][4], ft.t[i][6], d.w[i]);
+        }
+        {  // word 0
+            const uint32_t m = A0[0] * n0;
+            chain(A1, p[1], p[3], p[5], p[7], m);
+            if constexpr (P0ONE) chain_p0one(A0, p[2], p[4], p[6], m);
+            else chain(A0, p[0], p[2], p[4], p[6], m);
+        }
+        {  // word 1 = A0[1] + A1[0]
+            const uint32_t m = (A0[1] + A1[0]) * n0;
+            chain(A0 + 2, p[1], p[3], p[5], p[7], m);
+            if constexpr (P0ONE) chain_p0one(A1, p[2], p[4], p[6], m);
+            else chain(A1, p[0], p[2], p[4], p[6], m);
+        }
+        uint32_t sink;  // word 1 is now 0 (mod 2^32); its carry starts the final add
+        asm("add.cc.u32  %9, %10, %11;\n\t"
+            "addc.cc.u32 %0, %12, %21;\n\t"
+            "addc.cc.u32 %1, %13, %22;\n\t"
+            "addc.cc.u32 %2, %14, %23;\n\t"
+            "addc.cc.u32 %3, %15, %24;\n\t"
+            "addc.cc.u32 %4, %16, %25;\n\t"
+            "addc.cc.u32 %5, %17, %26;\n\t"
+            "addc.cc.u32 %6, %18, %27;\n\t"
+            "addc.cc.u32 %7, %19, %28;\n\t"
+            "addc.u32    %8, %20, 0;\n\t"
+            : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]), "=r"(lo[4]), "=r"(lo[5]), "=r"(lo[6]), "=r"(lo[7]), "=r"(top), "=r"(sink)
+            : "r"(A0[1]), "r"(A1[0]),
+              "r"(A0[2]), "r"(A0[3]), "r"(A0[4]), "r"(A0[5]), "r"(A0[6]), "r"(A0[7]), "r"(A0[8]), "r"(A0[9]), "r"(A0[10]),
+              "r"(A1[1]), "r"(A1[2]), "r"(A1[3]), "r"(A1[4]), "r"(A1[5]), "r"(A1[6]), "r"(A1[7]), "r"(A1[8]));
+    }
+    // t0 + r * (t1 - t0) with the pass's table, canonical
+    __device__ __forceinline__ W8 fold_fixed(const W8& t0, const W8& t1, const FoldTab& ft) const {
+        uint32_t lo[8], top;
+        mul_fixed_raw(lo, top, ft, diff_lazy(t1, t0));
+        return add(t0, reduce_once(lo, top));
+    }
     // (lo, top) < 2p  ->  canonical
     __device__ __forceinline__ W8 reduce_once(const uint32_t (&lo)[8], uint32_t top) const {
         uint32_t d[8];
@@ -361,7 +410,9 @@ __global__ void __launch_bounds__(kThreads, MINB)
 //   * the LAST product of every message point is not reduced at all: its 512-bit integer value prod * fac goes into a
 //     544-bit accumulator (64 wide multiply-adds instead of 128), and each thread does ONE Montgomery reduction per
 //     accumulator at the end (REDC is linear: sum REDC(x_i) = REDC(sum x_i) mod p);
-//   * moduli with p = 1 (mod 2^32) skip the n0 multiplication and the p[0] column of every reduction (ArithT<true>).
+//   * moduli with p = 1 (mod 2^32) skip the n0 multiplication and the p[0] column of every reduction (ArithT<true>);
+//   * the fold's multiplier r is the same for the whole pass: with a host-built table of r 2^(32 i + 64) mod p the
+//     product r d is eight rows on the same words plus two reduction steps (mul_fixed_raw): 80 / 78 instead of 128 / 120.
 // The accumulators (17 words each) would not fit the 128-register budget of two resident CTAs per SM, so they live in
 // shared memory: 5 x 128-bit per thread and sum, 80-byte stride (bank-conflict-free for 128-bit accesses), read, added to
 // and written back once per product.  K >= 2 (K = 1 has no product to defer; the host keeps k_fold_round_g4 for it).
@@ -426,13 +477,12 @@ __device__ __forceinline__ W8 wacc_reduce(const ArithT<P0ONE>& ar, const FieldDe
 // Fused fold + message with a claim (as k_fold_round_g4): sums S_0, S_inf, S_2 .. S_{K-1}, canonical.
 template <int K, bool P0ONE, int MINB = 2>
 __global__ void __launch_bounds__(kThreads, MINB)
-    k_fold_round_g4w(FieldDesc f, TabsIn<K> in, TabsOut<K> outp, ElemArg rarg, uint64_t n_quads, uint64_t* partials, unsigned int* ticket,
+    k_fold_round_g4w(FieldDesc f, TabsIn<K> in, TabsOut<K> outp, FoldTab ft, uint64_t n_quads, uint64_t* partials, unsigned int* ticket,
                      uint64_t* out, PeerArg peer) {
     static_assert(K >= 2, "K = 1 has no product to defer");
     constexpr int NS = n_sums(K);
     extern __shared__ uint4 wacc[];
     const ArithT<P0ONE> ar(f);
-    const W8 r = load8(rarg.w);
 #pragma unroll
     for (int x = 0; x < NS; ++x) wacc_zero(wacc_slot(wacc, x));
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -442,8 +492,8 @@ __global__ void __launch_bounds__(kThreads, MINB)
         for (int k = 0; k < K; ++k) {
             uint64_t w[16];
             ld_words<16>(in.p[k] + i * 16, w);
-            const W8 u0 = ar.fold(load8(w), load8(w + 4), r);
-            const W8 u1 = ar.fold(load8(w + 8), load8(w + 12), r);
+            const W8 u0 = ar.fold_fixed(load8(w), load8(w + 4), ft);  // 80 / 78 multiply-adds: the multiplier is the pass's r
+            const W8 u1 = ar.fold_fixed(load8(w + 8), load8(w + 12), ft);
             uint64_t o[8];
             store8(u0, o);
             store8(u1, o + 4);
@@ -482,7 +532,9 @@ __global__ void __launch_bounds__(kThreads, MINB)
 // Round-0 message (Prover::new's pass: sum-check-protocol/src/lib.rs:88-97 with G::to_univariate,
 // matrix-multiplication/src/lib.rs:110-122, generalised to K tables) in the same arithmetic.  No claim exists yet, so
 // X = 1 is summed too: K + 1 sums in the order S_0, S_inf, S_2 .. S_{K-1}, S_1 (the host rebuilds g(0..K), engine.cu).
-// One hypercube pair of every table per thread-iteration; 64 K + 64 instead of 128 K wide multiply-adds per point.
+// One hypercube pair of every table per thread-iteration; 64 K + 64 instead of 128 K wide multiply-adds per point, and for
+// K = 3 the first-level product at X = 2 comes from the other three by additions (the product of two linear factors is
+// quadratic): 3 reduced + 4 unreduced products per pair.
 template <int K, bool P0ONE, int MINB = 2>
 __global__ void __launch_bounds__(kThreads, MINB)
     k_round_evals_g4w(FieldDesc f, TabsIn<K> in, uint64_t n_pairs, uint64_t* partials, unsigned int* ticket, uint64_t* out, PeerArg peer) {
@@ -511,11 +563,19 @@ __global__ void __launch_bounds__(kThreads, MINB)
                 if (k == 0) {
                     prod[x] = fac[x];
                 } else if (k < K - 1) {
-                    prod[x] = ar.mul(prod[x], fac[x]);
+                    // K = 3: q(X) = a(X) b(X) is quadratic, so its value at X = 2 follows from the three products at
+                    // 0, inf and 1 by additions (below) -- one reduced product fewer per pair
+                    if (!(K == 3 && x == 2)) prod[x] = ar.mul(prod[x], fac[x]);
                 } else {
                     uint32_t t[16];
                     ar.mul_wide(t, prod[x], fac[x]);
                     wacc_add(wacc_slot(wacc, x), t);
+                }
+            }
+            if constexpr (K == 3) {
+                if (k == 1) {  // q(2) = q(0) + 2 q_1 + 4 q(inf) with q_1 = q(1) - q(0) - q(inf):  2 q(1) - q(0) + 2 q(inf)
+                    const W8 s1 = ar.add(prod[3], prod[1]);  // q(1) + q(inf)   (sums: 0 -> X = 0, 1 -> inf, 2 -> X = 2, 3 -> X = 1)
+                    prod[2] = ar.sub(ar.add(s1, s1), prod[0]);
                 }
             }
         }

@@ -5,6 +5,7 @@
 #include <cstdint>
 
 #include "eqfix.cuh"
+#include "g4_types.hpp"
 #include "kernels.cuh"
 
 namespace scb {
@@ -34,13 +35,14 @@ cudaError_t launch_round_evals_g29(int K, int blocks_per_sm_cap, int sms, cudaSt
 
 // Fourth generation (g4.cuh, "wide accumulators"): the last product of every message point is accumulated unreduced in
 // 544-bit shared-memory accumulators; p0one selects the variant for moduli that are 1 modulo 2^32 (g4_p0one).  K = 2..4.
-// launch_fold_round_g4w: sums S_0, S_inf, S_2 .. S_{K-1} like launch_fold_round_g4; launch_round_evals_g4w: K + 1 sums in
+// launch_fold_round_g4w: sums S_0, S_inf, S_2 .. S_{K-1} like launch_fold_round_g4, the challenge as its fold table
+// (g4_types.hpp); launch_round_evals_g4w: K + 1 sums in
 // the order S_0, S_inf, S_2 .. S_{K-1}, S_1 (no claim in round 0).
 extern int g_g4w_minb;  // 1: K = 3, p = 1 (mod 2^32) kernels compiled for one resident CTA per SM (option g4_blocks = 1; measured variant)
 bool g4w_supported(const FieldDesc& f, int K);
 bool g4_p0one(const FieldDesc& f);
 cudaError_t launch_fold_round_g4w(int K, bool p0one, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
-                                  uint64_t* const* outp, const ElemArg& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res,
+                                  uint64_t* const* outp, const g4::FoldTab& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res,
                                   const PeerArg& pa, int max_grid);
 cudaError_t launch_round_evals_g4w(int K, bool p0one, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
                                    uint64_t n_pairs, uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid);

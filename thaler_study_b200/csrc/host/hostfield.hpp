@@ -176,6 +176,9 @@ class HostField {
         for (uint32_t i = 0; i < n; ++i) w[i] = a.l[i];
     }
 
+    // 2a mod p on RAW (non-Montgomery) limbs: lets a caller build r 2^k mod p tables as plain integers (engine.cu: fold table)
+    Fe double_raw(const Fe& a) const { return dbl_raw(a); }
+
    private:
     bool geq_p(const Fe& a) const {
         for (int i = (int)n - 1; i >= 0; --i) {
