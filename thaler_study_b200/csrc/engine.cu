@@ -1242,7 +1242,7 @@ static int round_evals_impl(const scb_poly* p, uint32_t n_points, uint64_t* h_ou
         const uint32_t K = (uint32_t)p->t.size();
         const uint64_t* in[kMaxTables];
         for (uint32_t k = 0; k < K; ++k) in[k] = p->t[k].buf->ptr;
-        g_g4w_minb = opt(OPT_g4_blocks) == 1 ? 1 : 2;
+        g_g4w_minb = (int)opt(OPT_g4_blocks4);
         const cudaError_t le = launch_round_evals_g4w((int)K, opt(OPT_g4_p0one) != 0 && g4_p0one(f.d), (int)opt(OPT_bps), c->sms, g_stream, f.d, in,
                                                       p->t[0].len() / 2, c->partials, c->ticket, c->h_res, peer_arg(c), kMaxGrid);
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1370,7 +1370,7 @@ static int fix_and_round_impl(const scb_poly* p, const uint64_t* r, uint32_t n_p
         const bool usew = opt(OPT_g4_kernel) == 3 && g4w_supported(f.d, (int)K);
         cudaError_t le;
         if (usew) {
-            g_g4w_minb = opt(OPT_g4_blocks) == 1 ? 1 : 2;
+            g_g4w_minb = (int)opt(OPT_g4_blocks4);
             // fold table of the challenge: t[i] = r 2^(32 i + 64) mod p as plain integers (64 + 7 x 32 modular doublings)
             g4::FoldTab ft;
             {

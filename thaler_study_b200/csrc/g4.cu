@@ -206,11 +206,17 @@ static cudaError_t launch_rw(int blocks_per_sm_cap, int sms, cudaStream_t stream
 bool g4w_supported(const FieldDesc& f, int K) { return f.n == 4 && f.bits <= 255 && K >= 2 && K <= 4; }
 bool g4_p0one(const FieldDesc& f) { return (uint32_t)f.p[0] == 1u; }
 
-int g_g4w_minb = 2;  // experiment: 1 = the K = 3 kernels compiled for one resident CTA per SM (255 registers)
+int g_g4w_minb = 0;  // 0: measured defaults (K = 3 fold kernel: 3 resident CTAs per SM, 80 registers -- 10.16 against 10.66 ms at 2^28 x 3;
+                     // everything else 2); 1 / 2 / 3 force the K = 3 variants (option g4_blocks; profiles/r02_mont29.md)
 cudaError_t launch_fold_round_g4w(int K, bool p0one, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,
                                   uint64_t* const* outp, const g4::FoldTab& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res,
                                   const PeerArg& pa, int max_grid) {
-    if (g_g4w_minb == 1 && K == 3 && p0one) return launch_kw<3, true, 1>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid);
+    if (K == 3) {
+        const int mb = g_g4w_minb == 0 ? 3 : g_g4w_minb;
+        if (mb == 1 && p0one) return launch_kw<3, true, 1>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid);
+        if (mb == 3) return p0one ? launch_kw<3, true, 3>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid)
+                                  : launch_kw<3, false, 3>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid);
+    }
 #define SCB_KW(KK)                                                                                                                          \
     case KK:                                                                                                                                \
         return p0one ? launch_kw<KK, true>(blocks_per_sm_cap, sms, stream, f, in, outp, r, n_quads, partials, ticket, res, pa, max_grid)   \

@@ -38,7 +38,7 @@ cudaError_t launch_round_evals_g29(int K, int blocks_per_sm_cap, int sms, cudaSt
 // launch_fold_round_g4w: sums S_0, S_inf, S_2 .. S_{K-1} like launch_fold_round_g4, the challenge as its fold table
 // (g4_types.hpp); launch_round_evals_g4w: K + 1 sums in
 // the order S_0, S_inf, S_2 .. S_{K-1}, S_1 (no claim in round 0).
-extern int g_g4w_minb;  // 1: K = 3, p = 1 (mod 2^32) kernels compiled for one resident CTA per SM (option g4_blocks = 1; measured variant)
+extern int g_g4w_minb;  // option g4_blocks4: resident CTAs per SM the K = 3 kernels are compiled for (0: measured defaults)
 bool g4w_supported(const FieldDesc& f, int K);
 bool g4_p0one(const FieldDesc& f);
 cudaError_t launch_fold_round_g4w(int K, bool p0one, int blocks_per_sm_cap, int sms, cudaStream_t stream, const FieldDesc& f, const uint64_t* const* in,

@@ -37,7 +37,8 @@ namespace scb {
                                   shared-memory accumulators, round 0 included (g4.cuh, K >= 2); 1 = carry chains, one point fewer      \
                                   (14.7 ms per 2^28 x 3 launch); 2 = radix-2^29 lazy carries (g29.cuh: 20.8 ms); 0 = round 1's (18.2 ms) */ \
     X(g4_p0one, 1)             /* g4_kernel 3: use the p = 1 (mod 2^32) variant when the modulus allows (0: always the generic one) */   \
-    X(g4_blocks, 2)            /* 4-limb kernels: variant compiled for 2 or 3 resident CTAs per SM */                       \
+    X(g4_blocks, 2)            /* 4-limb kernels of generations 1-2: variant compiled for 2 or 3 resident CTAs per SM */     \
+    X(g4_blocks4, 0)           /* g4_kernel 3, K = 3: 0 = measured defaults (fold kernel 3 CTAs per SM, round 0 two), 1..3 force */ \
     X(tri_tiled, 1)            /* triangle x-phase as a shared-memory tiled field matmul */                                 \
     X(host_pack, 1)            /* narrowing upload of host tables (upload_engine.inc) */                                    \
     X(host_pack_threads, 0)    /* pack threads; 0: hardware threads / local_ranks */                                        \
