@@ -711,20 +711,32 @@ def generic_roofline(T, torch, F, g, v, K, p, ms, steps, res_stats, world):
         red, fold = (120, 78) if p0one else (128, 80)
         wide_executed = (2 * K * fold + K * (K - 2) * red + K * 64) * (1 << v) / 4.0
     modmuls_proof = (K * K + K - 1) * float(1 << v)
-    t_int_launch = modmuls_launch * imads_per_mul / imad_peak
+    # The integer bound is taken on the multiply-adds the best formulation in this repo needs (what the kernels execute):
+    # SURVEY's count -- (K^2 + K - 1) 2^v modmuls x 128 -- is reported next to it as `survey_count_*`; the kernels need
+    # fewer (one point fewer, unreduced last products, table folds, an interpolated point), so a fraction against the
+    # survey count could exceed 1 and is not what the kernel is judged by.
+    wide_proof = 2.0 * wide_executed + (K + 1) * (K - 1) * imads_per_mul * (1 << v) / 2.0  # later rounds halve: sum = 2 launches; round 0: X = 0..K
+    if g4_mode == 3 and K >= 2:
+        r0 = (3 * red + 4 * 64) if K == 3 else (K + 1) * ((K - 2) * red + 64)  # K = 3: first-level product at X = 2 interpolated
+        wide_proof = 2.0 * wide_executed + r0 * (1 << v) / 2.0
+    t_int_launch = wide_executed / imad_peak
     t_hbm_launch = alg_bytes / (peak * 1e9)
-    t_int_proof = modmuls_proof * imads_per_mul / imad_peak
+    t_int_proof = wide_proof / imad_peak
     t_hbm_proof = proof_bytes / (peak * 1e9)
+    survey_int_launch = modmuls_launch * imads_per_mul / imad_peak
+    survey_int_proof = modmuls_proof * imads_per_mul / imad_peak
     alone = {"kernel": kname + ", 2^%d-entry tables, timed alone" % v,
              "achieved": achieved, "frac": achieved / peak, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
              "traffic": ncu_traffic(tkey, v, K, p),
              "modmuls_per_launch": modmuls_launch, "modmuls_executed_per_launch": modmuls_executed, "imad_wide_per_modmul": imads_per_mul, "imad_wide_peak_per_s": imad_peak,
              "imad_wide_executed_per_launch": wide_executed, "frac_of_fmaheavy_issue_peak": wide_executed / imad_peak / (kms * 1e-3),
              "t_integer_bound_ms": t_int_launch * 1e3, "t_hbm_bound_ms": t_hbm_launch * 1e3,
-             "frac_of_slower_bound": max(t_int_launch, t_hbm_launch) / (kms * 1e-3)}
+             "frac_of_slower_bound": max(t_int_launch, t_hbm_launch) / (kms * 1e-3),
+             "survey_count_t_integer_ms": survey_int_launch * 1e3,
+             "survey_count_note": "SURVEY 8d's modmul count x 128 multiply-adds at the measured multiplier peak; the kernels execute fewer (imad_wide_executed_per_launch), so the bound above is taken on what they execute"}
     proof = {"proof_bytes_moved": proof_bytes, "proof_frac_of_hbm_roofline": (proof_bytes / (ms * 1e-3) / 1e9) / peak,
-             "proof_modmuls": modmuls_proof, "proof_t_integer_bound_ms": t_int_proof * 1e3, "proof_t_hbm_bound_ms": t_hbm_proof * 1e3,
-             "proof_frac_of_slower_bound": max(t_int_proof, t_hbm_proof) / (ms * 1e-3)}
+             "proof_modmuls": modmuls_proof, "proof_imad_wide_executed": wide_proof, "proof_t_integer_bound_ms": t_int_proof * 1e3, "proof_t_hbm_bound_ms": t_hbm_proof * 1e3,
+             "proof_frac_of_slower_bound": max(t_int_proof, t_hbm_proof) / (ms * 1e-3), "proof_survey_count_t_integer_ms": survey_int_proof * 1e3}
     int_bound = t_int_launch > t_hbm_launch
     roof = {"bound": "hbm", "kernel": alone["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": alone["traffic"], "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
@@ -732,7 +744,7 @@ def generic_roofline(T, torch, F, g, v, K, p, ms, steps, res_stats, world):
             "binding_roofline": "integer (IMAD.WIDE)" if int_bound else "hbm",
             "note": "contract fields describe the HBM side; for this policy the integer pipe binds -- see frac_of_slower_bound" if int_bound else None,
             "integer": {k: alone[k] for k in ("modmuls_per_launch", "modmuls_executed_per_launch", "imad_wide_per_modmul", "imad_wide_peak_per_s", "imad_wide_executed_per_launch",
-                                             "frac_of_fmaheavy_issue_peak", "t_integer_bound_ms", "t_hbm_bound_ms", "frac_of_slower_bound")}}
+                                             "frac_of_fmaheavy_issue_peak", "t_integer_bound_ms", "t_hbm_bound_ms", "frac_of_slower_bound", "survey_count_t_integer_ms", "survey_count_note")}}
     if world == 1 and res_stats["launches"] >= steps and res_stats["last_rounds"] > 0:
         res_ms = res_stats["total_ms"] / steps
         roof["resident_kernel"] = {"kernel_ms": res_ms, "rounds_last_launch": res_stats["last_rounds"], "share_of_step": res_ms / ms,

@@ -123,3 +123,33 @@ def test_g4_proof_2_24_matches_c_oracle():
     tabs_c = [cf.synth(s, 0, 1 << v) for s in seeds]
     want_c1, want = oracle_messages(OF, cf, tabs_c, K, transcript)
     assert got_c1 == want_c1 and transcript == want
+
+
+def test_wide_kernels_for_every_resident_cta_count():
+    """The K = 3 kernels of the fourth generation exist in builds for one, two and three resident CTAs per SM (option
+    g4_blocks4; 0 = the measured defaults): same sums, same folded tables, whole transcripts."""
+    p = BLS
+    F, cf, OF = T.Field(p), CField(p), O.BLS12_381_FR
+    rnd = random.Random(11)
+    v, K = 13, 3
+    seeds = [rnd.randrange(1 << 20) for _ in range(K)]
+    tabs_c = [cf.synth(s, 0, 1 << v) for s in seeds]
+    g = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, s) for s in seeds])
+    r = rnd.randrange(p)
+    f_c = [cf.fix_variable(t, cf.to_mont([r])) for t in tabs_c]
+    want = cf.from_mont(cf.product_round_evals(f_c, K + 1))
+    want0 = cf.from_mont(cf.product_round_evals(tabs_c, K + 1))
+    T.set_option("tail_vars", 0)
+    outs = []
+    for blocks in (0, 1, 2, 3):
+        for p0one in (1, 0):
+            T.set_option("g4_blocks4", blocks)
+            T.set_option("g4_p0one", p0one)
+            assert g.round_evals() == want0, (blocks, p0one)
+            g2, ev = g.fix_and_round_evals(r, claim=(want[0] + want[1]) % p)
+            assert ev == want, (blocks, p0one)
+            for k in range(K):
+                assert np.array_equal(g2.table(k).to_evaluations_mont(), f_c[k]), (blocks, p0one)
+            outs.append(T.generate_transcript(T.Prover(g)))
+    assert all(o == outs[0] for o in outs)
+    T.reset_options()
