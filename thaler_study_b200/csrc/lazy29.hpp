@@ -26,6 +26,11 @@
 #else
 #define L29_HD inline
 #endif
+#if defined(__CUDA_ARCH__)
+#define L29_UNROLL _Pragma("unroll")
+#else
+#define L29_UNROLL  // host passes: plain loops (g++ would warn about the unknown pragma)
+#endif
 
 namespace scb {
 namespace l29 {
@@ -49,7 +54,7 @@ struct Desc29 {
 // x < 2^256 as eight 32-bit words -> normalised limbs
 L29_HD L9 from_words(const uint32_t (&w)[8]) {
     L9 r;
-#pragma unroll
+L29_UNROLL
     for (int j = 0; j < NL; ++j) {
         const int bit = 29 * j, q = bit >> 5, s = bit & 31;
         uint32_t v = w[q] >> s;
@@ -63,9 +68,9 @@ L29_HD L9 from_words(const uint32_t (&w)[8]) {
 L29_HD void to_words(const L9& a, uint32_t (&w)[8], uint32_t& top) {
     uint64_t acc = 0;
     int emitted = 0;
-#pragma unroll
+L29_UNROLL
     for (int j = 0; j < NL; ++j) {
-#pragma unroll
+L29_UNROLL
         for (int rep = 0; rep < 2; ++rep) {
             if (emitted < 8 && 32 * (emitted + 1) <= 29 * j) {
                 w[emitted++] = (uint32_t)acc;
@@ -74,7 +79,7 @@ L29_HD void to_words(const L9& a, uint32_t (&w)[8], uint32_t& top) {
         }
         acc += (uint64_t)a.l[j] << (29 * j - 32 * emitted);
     }
-#pragma unroll
+L29_UNROLL
     for (int rep = 0; rep < 8; ++rep) {
         if (emitted < 8) {
             w[emitted++] = (uint32_t)acc;
@@ -87,7 +92,7 @@ L29_HD void to_words(const L9& a, uint32_t (&w)[8], uint32_t& top) {
 L29_HD L9 normalise(const L9& a) {
     L9 r;
     uint32_t c = 0;
-#pragma unroll
+L29_UNROLL
     for (int j = 0; j < NL - 1; ++j) {
         const uint64_t v = (uint64_t)a.l[j] + c;
         r.l[j] = (uint32_t)v & M29;
@@ -98,14 +103,14 @@ L29_HD L9 normalise(const L9& a) {
 }
 L29_HD L9 add(const L9& a, const L9& b) {
     L9 r;
-#pragma unroll
+L29_UNROLL
     for (int j = 0; j < NL; ++j) r.l[j] = a.l[j] + b.l[j];
     return r;
 }
 // a - b + k p for a normalised b below 2^256 (no limb goes negative); value below a + k p
 L29_HD L9 sub_kp(const Desc29& d, const L9& a, const L9& b) {
     L9 r;
-#pragma unroll
+L29_UNROLL
     for (int j = 0; j < NL; ++j) r.l[j] = a.l[j] + d.kp[j] - b.l[j];
     return r;
 }
@@ -113,17 +118,17 @@ L29_HD L9 sub_kp(const Desc29& d, const L9& a, const L9& b) {
 // x y 2^-261 mod p as 64-bit columns (not yet carried): value = sum t[j] 2^(29 j) < x y / 2^261 + p, every t[j] < 2^63.7.
 // Limb bounds: max limb(a) * max limb(b) <= 2^60.2.
 L29_HD void mont_cols(const Desc29& d, const L9& a, const L9& b, uint64_t (&t)[NL]) {
-#pragma unroll
+L29_UNROLL
     for (int j = 0; j < NL; ++j) t[j] = 0;
-#pragma unroll
+L29_UNROLL
     for (int i = 0; i < NL; ++i) {
-#pragma unroll
+L29_UNROLL
         for (int j = 0; j < NL; ++j) t[j] += (uint64_t)a.l[j] * b.l[i];
         const uint32_t m = ((uint32_t)t[0] * d.n0) & M29;
-#pragma unroll
+L29_UNROLL
         for (int j = 0; j < NL; ++j) t[j] += (uint64_t)m * d.p[j];
         const uint64_t c = t[0] >> 29;  // t[0] is a multiple of 2^29 now
-#pragma unroll
+L29_UNROLL
         for (int j = 0; j < NL - 1; ++j) t[j] = t[j + 1];
         t[NL - 1] = 0;
         t[0] += c;
@@ -132,7 +137,7 @@ L29_HD void mont_cols(const Desc29& d, const L9& a, const L9& b, uint64_t (&t)[N
 // columns -> normalised limbs
 L29_HD L9 carry_cols(uint64_t (&t)[NL]) {
     L9 r;
-#pragma unroll
+L29_UNROLL
     for (int j = 0; j < NL - 1; ++j) {
         r.l[j] = (uint32_t)t[j] & M29;
         t[j + 1] += t[j] >> 29;
@@ -157,27 +162,27 @@ L29_HD L9 mont(const Desc29& d, const L9& a, const L9& b) {
 template <bool P0ONE>
 L29_HD void mont_ps_cols(const Desc29& d, const L9& a, const L9& b, uint64_t (&out)[NL - 1]) {
     uint64_t c[2 * NL - 1];
-#pragma unroll
+L29_UNROLL
     for (int k = 0; k < 2 * NL - 1; ++k) c[k] = 0;
-#pragma unroll
+L29_UNROLL
     for (int i = 0; i < NL; ++i)
-#pragma unroll
+L29_UNROLL
         for (int j = 0; j < NL; ++j) c[i + j] += (uint64_t)a.l[j] * b.l[i];
-#pragma unroll
+L29_UNROLL
     for (int k = 0; k < NL; ++k) {
         const uint32_t lo = (uint32_t)c[k];
         const uint32_t m = P0ONE ? ((0u - lo) & M29) : ((lo * d.n0) & M29);
-#pragma unroll
+L29_UNROLL
         for (int j = 0; j < NL; ++j) c[k + j] += (uint64_t)m * (P0ONE && j == 0 ? 1u : d.p[j]);
         if (k + 1 < 2 * NL - 1) c[k + 1] += c[k] >> 29;
     }
-#pragma unroll
+L29_UNROLL
     for (int j = 0; j < NL - 1; ++j) out[j] = c[NL + j];
 }
 // eight columns -> nine limbs, carries rippled (limbs below 2^29, the top limb takes the rest)
 L29_HD L9 carry_cols8(uint64_t (&t)[NL - 1]) {
     L9 r;
-#pragma unroll
+L29_UNROLL
     for (int j = 0; j < NL - 2; ++j) {
         r.l[j] = (uint32_t)t[j] & M29;
         t[j + 1] += t[j] >> 29;
@@ -191,14 +196,14 @@ L29_HD L9 carry_cols8(uint64_t (&t)[NL - 1]) {
 // fine as an operand of another product (9 2^60.02 + 9 2^58 < 2^64), not for limb-wise sums.
 L29_HD L9 split_cols8(const uint64_t (&t)[NL - 1]) {
     uint32_t d0[NL - 1], d1[NL - 1], d2[NL - 1];
-#pragma unroll
+L29_UNROLL
     for (int j = 0; j < NL - 1; ++j) {
         d0[j] = (uint32_t)t[j] & M29;
         d1[j] = (uint32_t)(t[j] >> 29) & M29;
         d2[j] = (uint32_t)(t[j] >> 58);
     }
     L9 r;
-#pragma unroll
+L29_UNROLL
     for (int j = 0; j < NL - 1; ++j) r.l[j] = d0[j] + (j >= 1 ? d1[j - 1] : 0u) + (j >= 2 ? d2[j - 2] : 0u);
     r.l[NL - 1] = (uint32_t)(t[NL - 2] >> 29) + d2[NL - 3];  // digit 1 of the last column unmasked: it takes what is above
     return r;
