@@ -98,6 +98,10 @@ int scb_mle_fix_variables(const scb_mle* m, const uint64_t* partial_point, uint3
 int scb_mle_evaluate(const scb_mle* m, const uint64_t* point, uint32_t n_point, uint64_t* out_elem);
 /* same value with the point in the big-endian order of multilinear-extensions (r[0] <-> index MSB) */
 int scb_mle_evaluate_be(const scb_mle* m, const uint64_t* r, uint32_t n_r, uint64_t* out_elem);
+/* n_points evaluations of ONE table, LSB-first points stored back to back (points[t * n_point + j]): what the GKR
+ * prover's restrict_poly needs -- W~ along the line through b* and c*, k + 1 points (gkr-protocol/src/lib.rs:291-321) --
+ * as one pass over the table per 8 points instead of one per point.  out_elems: n_points elements. */
+int scb_mle_evaluate_many(const scb_mle* m, const uint64_t* points, uint32_t n_point, uint32_t n_points, uint64_t* out_elems);
 /* [ARK] relabel(a, b, k) (matrix-multiplication/src/lib.rs:82) */
 int scb_mle_relabel(const scb_mle* m, uint32_t a, uint32_t b, uint32_t k, scb_mle** out);
 /* [ARK] to_evaluations(): device -> host copy of the 2^num_vars entries */

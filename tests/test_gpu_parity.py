@@ -499,3 +499,24 @@ def test_grid_resident_kernel_matches_per_round_launches():
         assert o.returncode == 0, o.stderr[-2000:]
     assert len(outs[0].stdout.split()) == 12
     assert len(set(o.stdout for o in outs)) == 1
+
+
+@pytest.mark.parametrize("p", [1572869, 389, 0xFFFFFFFF00000001, O.BLS12_381_FR.p], ids=lambda p: f"p{p.bit_length()}")
+def test_evaluate_many_matches_single_evaluations_and_the_oracle(p):
+    """scb_mle_evaluate_many (restrict_poly's k + 1 evaluations along a line, gkr-protocol/src/lib.rs:291-321): the
+    row-wise kernel (one-limb fields, 2^8 .. 2^20 entries), the staged one and the single-evaluation fallback against
+    the C oracle's evaluation, 1 .. 21 points."""
+    from oracle.coracle import CField
+
+    F, cf = T.Field(p), CField(p)
+    rnd = random.Random(p % 977)
+    for v in (3, 8, 9, 13, 17):
+        m = T.DenseMultilinearExtension.synthetic(F, v, 5 + v)
+        tab = cf.synth(5 + v, 0, 1 << v)
+        for n_pts in (1, 7, 8, 9, 21):
+            pts = [[rnd.randrange(p) for _ in range(v)] for _ in range(n_pts)]
+            want = [cf.from_mont(cf.mle_evaluate_le(tab, cf.to_mont(pt)))[0] for pt in pts]
+            for rows in (1, 0):
+                T.set_option("mle_rows_multi", rows)
+                assert m.evaluate_many(pts) == want, (v, n_pts, rows)
+    T.reset_options()

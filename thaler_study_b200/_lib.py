@@ -51,6 +51,7 @@ SIGNATURES = {
     "scb_mle_fix_variables": (C.c_int, [vp, u64p, C.c_uint32, vpp]),
     "scb_mle_evaluate": (C.c_int, [vp, u64p, C.c_uint32, u64p]),
     "scb_mle_evaluate_be": (C.c_int, [vp, u64p, C.c_uint32, u64p]),
+    "scb_mle_evaluate_many": (C.c_int, [vp, u64p, C.c_uint32, C.c_uint32, u64p]),
     "scb_mle_relabel": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, vpp]),
     "scb_mle_to_evaluations": (C.c_int, [vp, u64p, C.c_size_t]),
     "scb_mle_copy_to_device": (C.c_int, [vp, vp]),

@@ -166,6 +166,15 @@ class DenseMultilinearExtension:
         check(lib.scb_mle_evaluate(self._h, _p64(pt), len(point), _p64(out)))
         return self.F.from_mont(out)[0]
 
+    def evaluate_many(self, points: Sequence[Sequence[int]]) -> List[int]:
+        """Several LSB-first evaluations of this table in one call (scb_mle_evaluate_many): the GKR prover's
+        restrict_poly evaluates W~ at k + 1 points of a line (gkr-protocol/src/lib.rs:291-321)."""
+        flat = [x for pt in points for x in pt]
+        pts = self.F.to_mont(flat)
+        out = np.zeros((len(points), self.F.n), dtype=np.uint64)
+        check(lib.scb_mle_evaluate_many(self._h, _p64(pts), len(points[0]), len(points), _p64(out)))
+        return self.F.from_mont(out)
+
     def evaluate_be(self, r: Sequence[int]) -> int:
         pt = self.F.to_mont(list(r)) if len(r) else np.zeros((1, self.F.n), dtype=np.uint64)
         out = np.zeros((1, self.F.n), dtype=np.uint64)

@@ -733,6 +733,9 @@ static int eval_table_multi(Ctx* c, const FieldImpl& f, const Table& t, const ui
     const uint32_t TC = N == 1 ? 8 : 2;
     uint32_t lb = v / 2;
     while (lb > 0 && ((size_t)TC * 8 * N << lb) > 64 * 1024) --lb;  // TC low tables in 64 KB of shared memory
+    // one-limb fields, tables up to 2^(8 + cap_bits) entries: the row-wise kernel with 256-entry rows (k_mle_rows_multi)
+    const bool rows = N == 1 && opt(OPT_mle_rows_multi) != 0 && v >= (uint32_t)kRowsMultiLB && v - kRowsMultiLB <= cap_bits && !t.p32;
+    if (rows) lb = kRowsMultiLB;
     if (v < 4 || lb < 2 || v - lb > cap_bits || t.p32) {
         for (uint32_t i = 0; i < T; ++i) RC_TRY(eval_table(c, f, t, pts + (size_t)i * v * N, nullptr, d_out + (size_t)i * N));
         return SCB_OK;
@@ -754,6 +757,21 @@ static int eval_table_multi(Ctx* c, const FieldImpl& f, const Table& t, const ui
     for (uint32_t t0 = 0; t0 < T; t0 += TC) {
         const uint32_t np = T - t0 < TC ? T - t0 : TC;
         const size_t smem = ((size_t)np * 8 * N) << lb;
+        if (rows) {
+            if (f.policy == POL_SP) {
+                auto kern = k_mle_rows_multi<PolSP, 8>;
+                kern<<<occ_grid(c, kern, (n >> kRowsMultiLB) * 32), kThreads, 0, g_stream>>>(f.d, t.buf->ptr, lo->ptr + (((size_t)t0 << lb) * N),
+                                                                                           hi->ptr + (((size_t)t0 << (v - lb)) * N), v, np, n, c->partials, c->ticket,
+                                                                                           d_out + (size_t)t0 * N);
+            } else {
+                auto kern = k_mle_rows_multi<PolG1, 8>;
+                kern<<<occ_grid(c, kern, (n >> kRowsMultiLB) * 32), kThreads, 0, g_stream>>>(f.d, t.buf->ptr, lo->ptr + (((size_t)t0 << lb) * N),
+                                                                                           hi->ptr + (((size_t)t0 << (v - lb)) * N), v, np, n, c->partials, c->ticket,
+                                                                                           d_out + (size_t)t0 * N);
+            }
+            LAUNCH_CHECK();
+            continue;
+        }
         DISPATCH_POLICY(f.policy, {
             constexpr int KTC = A::N == 1 ? 8 : 2;
             auto kern = k_mle_dot_multi<A, KTC>;
@@ -767,6 +785,18 @@ static int eval_table_multi(Ctx* c, const FieldImpl& f, const Table& t, const ui
     return SCB_OK;
 }
 
+extern "C" int scb_mle_evaluate_many(const scb_mle* m, const uint64_t* points, uint32_t n_point, uint32_t n_points, uint64_t* out_elems) {
+    ARG_TRY(m && out_elems && points, "null argument");
+    ARG_TRY(n_point == m->t.nv, "point dimension does not match num_vars");
+    ARG_TRY(n_points >= 1 && n_points <= 64, "between 1 and 64 points per call");
+    Ctx* c;
+    RC_TRY(get_ctx(&c));
+    const uint32_t N = m->f->d.n;
+    RC_TRY(eval_table_multi(c, *m->f, m->t, points, n_points, c->h_msgs));  // mapped host memory: results land there
+    CU_TRY(cudaStreamSynchronize(g_stream));
+    std::memcpy(out_elems, c->h_msgs, (size_t)8 * N * n_points);
+    return SCB_OK;
+}
 extern "C" int scb_mle_evaluate(const scb_mle* m, const uint64_t* point, uint32_t n_point, uint64_t* out_elem) {
     ARG_TRY(m && out_elem && (point || n_point == 0), "null argument");
     ARG_TRY(n_point == m->t.nv, "point dimension does not match num_vars");

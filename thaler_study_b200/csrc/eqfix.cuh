@@ -195,6 +195,65 @@ __global__ void __launch_bounds__(kThreads) k_mle_dot_multi(FieldDesc f, const u
     grid_reduce_finish<A, TC>(ar, acc, partials, ticket, out);
 }
 
+// The same for one-limb fields and tables of at most 2^20 entries (the GKR layer width of BASELINE configs[4]), row-wise
+// like k_mle_eval_fused: lb is fixed at 8, so the TC low tables are 16 KB of shared memory (many CTAs per SM, staged
+// with one 256-bit load per thread), a WARP takes a row of 256 entries -- two 256-bit loads per lane, read once and used
+// for all TC points -- and multiplies each point's row sum by that point's high-table entry.  k_mle_dot_multi staged
+// 64 KB per CTA through 32 dependent 8-byte loads per thread and ran one CTA per SM: 66-99 us per launch for an 8 MB
+// table (profiles/r02_launches_gkr.csv); this form takes a few microseconds.
+constexpr int kRowsMultiLB = 8;
+template <class A, int TC>
+__global__ void __launch_bounds__(kThreads) k_mle_rows_multi(FieldDesc f, const uint64_t* __restrict__ evals, const uint64_t* __restrict__ lo_all,
+                                                             const uint64_t* __restrict__ hi_all, uint32_t v, uint32_t n_pts, uint64_t n,
+                                                             uint64_t* partials, unsigned int* ticket, uint64_t* out) {
+    static_assert(A::N == 1, "one-limb fields only");
+    constexpr int LB = kRowsMultiLB, JL = (1 << LB) / 128;
+    __shared__ __align__(32) uint64_t lo_sm[TC << LB];
+    const A ar(f);
+    const int lane = threadIdx.x & 31;
+    const uint64_t n_rows = n >> LB;
+    const uint64_t n_warps = (uint64_t)gridDim.x * (kThreads / 32);
+    uint64_t row = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    uint64_t w[JL][4];
+    if (row < n_rows) {  // the row's loads are in flight while the low tables are staged
+#pragma unroll
+        for (int j = 0; j < JL; ++j) ld_words<4>(evals + ((row << LB) + (size_t)(j * 32 + lane) * 4), w[j]);
+    }
+    for (uint32_t i = threadIdx.x * 4; i < (n_pts << LB); i += kThreads * 4) {
+        uint64_t q[4];
+        ld_words<4>(lo_all + i, q);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) lo_sm[i + e] = q[e];
+    }
+    __syncthreads();
+    typename A::Acc acc[TC];
+#pragma unroll
+    for (int t = 0; t < TC; ++t) ar.acc_zero(acc[t]);
+    while (row < n_rows) {
+#pragma unroll
+        for (int t = 0; t < TC; ++t) {
+            if (t < (int)n_pts) {
+                typename A::Lz s;
+#pragma unroll
+                for (int j = 0; j < JL; ++j)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const typename A::Lz m = ar.lz_mul(ar.lz(ar.from_words(&w[j][e])), ar.lz(ar.from_words(lo_sm + ((size_t)t << LB) + (size_t)(j * 32 + lane) * 4 + e)));
+                        s = (j == 0 && e == 0) ? m : ar.lz_add(s, m);
+                    }
+                const uint64_t hw = __ldg(hi_all + (((size_t)t << (v - LB)) + row));
+                ar.acc_add(acc[t], ar.lz_mul(s, ar.lz(ar.from_words(&hw))));
+            }
+        }
+        row += n_warps;
+        if (row < n_rows) {
+#pragma unroll
+            for (int j = 0; j < JL; ++j) ld_words<4>(evals + ((row << LB) + (size_t)(j * 32 + lane) * 4), w[j]);
+        }
+    }
+    grid_reduce_finish<A, TC>(ar, acc, partials, ticket, out);
+}
+
 // ------------------------------------------------------------------------------------------
 // MLE evaluation in ONE launch (multilinear-extensions/src/lib.rs:6-24; [ARK] evaluate for the LSB-first order).
 // eq(i) over v index bits is the outer product of a table over the low LB bits and up to three sub-tables of at most

@@ -31,6 +31,7 @@ namespace scb {
     X(mle_lb, 0)               /* MLE evaluation: index bits of the low (shared-memory) eq table; 0: default */             \
     X(mle_u, 0)                /* MLE evaluation: 1 = one group per thread-iteration */                                     \
     X(mle_fused, 1)            /* MLE evaluation as ONE launch (eq sub-tables built per CTA in shared memory) */            \
+    X(mle_rows_multi, 1)       /* several evaluations of one table (GKR restrict_poly): row-wise kernel for one-limb fields */ \
     X(gkr_multi, 1)            /* GKR layer with challenges up front: up to 4 rounds per pass, no barriers (k_pqs_multi) */  \
     X(gkr_persist, 1)          /* GKR layer phases as one cooperative launch each */                                        \
     X(g4_kernel, 3)            /* 4-limb fused fold+message with a claim: 3 = carry chains + unreduced last products in 544-bit        \
