@@ -38,8 +38,15 @@ static cudaError_t launch_k(int blocks_per_sm_cap, int sms, cudaStream_t stream,
 // ---- fourth generation: wide accumulators in shared memory (k_fold_round_g4w / k_round_evals_g4w)
 // nb_cached: the caller's per-kernel static (kernels that differ only in a bool template argument share a function TYPE,
 // so a static in here would be shared between them and the second one would never get its shared-memory attribute)
+constexpr int kWideMaxDev = 16;
+struct WideCache {  // per device: the shared-memory opt-in is a per-context attribute
+    int nb[kWideMaxDev] = {};
+};
 template <class Kern>
-static cudaError_t wide_grid(Kern kern, int& nb_cached, size_t smem, int blocks_per_sm_cap, int sms, uint64_t items, int max_grid, int* grid_out) {
+static cudaError_t wide_grid(Kern kern, WideCache& cache, size_t smem, int blocks_per_sm_cap, int sms, uint64_t items, int max_grid, int* grid_out) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kWideMaxDev) dev = 0;
+    int& nb_cached = cache.nb[dev];
     if (nb_cached == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -60,7 +67,7 @@ static cudaError_t launch_kw(int blocks_per_sm_cap, int sms, cudaStream_t stream
                              const g4::FoldTab& r, uint64_t n_quads, uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid) {
     auto kern = g4::k_fold_round_g4w<K, P0ONE, MINB>;
     const size_t smem = g4::wacc_smem_bytes(g4::n_sums(K));
-    static int nb_cached = 0;
+    static WideCache nb_cached;
     int grid = 1;
     const cudaError_t e = wide_grid(kern, nb_cached, smem, blocks_per_sm_cap, sms, n_quads, max_grid, &grid);
     if (e != cudaSuccess) return e;
@@ -78,7 +85,7 @@ static cudaError_t launch_rw(int blocks_per_sm_cap, int sms, cudaStream_t stream
                              uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid) {
     auto kern = g4::k_round_evals_g4w<K, P0ONE, MINB>;
     const size_t smem = g4::wacc_smem_bytes(g4::n_sums(K) + 1);
-    static int nb_cached = 0;
+    static WideCache nb_cached;
     int grid = 1;
     const cudaError_t e = wide_grid(kern, nb_cached, smem, blocks_per_sm_cap, sms, n_pairs, max_grid, &grid);
     if (e != cudaSuccess) return e;
@@ -135,7 +142,7 @@ static cudaError_t launch_mle(int sms, cudaStream_t stream, const FieldDesc& f, 
                               uint64_t row0, uint64_t* partials, unsigned int* ticket, uint64_t* res, const PeerArg& pa, int max_grid) {
     auto kern = g4::k_mle_eval_fused_g4<P0ONE>;
     constexpr size_t smem = MleFusedCfg<PolGN<4>>::smem_bytes;
-    static int nb_cached = 0;
+    static WideCache nb_cached;
     int grid = 1;
     const uint64_t n_rows = (1ull << v_local) >> MleFusedCfg<PolGN<4>>::LB;
     const cudaError_t e = wide_grid(kern, nb_cached, smem, 0, sms, n_rows * 32, max_grid, &grid);
