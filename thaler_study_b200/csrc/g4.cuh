@@ -23,6 +23,10 @@
 //     t1 - t0 + p in (0, 2p) without a select: with the canonical challenge as the other operand the product stays
 //     below 2p and the usual single subtraction makes it canonical.
 //
+// A fourth generation (second half of the file: k_fold_round_g4w, k_round_evals_g4w; the default) goes further once the
+// multiplier pipe was measured to be the bound: unreduced last products in 544-bit accumulators, folds through a table of the
+// challenge, a variant for moduli that are 1 modulo 2^32 -- 1018 instead of 1537 wide multiply-adds per 4 entries (K = 3).
+//
 // Everything stored to HBM is canonical, as everywhere else.
 #pragma once
 #include <cstdint>
@@ -405,8 +409,8 @@ __global__ void __launch_bounds__(kThreads, MINB)
 
 // ------------------------------------------------------------------------------------------------ wide accumulators (r2b)
 // Fourth generation.  Measured on B200 (scripts/mont29_bench.cu, profiles/r02_mont29.md): a 32 x 32 -> 64-bit multiply-add
-// (IMAD.WIDE.U32, with or without carry) issues once per 4 cycles per SM sub-partition on the fmaheavy pipe, and these
-// kernels run with that pipe 85-95 % busy -- so the only way to be faster is to issue fewer of them:
+// (IMAD.WIDE.U32, with or without carry) issues once per 4 cycles per SM sub-partition on the fmaheavy pipe, and a bare
+// product loop keeps that pipe 91-95 % busy (these kernels: 70-76 %) -- so the way to be faster is to issue fewer of them:
 //   * the LAST product of every message point is not reduced at all: its 512-bit integer value prod * fac goes into a
 //     544-bit accumulator (64 wide multiply-adds instead of 128), and each thread does ONE Montgomery reduction per
 //     accumulator at the end (REDC is linear: sum REDC(x_i) = REDC(sum x_i) mod p);
