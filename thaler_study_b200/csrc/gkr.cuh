@@ -28,9 +28,18 @@ struct EqPair {  // eq(point; idx) = lo[idx & (2^lb - 1)] * hi[idx >> lb]
     const uint64_t* hi;
     uint32_t lb;
 };
+// eq tables are small (at most 2^12 + 2^14 entries) and read by every thread of a gate-list kernel at random positions:
+// L1-allocating loads (ld_el's streaming loads bypass L1: ncu showed a 0.03 % L1 hit rate in k_gkr_wiring_eval)
+template <class A>
+__device__ __forceinline__ typename A::El ld_el_cached(const A& ar, const uint64_t* __restrict__ tab, uint64_t idx) {
+    uint64_t w[A::N];
+#pragma unroll
+    for (int q = 0; q < A::N; ++q) w[q] = __ldg(tab + idx * A::N + q);
+    return ar.from_words(w);
+}
 template <class A>
 __device__ __forceinline__ typename A::El eq_at(const A& ar, const EqPair& e, uint64_t idx) {
-    return ar.mul(ld_el(ar, e.lo, idx & ((1ull << e.lb) - 1)), ld_el(ar, e.hi, idx >> e.lb));
+    return ar.mul(ld_el_cached(ar, e.lo, idx & ((1ull << e.lb) - 1)), ld_el_cached(ar, e.hi, idx >> e.lb));
 }
 
 // Circuit::evaluate, one layer (gkr-protocol/src/circuit.rs:108-116)
@@ -48,10 +57,13 @@ __global__ void __launch_bounds__(kThreads) k_gkr_eval_layer(FieldDesc f, const 
     }
 }
 
-// phase-1 tables h1, h2 over b (one thread per b, its gates through the CSR by in0)
+// phase-1 tables h1, h2 over b (one thread per b, its gates through the CSR by in0).  Position t of the CSR order gives
+// the gate id and type (idx0[t], type in bit 31) and the gate's other input (oth0[t] = in1 of that gate) from coalesced
+// arrays, so the only gathers left are the eq lookups and W[in1].
+constexpr uint32_t kGateIdMask = 0x7fffffffu;
 template <class A>
 __global__ void __launch_bounds__(kThreads) k_gkr_phase1(FieldDesc f, EqPair eq_r, const uint32_t* __restrict__ off0, const uint32_t* __restrict__ idx0,
-                                                         const uint8_t* __restrict__ types, const uint32_t* __restrict__ in1,
+                                                         const uint32_t* __restrict__ oth0,
                                                          const uint64_t* __restrict__ w, uint64_t* __restrict__ h1, uint64_t* __restrict__ h2,
                                                          uint64_t n_b) {
     const A ar(f);
@@ -59,10 +71,10 @@ __global__ void __launch_bounds__(kThreads) k_gkr_phase1(FieldDesc f, EqPair eq_
     for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_b; b += stride) {
         typename A::El s1 = ar.zero(), s2 = ar.zero();
         for (uint32_t t = off0[b]; t < off0[b + 1]; ++t) {
-            const uint32_t a = idx0[t];
+            const uint32_t at = idx0[t], a = at & kGateIdMask;
             const typename A::El e = eq_at(ar, eq_r, a);
-            const typename A::El ew = ar.mul(e, ld_el(ar, w, in1[a]));
-            if (types[a]) {
+            const typename A::El ew = ar.mul(e, ld_el(ar, w, oth0[t]));
+            if (at >> 31) {
                 s1 = ar.add(s1, ew);
             } else {
                 s1 = ar.add(s1, e);
@@ -80,8 +92,8 @@ __global__ void __launch_bounds__(kThreads) k_gkr_phase1(FieldDesc f, EqPair eq_
 // phase-2 tables Q = A + wu*M, S = wu*A over c (one thread per c, its gates through the CSR by in1)
 template <class A>
 __global__ void __launch_bounds__(kThreads) k_gkr_phase2(FieldDesc f, EqPair eq_r, EqPair eq_u, const uint32_t* __restrict__ off1,
-                                                         const uint32_t* __restrict__ idx1, const uint8_t* __restrict__ types,
-                                                         const uint32_t* __restrict__ in0, ElemArg wu_arg, uint64_t* __restrict__ q,
+                                                         const uint32_t* __restrict__ idx1,
+                                                         const uint32_t* __restrict__ oth1, ElemArg wu_arg, uint64_t* __restrict__ q,
                                                          uint64_t* __restrict__ s, uint64_t n_c, const uint64_t* wu_dev = nullptr) {
     const A ar(f);
     uint64_t wu_w[A::N];  // W~(u): by value, or left in device memory by the previous kernel of a batched layer proof
@@ -92,9 +104,9 @@ __global__ void __launch_bounds__(kThreads) k_gkr_phase2(FieldDesc f, EqPair eq_
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_c; c += stride) {
         typename A::El sa = ar.zero(), sm = ar.zero();
         for (uint32_t t = off1[c]; t < off1[c + 1]; ++t) {
-            const uint32_t a = idx1[t];
-            const typename A::El e = ar.mul(eq_at(ar, eq_r, a), eq_at(ar, eq_u, in0[a]));
-            if (types[a]) sm = ar.add(sm, e);
+            const uint32_t at = idx1[t], a = at & kGateIdMask;
+            const typename A::El e = ar.mul(eq_at(ar, eq_r, a), eq_at(ar, eq_u, oth1[t]));  // oth1[t] = in0 of that gate
+            if (at >> 31) sm = ar.add(sm, e);
             else sa = ar.add(sa, e);
         }
         uint64_t o[A::N];
@@ -102,6 +114,66 @@ __global__ void __launch_bounds__(kThreads) k_gkr_phase2(FieldDesc f, EqPair eq_
         st_words<A::N>(q + c * A::N, o);
         ar.to_words(ar.mul(wu, sa), o);
         st_words<A::N>(s + c * A::N, o);
+    }
+}
+
+// ---- small-prime fields: the same two tables by SCATTER (r2b).  The CSR kernels above are one thread per output with a
+// loop over its gates: three dependent levels of uncoalesced loads, a third of the lanes active on average, 83-90 % of
+// the stall samples on the load scoreboard (68-74 us per launch at width 2^20).  For p < 2^28 a sum of 2^26 canonical
+// residues fits 64 bits with room to spare, so a thread per GATE (coalesced gate list, eq(r; a) coalesced in a, one
+// gather of W) adds its contribution with a 64-bit integer atomic -- exact and order-independent, so the tables are the
+// same field elements -- and a second small kernel reduces modulo p (phase 2: and forms Q, S).  The destination tables
+// must be zero on entry.
+__device__ __forceinline__ uint32_t eq_at_sp(const PolSP& ar, const EqPair& e, uint64_t idx) {  // L1-allocating loads: small, hot tables
+    return ar.mul((uint32_t)__ldg(e.lo + (idx & ((1ull << e.lb) - 1))), (uint32_t)__ldg(e.hi + (idx >> e.lb)));
+}
+__global__ void __launch_bounds__(kThreads) k_gkr_phase1_scatter_sp(FieldDesc f, EqPair eq_r, const uint8_t* __restrict__ types,
+                                                                    const uint32_t* __restrict__ in0, const uint32_t* __restrict__ in1,
+                                                                    const uint64_t* __restrict__ w, unsigned long long* __restrict__ h1,
+                                                                    unsigned long long* __restrict__ h2, uint64_t n_gates) {
+    const PolSP ar(f);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n_gates; a += stride) {
+        const uint32_t b = in0[a];
+        const uint32_t e = eq_at_sp(ar, eq_r, a);
+        const uint32_t ew = ar.mul(e, (uint32_t)w[in1[a]]);
+        if (types[a]) {
+            atomicAdd(h1 + b, (unsigned long long)ew);
+        } else {
+            atomicAdd(h1 + b, (unsigned long long)e);
+            atomicAdd(h2 + b, (unsigned long long)ew);
+        }
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_gkr_phase1_finish_sp(FieldDesc f, uint64_t* __restrict__ h1, uint64_t* __restrict__ h2, uint64_t n_b) {
+    const uint64_t p = f.p[0];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_b; b += stride) {
+        h1[b] %= p;
+        h2[b] %= p;
+    }
+}
+// phase 2: sa[c] (into q) and sm[c] (into s) as integer sums, then Q = sa + wu sm, S = wu sa in place
+__global__ void __launch_bounds__(kThreads) k_gkr_phase2_scatter_sp(FieldDesc f, EqPair eq_r, EqPair eq_u, const uint8_t* __restrict__ types,
+                                                                    const uint32_t* __restrict__ in0, const uint32_t* __restrict__ in1,
+                                                                    unsigned long long* __restrict__ q, unsigned long long* __restrict__ s, uint64_t n_gates) {
+    const PolSP ar(f);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n_gates; a += stride) {
+        const uint32_t e = ar.mul(eq_at_sp(ar, eq_r, a), eq_at_sp(ar, eq_u, in0[a]));
+        atomicAdd((types[a] ? s : q) + in1[a], (unsigned long long)e);
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_gkr_phase2_finish_sp(FieldDesc f, ElemArg wu_arg, uint64_t* __restrict__ q, uint64_t* __restrict__ s,
+                                                                   uint64_t n_c, const uint64_t* wu_dev) {
+    const PolSP ar(f);
+    const uint32_t wu = (uint32_t)(wu_dev ? __ldcg(wu_dev) : wu_arg.w[0]);
+    const uint64_t p = f.p[0];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_c; c += stride) {
+        const uint32_t sa = (uint32_t)(q[c] % p), sm = (uint32_t)(s[c] % p);
+        q[c] = ar.add(sa, ar.mul(wu, sm));
+        s[c] = ar.mul(wu, sa);
     }
 }
 

@@ -227,35 +227,38 @@ __device__ __forceinline__ void grid_reduce_finish(const A& ar, typename A::Acc 
     __shared__ uint64_t sm[32 * NP * AW];
     __shared__ bool is_last;
     block_reduce<A, NP>(ar, acc, sm);
-    if (threadIdx.x == 0) {
+    if (gridDim.x > 1) {  // a single CTA already holds the total in thread 0: no partials, no ticket, no second tree
+                          // (the small launches of a GKR layer spent most of their 11-14 us here)
+        if (threadIdx.x == 0) {
 #pragma unroll
-        for (int x = 0; x < NP; ++x) {
-            uint64_t w[AW];
-            ar.acc_to_words(acc[x], w);
+            for (int x = 0; x < NP; ++x) {
+                uint64_t w[AW];
+                ar.acc_to_words(acc[x], w);
 #pragma unroll
-            for (int i = 0; i < AW; ++i) __stcg(&partials[((size_t)blockIdx.x * NP + x) * AW + i], w[i]);
+                for (int i = 0; i < AW; ++i) __stcg(&partials[((size_t)blockIdx.x * NP + x) * AW + i], w[i]);
+            }
+            __threadfence();
+            unsigned int t = atomicAdd(ticket, 1u);
+            is_last = (t == gridDim.x - 1);
         }
+        __syncthreads();
+        if (!is_last) return;
         __threadfence();
-        unsigned int t = atomicAdd(ticket, 1u);
-        is_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
 #pragma unroll
-    for (int x = 0; x < NP; ++x) ar.acc_zero(acc[x]);
-    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        for (int x = 0; x < NP; ++x) ar.acc_zero(acc[x]);
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
 #pragma unroll
-        for (int x = 0; x < NP; ++x) {
-            uint64_t w[AW];
+            for (int x = 0; x < NP; ++x) {
+                uint64_t w[AW];
 #pragma unroll
-            for (int i = 0; i < AW; ++i) w[i] = __ldcg(&partials[((size_t)b * NP + x) * AW + i]);
-            typename A::Acc o;
-            ar.acc_from_words(o, w);
-            ar.acc_merge(acc[x], o);
+                for (int i = 0; i < AW; ++i) w[i] = __ldcg(&partials[((size_t)b * NP + x) * AW + i]);
+                typename A::Acc o;
+                ar.acc_from_words(o, w);
+                ar.acc_merge(acc[x], o);
+            }
         }
+        block_reduce<A, NP>(ar, acc, sm);
     }
-    block_reduce<A, NP>(ar, acc, sm);
     if constexpr (NP * A::N <= 32) {
         if (peer != nullptr && peer->world > 1) {  // sharded: warp 0 exchanges the sums with the peer GPUs (CTA-uniform branch)
             __syncthreads();  // sm is free again

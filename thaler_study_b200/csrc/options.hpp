@@ -34,6 +34,7 @@ namespace scb {
     X(mle_rows_multi, 1)       /* several evaluations of one table (GKR restrict_poly): row-wise kernel for one-limb fields */ \
     X(gkr_multi, 1)            /* GKR layer with challenges up front: up to 4 rounds per pass, no barriers (k_pqs_multi) */  \
     X(gkr_persist, 1)          /* GKR layer phases as one cooperative launch each */                                        \
+    X(gkr_scatter, 1)          /* GKR phase tables for small-prime fields: thread per gate + 64-bit integer atomics (gkr.cuh) */ \
     X(g4_kernel, 3)            /* 4-limb fused fold+message with a claim: 3 = carry chains + unreduced last products in 544-bit        \
                                   shared-memory accumulators, round 0 included (g4.cuh, K >= 2); 1 = carry chains, one point fewer      \
                                   (14.7 ms per 2^28 x 3 launch); 2 = radix-2^29 lazy carries (g29.cuh: 20.8 ms); 0 = round 1's (18.2 ms) */ \
