@@ -760,12 +760,12 @@ static int eval_table_multi(Ctx* c, const FieldImpl& f, const Table& t, const ui
         if (rows) {
             if (f.policy == POL_SP) {
                 auto kern = k_mle_rows_multi<PolSP, 8>;
-                kern<<<occ_grid(c, kern, (n >> kRowsMultiLB) * 32), kThreads, 0, g_stream>>>(f.d, t.buf->ptr, lo->ptr + (((size_t)t0 << lb) * N),
+                kern<<<grid_for(c, (n >> kRowsMultiLB) * 32, (int)opt(OPT_mle_rows_bps)), kThreads, 0, g_stream>>>(f.d, t.buf->ptr, lo->ptr + (((size_t)t0 << lb) * N),
                                                                                            hi->ptr + (((size_t)t0 << (v - lb)) * N), v, np, n, c->partials, c->ticket,
                                                                                            d_out + (size_t)t0 * N);
             } else {
                 auto kern = k_mle_rows_multi<PolG1, 8>;
-                kern<<<occ_grid(c, kern, (n >> kRowsMultiLB) * 32), kThreads, 0, g_stream>>>(f.d, t.buf->ptr, lo->ptr + (((size_t)t0 << lb) * N),
+                kern<<<grid_for(c, (n >> kRowsMultiLB) * 32, (int)opt(OPT_mle_rows_bps)), kThreads, 0, g_stream>>>(f.d, t.buf->ptr, lo->ptr + (((size_t)t0 << lb) * N),
                                                                                            hi->ptr + (((size_t)t0 << (v - lb)) * N), v, np, n, c->partials, c->ticket,
                                                                                            d_out + (size_t)t0 * N);
             }

@@ -32,6 +32,7 @@ namespace scb {
     X(mle_u, 0)                /* MLE evaluation: 1 = one group per thread-iteration */                                     \
     X(mle_fused, 1)            /* MLE evaluation as ONE launch (eq sub-tables built per CTA in shared memory) */            \
     X(mle_rows_multi, 1)       /* several evaluations of one table (GKR restrict_poly): row-wise kernel for one-limb fields */ \
+    X(mle_rows_bps, 2)         /* ... its CTAs per SM (fewer CTAs: fewer partials for the last CTA to add up) */               \
     X(gkr_multi, 1)            /* GKR layer with challenges up front: up to 4 rounds per pass, no barriers (k_pqs_multi) */  \
     X(gkr_persist, 1)          /* GKR layer phases as one cooperative launch each */                                        \
     X(gkr_scatter, 1)          /* GKR phase tables for small-prime fields: thread per gate + 64-bit integer atomics (gkr.cuh) */ \
