@@ -333,6 +333,71 @@ __global__ void __launch_bounds__(kThreads) k_pqs_multi(FieldDesc f, const uint6
     grid_reduce_finish<A, 3 * R>(ar, acc, partials, ticket, out);
 }
 
+// ---- the last rounds of a phase in ONE CTA (r2b): once the three tables have at most 2^kPqsTailMaxVars entries they fit
+// shared memory, and the remaining rounds (message, fold, message, ...) need nothing but block barriers -- one launch
+// instead of ceil(m / R) launches of k_pqs_multi whose 11-14 us each were launch and reduction latency, not work.
+// Round t (t = 0 .. m-1): message of the tables as they are (three sums to out_slots[3 t ..]), then the fold by
+// challenges[t]; the single entries left after the last fold go to Po / Qo / So (W~(u) for phase 2 of a GKR layer).
+// One-limb fields.  The fold is done in place in chunks of blockDim pairs in increasing order: chunk i reads entries
+// [2 i B, 2 (i + 1) B) and writes [i B, (i + 1) B), which no later chunk reads.
+constexpr int kPqsTailMaxVars = 11;  // 3 x 2^11 x 8 B = 48 KB of shared memory
+template <class A>
+__global__ void __launch_bounds__(kThreads) k_pqs_tail(FieldDesc f, const uint64_t* __restrict__ P, const uint64_t* __restrict__ Q,
+                                                       const uint64_t* __restrict__ S, uint32_t m, const uint64_t* __restrict__ challenges,
+                                                       uint64_t* out_slots, uint64_t* __restrict__ Po, uint64_t* __restrict__ Qo, uint64_t* __restrict__ So) {
+    static_assert(A::N == 1, "one-limb fields only");
+    constexpr int AW = A::AW;
+    extern __shared__ uint64_t tail_sm[];  // [3][2^m]
+    __shared__ uint64_t red_sm[32 * 3 * AW];
+    const A ar(f);
+    const uint32_t n0 = 1u << m;
+    uint64_t* T[3] = {tail_sm, tail_sm + n0, tail_sm + 2 * n0};
+    const uint64_t* in[3] = {P, Q, S};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        for (uint32_t i = threadIdx.x; i < n0; i += blockDim.x) T[k][i] = in[k][i];
+    __syncthreads();
+    for (uint32_t t = 0; t < m; ++t) {
+        const uint32_t pairs = n0 >> (t + 1);
+        typename A::Acc acc[3];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) ar.acc_zero(acc[x]);
+        for (uint32_t j = threadIdx.x; j < pairs; j += blockDim.x) {
+            const typename A::El pp[2] = {ar.from_words(T[0] + 2 * j), ar.from_words(T[0] + 2 * j + 1)};
+            const typename A::El qq[2] = {ar.from_words(T[1] + 2 * j), ar.from_words(T[1] + 2 * j + 1)};
+            const typename A::El ss[2] = {ar.from_words(T[2] + 2 * j), ar.from_words(T[2] + 2 * j + 1)};
+            pqs_accumulate(ar, pp, qq, ss, acc);
+        }
+        block_reduce<A, 3>(ar, acc, red_sm);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int x = 0; x < 3; ++x) ar.to_words(ar.msg_final(acc[x], 0), out_slots + (size_t)(3 * t + x));
+        }
+        const uint64_t rw = __ldg(challenges + t);
+        const typename A::El r = ar.from_words(&rw);
+        for (uint32_t j0 = 0; j0 < pairs; j0 += blockDim.x) {  // in-place fold, chunk by chunk
+            const uint32_t j = j0 + threadIdx.x;
+            typename A::El v[3];
+            if (j < pairs) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) v[k] = ar.fold(ar.from_words(T[k] + 2 * j), ar.from_words(T[k] + 2 * j + 1), r);
+            }
+            __syncthreads();  // every read of this chunk (and the message pass above) is done
+            if (j < pairs) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) ar.to_words(v[k], T[k] + j);
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        Po[0] = T[0][0];
+        Qo[0] = T[1][0];
+        So[0] = T[2][0];
+        __threadfence_system();  // out_slots may be mapped host memory
+    }
+}
+
 // ---- all rounds of one P*Q + S sum-check in one cooperative launch, challenges known up front ----
 // Round 0 is the message of the tables as they are; round t >= 1 folds by challenges[t-1] and accumulates the next
 // message (the bodies of k_pqs_round / k_pqs_fold_round).  The CTAs meet at a ticket/flag barrier in device memory

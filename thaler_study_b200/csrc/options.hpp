@@ -35,6 +35,7 @@ namespace scb {
     X(mle_rows_bps, 2)         /* ... its CTAs per SM (fewer CTAs: fewer partials for the last CTA to add up) */               \
     X(gkr_multi, 1)            /* GKR layer with challenges up front: up to 4 rounds per pass, no barriers (k_pqs_multi) */  \
     X(gkr_persist, 1)          /* GKR layer phases as one cooperative launch each */                                        \
+    X(gkr_tail, 1)             /* GKR layer with challenges up front: the last 11 rounds of a phase in one CTA (k_pqs_tail) */ \
     X(gkr_scatter, 1)          /* GKR phase tables for small-prime fields: thread per gate + 64-bit integer atomics (gkr.cuh) */ \
     X(g4_kernel, 3)            /* 4-limb fused fold+message with a claim: 3 = carry chains + unreduced last products in 544-bit        \
                                   shared-memory accumulators, round 0 included (g4.cuh, K >= 2); 1 = carry chains, one point fewer      \
