@@ -339,6 +339,9 @@ int scb_gkr_prover_prove_layer(scb_gkr_prover* p, uint32_t i, const uint64_t* r_
  * rank) are exchanged by the caller with any transport (torch.distributed in thaler_study_b200/distributed.py). */
 typedef struct scb_peers scb_peers;
 int scb_peers_create(uint32_t rank, uint32_t world, size_t gather_bytes, scb_peers** out, uint8_t* handle_out /* 64 B */);
+/* capacity in bytes of one gather area of the window (what scb_peers_create was given, rounded up): the sharded prover
+ * picks its consolidation point so that all ranks' slabs of all tables fit */
+int scb_peers_gather_capacity(const scb_peers* p, size_t* out_bytes);
 int scb_peers_connect(scb_peers* p, const uint8_t* all_handles /* world * 64 B, rank order */);
 void scb_peers_free(scb_peers* p);
 /* make `p` (or none) the exchange group used by this thread's subsequent scb_poly_round_evals /

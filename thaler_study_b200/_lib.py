@@ -118,6 +118,7 @@ SIGNATURES = {
     "scb_gkr_prover_restrict_evals": (C.c_int, [vp, u64p, u64p, C.c_uint32, u32p]),
     "scb_gkr_prover_prove_layer": (C.c_int, [vp, C.c_uint32, u64p, u64p, C.c_uint32, u64p, u64p, u64p, C.c_uint32, u32p]),
     "scb_peers_create": (C.c_int, [C.c_uint32, C.c_uint32, C.c_size_t, vpp, u8p]),
+    "scb_peers_gather_capacity": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
     "scb_peers_connect": (C.c_int, [vp, u8p]),
     "scb_peers_free": (None, [vp]),
     "scb_peers_set_current": (C.c_int, [vp]),

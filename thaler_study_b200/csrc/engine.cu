@@ -1691,6 +1691,11 @@ static int peers_check(Ctx* c) {
     }
     return SCB_OK;
 }
+extern "C" int scb_peers_gather_capacity(const scb_peers* p, size_t* out_bytes) {
+    ARG_TRY(p && out_bytes, "null argument");
+    *out_bytes = p->gather_bytes;
+    return SCB_OK;
+}
 // Consolidation: every rank writes its slabs into every peer's gather area (NVLink P2P stores); afterwards each
 // rank holds the rank-order concatenation of all slabs and continues replicated, with no further communication.
 extern "C" int scb_peers_gather_poly(scb_peers* p, const scb_poly* slab, scb_poly** out) {

@@ -200,6 +200,13 @@ static int prover_new_impl(const scb_poly* g, scb_peers* peers, uint32_t world, 
         // round-trip over NVLink, profiles/r01_pairs.md); below it the passes run replicated on all ranks with no
         // exchange but on world x the data, and the gather itself moves world x K x 4 x 2^lv bytes into every window.
         p->consolidate_at = consolidate_at < 1 ? (opt(OPT_consolidate_auto) > 1 ? (uint32_t)opt(OPT_consolidate_auto) : 16) : consolidate_at;
+        if (consolidate_at < 1) {  // the library's own choice must fit the window: world x K tables x 2^lv entries of 8 n_limbs bytes
+            size_t cap = 0;
+            uint32_t K = 0;
+            RC_TRY(scb_peers_gather_capacity(peers, &cap));
+            RC_TRY(scb_poly_n_tables(g, &K));
+            while (p->consolidate_at > 3 && ((size_t)world * K * 8 * p->fi->d.n << p->consolidate_at) > cap) --p->consolidate_at;
+        }
         p->sharded = true;
         RC_TRY(maybe_consolidate(p.get()));
     }
