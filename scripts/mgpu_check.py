@@ -58,6 +58,18 @@ for p, lv, K, cat in ((1572869, 20, 3, 16), (1572869, 18, 3, 3), (1572869, 17, 4
         good = msgs == want and c_1 == T.Prover(full).c_1() and T.verify_transcript(msgs, T.Verifier(lv + lg, full))
         print(f"p_bits={F.bits} lv={lv} K={K} consolidate_at={cat}: {'ok' if good else 'MISMATCH'}")
         ok = ok and good
+# consolidate_at = 0 (the library's choice) with a window too small for its default of 2^16 entries per rank: it must pick
+# a smaller slab size that fits (a 4-limb slab set did not fit the 32 MB default window at 8 ranks) -- same transcript
+small = Peers(gather_bytes=1 << 20)
+for p, lv, K in ((BLS, 14, 3), (1572869, 18, 3)):
+    F = T.Field(p)
+    slabs = [T.DenseMultilinearExtension.synthetic(F, lv, 700 + k, start=rank << lv) for k in range(K)]
+    c_1, msgs = prove_sharded_p2p(T.ProductMLE.new(slabs), small, consolidate_at=0)
+    if rank == 0:
+        full = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, lv + lg, 700 + k) for k in range(K)])
+        good = msgs == T.generate_transcript(T.Prover(full)) and c_1 == T.Prover(full).c_1()
+        print(f"small window p_bits={F.bits} lv={lv} K={K}: {'ok' if good else 'MISMATCH'}")
+        ok = ok and good
 # slabs uploaded from host tables through the narrowing upload (packed uint32 from the start): same transcript
 T.set_option("host_pack_min_vars", 8)
 T.set_option("host_pack_chunk_log2", 10)

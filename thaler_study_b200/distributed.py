@@ -198,7 +198,7 @@ class Peers:
             raise RuntimeError(err)
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:  # at interpreter shutdown the module globals may be gone already
             lib.scb_peers_free(self._h)
             self._h = None
 
