@@ -754,21 +754,27 @@ static int eval_table_multi(Ctx* c, const FieldImpl& f, const Table& t, const ui
     });
     LAUNCH_CHECK();
     const uint64_t n = t.len();
-    for (uint32_t t0 = 0; t0 < T; t0 += TC) {
-        const uint32_t np = T - t0 < TC ? T - t0 : TC;
+    const uint32_t step = rows && T > 8 ? 24 : TC;  // the row-wise kernel also exists for 24 points per pass
+    for (uint32_t t0 = 0; t0 < T; t0 += step) {
+        const uint32_t np = T - t0 < step ? T - t0 : step;
         const size_t smem = ((size_t)np * 8 * N) << lb;
         if (rows) {
+            const int grid = grid_for(c, (n >> kRowsMultiLB) * 32, (int)opt(OPT_mle_rows_bps));
+            const uint64_t* lo_p = lo->ptr + (((size_t)t0 << lb) * N);
+            const uint64_t* hi_p = hi->ptr + (((size_t)t0 << (v - lb)) * N);
+            uint64_t* out_p = d_out + (size_t)t0 * N;
+#define SCB_ROWS_MULTI(POL, TCC)                                                                                                        \
+    {                                                                                                                                   \
+        auto kern = k_mle_rows_multi<POL, TCC>;                                                                                         \
+        RC_TRY(allow_smem(kern, (size_t)TCC * 8 << kRowsMultiLB));                                                                      \
+        kern<<<grid, kThreads, smem, g_stream>>>(f.d, t.buf->ptr, lo_p, hi_p, v, np, n, c->partials, c->ticket, out_p);                 \
+    }
             if (f.policy == POL_SP) {
-                auto kern = k_mle_rows_multi<PolSP, 8>;
-                kern<<<grid_for(c, (n >> kRowsMultiLB) * 32, (int)opt(OPT_mle_rows_bps)), kThreads, 0, g_stream>>>(f.d, t.buf->ptr, lo->ptr + (((size_t)t0 << lb) * N),
-                                                                                           hi->ptr + (((size_t)t0 << (v - lb)) * N), v, np, n, c->partials, c->ticket,
-                                                                                           d_out + (size_t)t0 * N);
+                if (step == 24) SCB_ROWS_MULTI(PolSP, 24) else SCB_ROWS_MULTI(PolSP, 8)
             } else {
-                auto kern = k_mle_rows_multi<PolG1, 8>;
-                kern<<<grid_for(c, (n >> kRowsMultiLB) * 32, (int)opt(OPT_mle_rows_bps)), kThreads, 0, g_stream>>>(f.d, t.buf->ptr, lo->ptr + (((size_t)t0 << lb) * N),
-                                                                                           hi->ptr + (((size_t)t0 << (v - lb)) * N), v, np, n, c->partials, c->ticket,
-                                                                                           d_out + (size_t)t0 * N);
+                if (step == 24) SCB_ROWS_MULTI(PolG1, 24) else SCB_ROWS_MULTI(PolG1, 8)
             }
+#undef SCB_ROWS_MULTI
             LAUNCH_CHECK();
             continue;
         }

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreads) k_mle_rows_multi(FieldDesc f, const 
                                                              uint64_t* partials, unsigned int* ticket, uint64_t* out) {
     static_assert(A::N == 1, "one-limb fields only");
     constexpr int LB = kRowsMultiLB, JL = (1 << LB) / 128;
-    __shared__ __align__(32) uint64_t lo_sm[TC << LB];
+    extern __shared__ __align__(32) uint64_t lo_sm[];  // n_pts << LB words (TC = 24: up to 48 KB, one launch for the 21 points of a 2^20-wide layer)
     const A ar(f);
     const int lane = threadIdx.x & 31;
     const uint64_t n_rows = n >> LB;

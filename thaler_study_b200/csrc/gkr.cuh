@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kThreads) k_pqs_multi(FieldDesc f, const uint6
 // challenges[t]; the single entries left after the last fold go to Po / Qo / So (W~(u) for phase 2 of a GKR layer).
 // One-limb fields.  The fold is done in place in chunks of blockDim pairs in increasing order: chunk i reads entries
 // [2 i B, 2 (i + 1) B) and writes [i B, (i + 1) B), which no later chunk reads.
-constexpr int kPqsTailMaxVars = 11;  // 3 x 2^11 x 8 B = 48 KB of shared memory
+constexpr int kPqsTailMaxVars = 12;  // 3 x 2^12 x 8 B = 96 KB of shared memory (k = 20: two k_pqs_multi passes, then the tail)
 template <class A>
 __global__ void __launch_bounds__(kThreads) k_pqs_tail(FieldDesc f, const uint64_t* __restrict__ P, const uint64_t* __restrict__ Q,
                                                        const uint64_t* __restrict__ S, uint32_t m, const uint64_t* __restrict__ challenges,
