@@ -95,7 +95,28 @@ def cfg2(p):
     host = m.to_evaluations_mont()
     t_e2e, _ = timed(lambda: T.vsbw_multilinear_from_evaluations(F, host, r), reps=3, warm=1)
     nbytes = (1 << v) * 8 * F.n
-    return {"config": "configs[1]: MLE evaluation, 2^24 evals, random point (vsbw order), eq table by doubling", "field_bits": F.bits,
+    # raw C-ABI call with the point already in Montgomery limbs (what a Rust caller issues): no Python int <-> limb conversion
+    from thaler_study_b200._lib import check, lib, u64p
+    pt = F.to_mont(r)
+    out = np.zeros((1, F.n), dtype=np.uint64)
+    raw = []
+    for _ in range(30):
+        t0 = time.perf_counter()
+        check(lib.scb_mle_evaluate_be(m._h, pt.ctypes.data_as(u64p), v, out.ctypes.data_as(u64p)))
+        raw.append(time.perf_counter() - t0)
+    t_raw = sorted(raw)[len(raw) // 2]
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    # 4-limb fields: the integer pipe binds (64 wide multiply-adds per entry + row reductions at 9.31 T/s, profiles/r02_mont29.md)
+    t_int = (1 << v) * 90 / 9.31e12 if F.n == 4 else 0.0
+    roof = {"bound": "hbm", "achieved": nbytes / t_raw / 1e9, "peak": peak, "unit": "GB/s", "frac": nbytes / t_raw / 1e9 / peak, "traffic": None,
+            "peak_source": peak_src, "call_ms": t_raw * 1e3, "t_hbm_bound_ms": nbytes / (peak * 1e9) * 1e3, "t_integer_bound_ms": t_int * 1e3 or None,
+            "frac_of_slower_bound": max(nbytes / (peak * 1e9), t_int) / t_raw,
+            "note": "whole synchronous C-ABI call (launch + kernel + wait), not the kernel alone; an empty launch + wait costs 9.5 us on these boxes"}
+    return {"config": "configs[1]: MLE evaluation, 2^24 evals, random point (vsbw order), eq table by doubling", "field_bits": F.bits, "roofline": roof,
             "checks": {"be==le(reversed)": be == le, "eq_table==24_folds": be == folded},
             "device_resident_ms": t_dev * 1e3, "device_resident_GBs": nbytes / t_dev / 1e9, "best_ms": t_min * 1e3,
             "device_span_ms(cuda events)": t_ev * 1e3, "device_span_GBs": nbytes / t_ev / 1e9,
@@ -145,7 +166,12 @@ def cfg4(p=P28):
     t_prove, _ = timed(lambda: T.generate_transcript(T.Prover(g)), reps=3, warm=1)
     return {"config": "configs[3]: triangle-counting sum-check, random 1024-node graph (30 rounds)", "field_bits": F.bits, "modulus": p,
             "checks": {"c_1==6*triangles": c1 == tri6_exact % p and tri6_exact < p, "float_check": tri6 == tri6_exact, "verified": ok},
-            "triangles": tri6_exact // 6, "prove_ms": t_prove * 1e3, "first_call_ms": t_first * 1e3}
+            "triangles": tri6_exact // 6, "prove_ms": t_prove * 1e3, "first_call_ms": t_first * 1e3,
+            "roofline": {"bound": "integer + latency", "t_integer_bound_ms": float(n) ** 3 / 9.31e12 * 1e3,
+                         "note": "n^3 wide multiply-adds of the one field matmul (M = f2 f1, tri.cuh) at the measured 9.31 T/s multiplier peak; the matmul launch takes "
+                                 "0.216 ms (profiles/r02_launches_triangle_mle.csv), the other ~0.8 ms are 30 Fiat-Shamir rounds of 3-4 dependent small launches each "
+                                 "(~9.5 us launch + wait floor per synchronous call, profiles/r02_launch_latency.jsonl)",
+                         "frac_of_integer_bound": float(n) ** 3 / 9.31e12 / t_prove}}
 
 
 if __name__ == "__main__":
