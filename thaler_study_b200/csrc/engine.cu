@@ -672,7 +672,10 @@ static int eval_table_fused(Ctx* c, const FieldImpl& f, const Table& t, const ui
         constexpr size_t smem = MleFusedCfg<A>::smem_bytes;
         RC_TRY(allow_smem(kern, smem));
         const uint64_t n_rows = t.len() >> MleFusedCfg<A>::LB;
-        kern<<<occ_grid(c, kern, n_rows * 32, smem), kThreads, smem, g_stream>>>(f.d, pa, t.buf->ptr, t.nv, v_total, row0, c->partials, c->ticket, res,
+        // one-limb fields up to 2^25 entries: three CTAs per SM instead of the five that fit -- fewer table builds and partial sums on the
+        // latency-bound path (2^24: 50.6 -> 45.6 us per call, scripts/kbench_mle_bps.py); larger tables keep the full wave for bandwidth
+        const int pref = (A::N == 1 && t.nv <= 25) ? 3 : 0;
+        kern<<<occ_grid(c, kern, n_rows * 32, smem, pref), kThreads, smem, g_stream>>>(f.d, pa, t.buf->ptr, t.nv, v_total, row0, c->partials, c->ticket, res,
                                                                              peer_arg(c));
     });
     LAUNCH_CHECK();
