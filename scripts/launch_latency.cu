@@ -35,6 +35,7 @@ int main(int argc, char** argv) {
     };
     bench("small params, cudaStreamSynchronize", [&](int i) { k_small<<<1, 32, 0, s>>>(nullptr, i); cudaStreamSynchronize(s); });
     bench("1280-byte params, cudaStreamSynchronize", [&](int i) { k_big<<<1, 32, 0, s>>>(b, nullptr, i); cudaStreamSynchronize(s); });
+    bench("small params, spin on cudaStreamQuery", [&](int i) { k_small<<<1, 32, 0, s>>>(nullptr, i); while (cudaStreamQuery(s) == cudaErrorNotReady) {} });
     bench("small params, host polls a mapped flag", [&](int i) { k_small<<<1, 32, 0, s>>>(flag, (uint64_t)i + 5); while (*flag != (uint64_t)i + 5) {} });
     bench("1280-byte params, host polls a mapped flag", [&](int i) { k_big<<<1, 32, 0, s>>>(b, flag, (uint64_t)i + 5); while (*flag != (uint64_t)i + 5) {} });
     bench("grid of 1184 CTAs x 256, cudaStreamSynchronize", [&](int i) { k_small<<<1184, 256, 0, s>>>(nullptr, i); cudaStreamSynchronize(s); });
