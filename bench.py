@@ -188,6 +188,14 @@ def pair_pass_stats(T):
     return {"launches": n.value, "total_ms": ms.value}
 
 
+def grid_pass_stats(T):
+    import ctypes as C
+
+    n, ms, wg, wp = C.c_uint64(), C.c_double(), C.c_uint64(), C.c_uint64()
+    T.lib.scb_grid_pass_stats(C.byref(n), C.byref(ms), C.byref(wg), C.byref(wp))
+    return {"launches": n.value, "total_ms": ms.value, "w21_grid": wg.value, "w21_pair": wp.value}
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -400,13 +408,14 @@ def run_ours(args):
         clocks = sampler.stop() if sampler else None  # samples cover exactly the timed region
         res = resident_stats(T)  # CUDA-event time of the resident kernels launched inside the timed region
         pst = pair_pass_stats(T)
+        gst = grid_pass_stats(T)
         ms = ev0.elapsed_time(ev1) / steps
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         verified = all_true(verify(transcript, g, v_local))  # the LAST TIMED proof, not a separate run
-        return {"ms": ms, "launches": launches, "clocks": clocks, "res": res, "pass": pst, "verified": verified, "g": g, "tabs": tabs,
+        return {"ms": ms, "launches": launches, "clocks": clocks, "res": res, "pass": pst, "gridp": gst, "verified": verified, "g": g, "tabs": tabs,
                 "transcript_bytes": sum(map(len, transcript))}
 
     # ---- the two curves
@@ -423,7 +432,7 @@ def run_ours(args):
     v, ms, g, tabs = main["v_local"], main["ms"], main["g"], main["tabs"]
     total_entries = 1 << (v + lg)
     value = total_entries / (ms * 1e-3) / 1e6
-    res_stats, pass_stats = main["res"], main["pass"]
+    res_stats, pass_stats, grid_stats = main["res"], main["pass"], main["gridp"]
 
     # ---- sharded == single, byte for byte (N > 1): a 2^20-per-rank instance proved sharded and by rank 0 alone
     sharded_equals_single = None
@@ -453,28 +462,43 @@ def run_ours(args):
     roof = None
     steps = args.steps
     first_alone = pass_stats["launches"] == steps  # the pass over the 8-byte tables ran as its own launch
+    # option pair_w21 (K = 3, p < 2^21, first pair pass alone): the grid pass also WRITES one 8-byte word per index (the three
+    # 21-bit entries) and the first pair pass reads those words instead of the 8-byte tables (csrc/pairs.cuh)
+    w21 = first_alone and grid_stats["w21_grid"] == steps and grid_stats["w21_pair"] == steps
     if rank == 0 and F.policy == 0 and T.get_option("pairs") != 0 and res_stats["launches"] >= steps:
         peak, peak_src = hbm_peak()
         pbytes = pass_bytes(v, K, E)  # local passes over this rank's slab (sharded: until consolidation, then replicated)
+        if w21:
+            pbytes[0] = (1 << v) * 8 + K * (1 << (v - 2)) * 4
         res_ms = res_stats["total_ms"] / steps  # all resident launches of a proof (sharded: before + after consolidation)
         res_bytes = sum(pbytes[1:]) if first_alone else sum(pbytes)
-        times = []
-        for i in range(3 + max(steps, 5)):  # Prover::new's grid kernel, timed alone (call includes one sync + 128 B D2H)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            g.grid_evals()
-            b.record()
-            torch.cuda.synchronize()
-            if i >= 3:
-                times.append(a.elapsed_time(b))
-        gms = sum(times) / len(times)
-        grid_bytes = K * (1 << v) * E
-        proof_bytes = grid_bytes + sum(pbytes)  # per GPU: 8 (grid) + 8+1 (first pair pass) + 1.25*(1+1/4+..) = 18.7 B per entry-column
-        floor_bytes = 2.0 * K * (1 << v) * E  # any schedule reads the caller's 8-byte tables once before r_1 exists and once after
-        grid = {"kernel": "k_grid_sp_pf<3> (Prover::new; u64 input, register double buffer), 2^%d-entry tables" % v, "kernel_ms": gms,
-                "achieved": grid_bytes / (gms * 1e-3) / 1e9, "frac": grid_bytes / (gms * 1e-3) / 1e9 / peak,
-                "algorithmic_bytes_per_launch": grid_bytes, "traffic": ncu_traffic("k_grid_sp_pf", v, K, p), "share_of_step": gms / ms,
-                "timing": "CUDA events around the call, timed alone after the timed region (call includes one sync + 128 B D2H)"}
+        grid_bytes = K * (1 << v) * E + ((1 << v) * 8 if w21 else 0)
+        if grid_stats["launches"] == steps:  # Prover::new's grid pass as the proof ran it
+            gms = grid_stats["total_ms"] / steps
+            g_timing = "CUDA events around the launch on its stream, all %d launches of the timed region (rank 0)" % steps
+        else:
+            times = []
+            for i in range(3 + max(steps, 5)):  # timed alone (call includes one sync + 128 B D2H)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                g.grid_evals()
+                b.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    times.append(a.elapsed_time(b))
+            gms = sum(times) / len(times)
+            g_timing = "CUDA events around the call, timed alone after the timed region (call includes one sync + 128 B D2H)"
+        proof_bytes = grid_bytes + sum(pbytes)  # per GPU and entry-column: 8 (grid) + 8+1 (first pair pass) + 1.25*(1+1/4+..) = 18.7 B; w21: 16 B per index less
+        # what any schedule must move: the caller's 8-byte tables once before r_1 exists; after r_1 either the same bytes again or a
+        # narrower copy written and read back -- K entries of a b-bit field need ceil(K b / 8) bytes per index each way
+        bits = int(p).bit_length()
+        narrow = 2 * ((K * bits + 7) // 8) * (1 << v)
+        floor_bytes = K * (1 << v) * E + min(K * (1 << v) * E, narrow)
+        gname = "k_grid_sp_pf_w21" if w21 else "k_grid_sp_pf"
+        grid = {"kernel": "%s (Prover::new: the 16 grid sums that yield c_1, g_1 and g_2; u64 input, register double buffer%s), 2^%d-entry tables"
+                          % (gname + ("" if w21 else "<3>"), "; also writes one 8-byte word of three 21-bit entries per index" if w21 else "", v),
+                "kernel_ms": gms, "achieved": grid_bytes / (gms * 1e-3) / 1e9, "frac": grid_bytes / (gms * 1e-3) / 1e9 / peak,
+                "algorithmic_bytes_per_launch": grid_bytes, "traffic": ncu_traffic(gname, v, K, p), "share_of_step": gms / ms, "timing": g_timing}
         resident = {"kernel": "k_persist_pairs_sp<3> (the remaining pair passes, %d resident launch(es) per proof)" % (res_stats["launches"] // steps),
                     "kernel_ms": res_ms, "algorithmic_bytes_per_launch": res_bytes, "achieved": res_bytes / (res_ms * 1e-3) / 1e9,
                     "frac": res_bytes / (res_ms * 1e-3) / 1e9 / peak, "share_of_step": res_ms / ms,
@@ -482,25 +506,34 @@ def run_ours(args):
                     "traffic": None, "traffic_note": "ncu serialises kernel and host, so a resident kernel cannot run under it"}
         proof = {"proof_bytes_moved_per_gpu": proof_bytes, "proof_frac_of_hbm_roofline": (proof_bytes / (ms * 1e-3) / 1e9) / peak,
                  "proof_floor_bytes_per_gpu": floor_bytes, "proof_frac_vs_floor": (floor_bytes / (ms * 1e-3) / 1e9) / peak,
-                 "proof_floor_note": "any schedule must read the caller's 8-byte tables once before r_1 exists and once after: 2*K*2^v*E",
+                 "proof_floor_note": "any schedule must read the caller's 8-byte tables once before r_1 exists (K*2^v*E) and afterwards either read them "
+                                     "again or write and read back a narrower copy (2*ceil(K*bits(p)/8)*2^v)",
                  "proof_survey_bytes": 4.0 * K * (1 << v) * E,
                  "proof_survey_note": "SURVEY 8d's 4*K*2^v*E assumes one round per pass and 8-byte intermediates; two rounds per pass with "
-                                      "uint32 intermediates move fewer bytes, so a fraction against it can exceed 1 and is not reported"}
+                                      "uint32 intermediates move fewer bytes, so a fraction against it can exceed 1 and is not reported",
+                 "w21_triples": bool(w21)}
         if first_alone:
             pms = pass_stats["total_ms"] / pass_stats["launches"]
-            roof = {"bound": "hbm",
-                    "kernel": "k_pair_pass_sp<3,in=u64,out=u32> (rounds 3-4 of the proof: folds two variables of the 2^%d-entry tables and "
-                              "accumulates the 16 grid sums of the next two messages%s)" % (v, "" if world == 1 else "; finishing thread exchanges them with the peers"),
-                    "achieved": pbytes[0] / (pms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": pbytes[0] / (pms * 1e-3) / 1e9 / peak,
-                    "traffic": ncu_traffic("k_pair_pass_sp", v, K, p), "kernel_ms": pms, "algorithmic_bytes_per_launch": pbytes[0], "peak_source": peak_src,
+            pname = "k_pair_pass_sp_w21" if w21 else "k_pair_pass_sp"
+            pair = {"kernel": "%s (rounds 3-4 of the proof: folds two variables of the 2^%d-entry tables and accumulates the 16 grid sums of the next two "
+                              "messages%s)" % ("k_pair_pass_sp_w21 <in = 21-bit triples, out = u32>" if w21 else "k_pair_pass_sp<3,in=u64,out=u32>", v,
+                                               "" if world == 1 else "; finishing thread exchanges them with the peers"),
+                    "achieved": pbytes[0] / (pms * 1e-3) / 1e9, "frac": pbytes[0] / (pms * 1e-3) / 1e9 / peak,
+                    "traffic": ncu_traffic(pname, v, K, p), "kernel_ms": pms, "algorithmic_bytes_per_launch": pbytes[0],
                     "timing": "CUDA events around the launch on its stream, all %d launches of the timed region (rank 0)" % pass_stats["launches"],
-                    "share_of_step": pms / ms, "grid_kernel_alone": grid, "resident_kernel": resident}
+                    "share_of_step": pms / ms}
+            # the dominant kernel of the step heads the block; the other two follow
+            top, other_key, other = (grid, "first_pair_pass_kernel", pair) if gms >= pms else (pair, "grid_kernel", grid)
+            roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved"], "peak": peak, "unit": "GB/s", "frac": top["frac"],
+                    "traffic": top["traffic"], "kernel_ms": top["kernel_ms"], "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"],
+                    "peak_source": peak_src, "timing": top["timing"], "share_of_step": top["share_of_step"], other_key: other,
+                    "resident_kernel": resident}
         else:
             roof = {"bound": "hbm", "kernel": resident["kernel"], "achieved": resident["achieved"], "peak": peak, "unit": "GB/s",
                     "frac": resident["frac"], "traffic": None, "traffic_note": resident["traffic_note"], "kernel_ms": res_ms,
                     "algorithmic_bytes_per_launch": res_bytes, "peak_source": peak_src,
                     "timing": "CUDA events around the launches on their stream, all %d launches of the timed region (rank 0)" % res_stats["launches"],
-                    "share_of_step": res_ms / ms, "latency_us": resident["latency_us"], "grid_kernel_alone": grid}
+                    "share_of_step": res_ms / ms, "latency_us": resident["latency_us"], "grid_kernel": grid}
         roof.update(proof)
     elif rank == 0:
         roof = generic_roofline(T, torch, F, g, v, K, p, ms, steps, res_stats, world)

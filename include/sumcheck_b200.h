@@ -234,6 +234,9 @@ int scb_resident_stats(uint64_t* launches, double* total_kernel_ms, uint32_t* la
                        double* last_turn_us, uint32_t cap);
 /* launches and summed CUDA-event kernel time of the stand-alone pair passes (scb_poly_pair_pass) since the last reset */
 int scb_pair_pass_stats(uint64_t* launches, double* total_kernel_ms);
+/* the same for the grid passes (scb_poly_grid_evals, Prover::new), and how many grid / pair passes wrote / read the
+ * 21-bit triples of option pair_w21 (K = 3 tables over a field of at most 21 bits; csrc/pairs.cuh) */
+int scb_grid_pass_stats(uint64_t* launches, double* total_kernel_ms, uint64_t* w21_grid_launches, uint64_t* w21_pair_launches);
 void scb_resident_stats_reset(void);
 
 /* ------------------------------------------------------------------ round-message algebra (host) */

@@ -121,6 +121,48 @@ def test_pair_kernel_matches_one_round_per_pass():
     assert len(set(o.stdout for o in outs)) == 1
 
 
+def test_w21_triples_match_the_8_byte_first_pass():
+    """Option pair_w21 (K = 3 tables over a field of at most 21 bits, first pair pass as its own launch): Prover::new's grid
+    pass also writes word i = A[i] | B[i] << 21 | C[i] << 42 and the pair pass reads those words instead of the caller's
+    8-byte tables (csrc/pairs.cuh).  Transcripts must not depend on it -- switched off, on, and on with pipelined loads --
+    and the stats must show that the triple kernels really ran exactly where they apply (not for K != 3, not for a
+    28-bit field).  Includes tables of p - 1 everywhere (all 21 bits of every field of a word set)."""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import ctypes as C, hashlib, numpy as np\n"
+        "import thaler_study_b200 as T; T.options_from_env()\n"
+        "def w21():\n"
+        "    a, b = C.c_uint64(), C.c_uint64()\n"
+        "    T.lib.scb_grid_pass_stats(None, None, C.byref(a), C.byref(b)); return a.value, b.value\n"
+        "for p, v, K, applies in ((1572869, 20, 3, 1), (1572869, 17, 3, 1), (1572869, 13, 3, 1), (1572869, 12, 3, 1), (5, 14, 3, 1), (389, 15, 3, 1),\n"
+        "                         (1572869, 11, 3, 0), (1572869, 16, 2, 0), (1572869, 16, 4, 0), (268435399, 16, 3, 0)):\n"
+        "    F = T.Field(p)\n"
+        "    T.lib.scb_resident_stats_reset()\n"
+        "    g = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, v, 90 + k) for k in range(K)])\n"
+        "    tr = T.generate_transcript(T.Prover(g))\n"
+        "    assert T.verify_transcript(tr, T.Verifier(v, g))\n"
+        "    used = w21()\n"
+        "    want = (1, 1) if (applies and T.get_option('pair_w21') != 0) else (0, 0)\n"
+        "    assert used == want, (p, v, K, used, want)\n"
+        "    print(hashlib.sha256(b''.join(tr)).hexdigest())\n"
+        "p = 1572869; F = T.Field(p)\n"
+        "for pat in ([p - 1], [0, p - 1, p - 1, 0, 1]):\n"
+        "    tabs = [T.DenseMultilinearExtension.from_evaluations_vec(F, 18, np.resize(np.array(pat[k %% len(pat):] + pat[:k %% len(pat)], dtype=np.uint64), 1 << 18)) for k in range(3)]\n"
+        "    g = T.ProductMLE.new(tabs)\n"
+        "    tr = T.generate_transcript(T.Prover(g))\n"
+        "    assert T.verify_transcript(tr, T.Verifier(18, g))\n"
+        "    print(hashlib.sha256(b''.join(tr)).hexdigest())\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    outs = []
+    for env_add in ({"SCB_PAIR_W21": "0"}, {"SCB_PAIR_W21": "1"}, {"SCB_PAIR_W21": "2"}):
+        env = dict(os.environ, SCB_PAIR_FIRST_ALONE="12", **env_add)
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600))
+    for o in outs:
+        assert o.returncode == 0, o.stderr[-2000:]
+    assert len(outs[0].stdout.split()) == 12
+    assert len(set(o.stdout for o in outs)) == 1
+
+
 # ----------------------------------------------------------------------------- the resident-kernel entry points, directly
 def _mont1(F, x):
     return int(F.to_mont([x])[0, 0])

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_packed_upload_scheduler_on_a_memcpy_backend(k, nv, chunk_log2, workers, raw_lane):
     """host/hostpack.hpp: pack workers take chunks from the front, the raw lane from the back; every entry must arrive
     narrowed at its place exactly once (no device involved: the back end copies into host memory)."""
-    for seed in (1, 2, 3):
+    for seed in (1, 2, 3, 5, 6, 7):  # bit 0: streaming stores, bit 1: 21-bit wire format, bit 2: software prefetch
         _lib.check(_lib.lib.scb_host_pack_selftest(k, nv, chunk_log2, workers, raw_lane, seed))
 
 

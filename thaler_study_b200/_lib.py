@@ -89,6 +89,7 @@ SIGNATURES = {
     "scb_poly_resident_pairs": (C.c_int, [vp, u64p, u64p, C.c_uint32, PAIR_CB, vp, u32p, C.POINTER(vp)]),
     "scb_resident_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_double), u32p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint32]),
     "scb_pair_pass_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+    "scb_grid_pass_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "scb_resident_stats_reset": (None, []),
     "scb_poly_resident_rounds": (C.c_int, [vp, u64p, C.c_uint32, C.c_uint32, ROUND_CB, vp, u32p, C.POINTER(vp)]),
     "scb_evals_to_univariate": (C.c_int, [vp, C.c_uint32, u64p, C.c_uint32, u64p, u64p, C.c_uint32, u32p]),

@@ -290,6 +290,17 @@ struct scb_poly {
     // triangle_counting::G while an x variable is left: M[z][x] = sum_y f2[z][y] f1[y][x] (tri.cuh), index (z << xn) | x
     bool has_aux = false;
     Table aux;
+    // pairs.cuh, 21-bit triples: word i = t[0][i] | t[1][i] << 21 | t[2][i] << 42, written by the grid pass of a prover that will
+    // run the first pair pass as its own launch.  Valid only for the buffers it was built from (w21_ok): copies of this struct
+    // with other tables simply ignore it.
+    mutable BufRef w21;
+    mutable const uint64_t* w21_src[3] = {nullptr, nullptr, nullptr};
+    bool w21_ok() const {
+        if (!w21 || t.size() != 3) return false;
+        for (int k = 0; k < 3; ++k)
+            if (t[k].p32 || !t[k].buf || t[k].buf->ptr != w21_src[k] || t[k].nv != t[0].nv) return false;
+        return true;
+    }
     bool any_packed() const {
         for (const Table& x : t)
             if (x.p32) return true;

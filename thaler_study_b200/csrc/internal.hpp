@@ -28,6 +28,8 @@ void set_error(const char* fmt, ...);
 bool resident_rounds_ok(const struct ::scb_poly* p, bool need_grid);
 // engine.cu: can this polynomial's proof run two rounds per pass over the tables (pairs.cuh)?
 bool pair_passes_ok(const struct ::scb_poly* p);
+// engine.cu: scb_poly_grid_evals; make_w21: also leave the 21-bit triples for a first pair pass that runs alone (pairs.cuh)
+int poly_grid_evals_ex(const struct ::scb_poly* p, uint64_t* out_elems, bool make_w21);
 // engine.cu: are this polynomial's tables stored as packed uint32 (packed.cuh)?
 bool poly_is_packed(const struct ::scb_poly* p);
 

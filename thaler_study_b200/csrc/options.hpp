@@ -15,6 +15,7 @@ namespace scb {
     X(pairs, 1)                /* two rounds per pass over the tables (pairs.cuh) */                                        \
     X(pair_resident, 1)        /* pair passes inside one resident kernel; 0: one ordinary launch per pass (ncu) */          \
     X(pair_first_alone, 26)    /* tables of >= 2^n entries: the pass over 8-byte tables is its own launch; 0: never */     \
+    X(pair_w21, 2)             /* K = 3, p < 2^21, first pair pass alone: the grid pass writes 21-bit triples for it (2: that pass prefetches, 2 CTAs/SM; 1: 3 CTAs/SM); 0: off */ \
     X(pair_stage, 0)           /* cp.async staging in the pair kernels (measured slower) */                                 \
     X(pair_pipe, 1)            /* resident pair kernel: loads pipelined across tables */                                    \
     X(pair_bps, 0)             /* resident pair kernel: cap on CTAs per SM; 0: occupancy calculator */                      \
@@ -51,6 +52,7 @@ namespace scb {
     X(host_pack_raw, 1)        /* device-side narrowing lane; 2: also from pageable memory (tests) */                       \
     X(host_pack_raw_slots, 3)  /* chunks the device-side lane keeps in flight (1..8) */                                     \
     X(host_pack_wire, 21)      /* 21: three 21-bit entries per 64-bit word when p < 2^21; 32: uint32 */                     \
+    X(host_pack_prefetch, 4096) /* pack threads prefetch this many bytes ahead of their loads; 0: off (hostpack.hpp) */                     \
     X(host_pack_nt, 0)         /* streaming stores into the staging buffers */                                              \
     X(local_ranks, 1)          /* processes sharing this box's host cores (set by the sharded driver) */                    \
     X(sha_scalar, 0)           /* portable SHA-256 compression instead of the x86 SHA extensions */                         \

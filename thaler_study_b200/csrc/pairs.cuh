@@ -537,6 +537,105 @@ __global__ void __launch_bounds__(kThreads, 2)
     grid_canon<K>(ar, c32, acc);
     grid_reduce_finish<PolSP, NG>(ar, acc, partials, ticket, out, GridConsts<K>::msg_k, &peer);
 }
+// ------------------------------------------------------------------------------------------ 21-bit triples
+// K = 3 tables over a field of at most 21 bits (the reference's F_1572869): entry i of all three tables fits ONE
+// 64-bit word, A[i] | B[i] << 21 | C[i] << 42.  Prover::new's grid pass has every entry in registers anyway, so it
+// writes that word (8 bytes per index instead of the 24 it read); the first pair pass -- the one that would read the
+// caller's 8-byte tables a second time -- then streams 8 bytes per index instead of 24.  Per index a proof moves
+// 24 + 8 (grid pass) + 8 + 3 (pair pass) + 3.75 (1 + 1/4 + ...) = 48 bytes instead of 24 + 24 + 3 + 3.75 + ... = 56,
+// and the index structure (adjacent pairs, power-of-two groups) is untouched.  Same field elements: the packed word
+// holds the canonical values the second read would have fetched.
+constexpr uint32_t kW21Mask = 0x1fffffu;
+__global__ void __launch_bounds__(kThreads, 2)
+    k_grid_sp_pf_w21(FieldDesc f, TabsIn<3> in, uint64_t* __restrict__ w21, uint64_t n_groups, uint64_t* partials, unsigned int* ticket,
+                     uint64_t* out, PeerArg peer) {
+    constexpr int K = 3, NG = (K + 1) * (K + 1);
+    const PolSP ar(f);
+    uint64_t acc[NG];
+#pragma unroll
+    for (int i = 0; i < NG; ++i) acc[i] = 0;
+    const uint32_t c32 = (uint32_t)((1ull << 32) % ar.p);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t w[K][4];
+    if (g < n_groups) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) ld_words<4>(in.p[k] + g * 4, w[k]);
+    }
+    uint32_t it = 0;
+    while (g < n_groups) {
+        if ((++it % GridConsts<K>::fold_every) == 0) grid_fold(c32, acc);
+        uint32_t c[K][4];
+        uint64_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) c[k][q] = (uint32_t)w[k][q];
+            o[q] = w[0][q] | (w[1][q] << 21) | (w[2][q] << 42);  // canonical entries are below p < 2^21
+        }
+        st_words<4>(w21 + g * 4, o);
+        const uint64_t gn = g + stride;
+        if (gn < n_groups) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) ld_words<4>(in.p[k] + gn * 4, w[k]);
+        }
+        grid_accumulate<K>(ar, c, acc);
+        g = gn;
+    }
+    grid_canon<K>(ar, c32, acc);
+    grid_reduce_finish<PolSP, NG>(ar, acc, partials, ticket, out, GridConsts<K>::msg_k, &peer);
+}
+// the pair pass over the triple words: 16 words in, 3 x 4 packed uint32 out per thread-iteration.
+// PF: the next thread-iteration's 128 bytes are in flight while this one is folded (two CTAs per SM instead of three).
+template <bool PF>
+__global__ void __launch_bounds__(kThreads, (PF ? 2 : 3))
+    k_pair_pass_sp_w21(FieldDesc f, const uint64_t* __restrict__ w21, TabsOut<3> outp, ElemArg ra_arg, ElemArg rb_arg, uint64_t n_groups,
+                       uint64_t* partials, unsigned int* ticket, uint64_t* out, PeerArg peer) {
+    constexpr int K = 3, NG = (K + 1) * (K + 1);
+    const PolSP ar(f);
+    const PolSP::FoldC ra = ar.fold_const(ar.from_words(ra_arg.w)), rb = ar.fold_const(ar.from_words(rb_arg.w));
+    uint64_t acc[NG];
+#pragma unroll
+    for (int i = 0; i < NG; ++i) acc[i] = 0;
+    const uint32_t c32 = (uint32_t)((1ull << 32) % ar.p);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t w[16], wn[PF ? 16 : 1];
+    if (PF && g < n_groups) ld_words<16>(w21 + g * 16, w);
+    uint32_t it = 0;
+    while (g < n_groups) {
+        if ((++it % GridConsts<K>::fold_every) == 0) grid_fold(c32, acc);
+        const uint64_t gn = g + stride;
+        if constexpr (PF) {
+            if (gn < n_groups) ld_words<16>(w21 + gn * 16, wn);
+        } else {
+            ld_words<16>(w21 + g * 16, w);
+        }
+        uint32_t c[K][4];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            uint32_t t[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) t[q] = (uint32_t)(w[q] >> (21 * k)) & kW21Mask;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t lo = ar.fold_c(t[4 * q], t[4 * q + 1], ra), hi = ar.fold_c(t[4 * q + 2], t[4 * q + 3], ra);
+                c[k][q] = ar.fold_c(lo, hi, rb);
+            }
+            uint64_t o[2] = {(uint64_t)c[k][0] | ((uint64_t)c[k][1] << 32), (uint64_t)c[k][2] | ((uint64_t)c[k][3] << 32)};
+            st_words<2>(outp.p[k] + g * 2, o);
+        }
+        grid_accumulate<K>(ar, c, acc);
+        if constexpr (PF) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) w[q] = wn[q];
+        }
+        g = gn;
+    }
+    grid_canon<K>(ar, c32, acc);
+    grid_reduce_finish<PolSP, NG>(ar, acc, partials, ticket, out, GridConsts<K>::msg_k, &peer);
+}
+
 // K6b  one pair pass as its own launch (what the resident kernel runs per pass; used for profiling and as the
 // non-resident path).
 template <int K, bool IN32, bool STAGED>

@@ -216,8 +216,16 @@ static int prover_new_impl(const scb_poly* g, scb_peers* peers, uint32_t world, 
         // GPUs by the kernel's finishing thread)
         uint64_t w[32];
         {
+            // when the first pair pass will run as its own launch (the condition of scb_fs_generate_transcript), the grid pass
+            // may leave it a narrower copy of the tables (21-bit triples, pairs.cuh)
+            uint32_t live = 0;
+            RC_TRY(scb_poly_num_vars(p->g, &live));
+            const uint32_t first_alone = (uint32_t)opt(OPT_pair_first_alone);
+            const bool resident = opt(OPT_pair_resident) != 0;  // 0: every pass is an ordinary launch (a sharded proof consolidates first)
+            const bool alone_next = !poly_is_packed(p->g) && live >= 4 &&
+                                    (resident ? first_alone != 0 && live >= first_alone && (!p->sharded || live > p->consolidate_at) : !p->sharded);
             PeersScope scope(p->sharded ? p->peers : nullptr);
-            RC_TRY(scb_poly_grid_evals(p->g, w));
+            RC_TRY(poly_grid_evals_ex(p->g, w, alone_next));
         }
         const uint32_t np = p->np;
         p->grid.resize((size_t)np * np);
