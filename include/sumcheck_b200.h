@@ -136,7 +136,8 @@ int scb_poly_matmul_g(const scb_mle* f_a, const scb_mle* f_b, scb_poly** out);
  * tables use (scb_poly_allow_packed).  SCB_EINVAL if an entry is not a canonical field element (>= p).  Options
  * (scb_set_option): host_pack = 0 (plain copies), host_pack_threads, host_pack_min_vars, host_pack_chunk_log2,
  * host_pack_raw = 0 (no device-side lane; it is also skipped when a table is not in pinned memory), host_pack_wire = 32
- * (uint32 on the wire), host_pack_nt = 1 (streaming stores into the staging buffers). */
+ * (uint32 on the wire), host_pack_nt = 1 (streaming stores into the staging buffers), host_pack_prefetch = bytes the pack
+ * threads prefetch ahead of their loads (default 4096; 0 = none). */
 int scb_poly_product_from_host(const scb_field* f, uint32_t k, uint32_t num_vars, const uint64_t* const* host_tables, scb_poly** out);
 /* scb_mle_from_host and the two *_multilinear_from_evaluations calls take the same narrowing upload for such tables
  * when the process is the only rank of its box (option local_ranks = 1, the default; the sharded driver sets it) and
