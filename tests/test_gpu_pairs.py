@@ -124,7 +124,8 @@ def test_pair_kernel_matches_one_round_per_pass():
 def test_w21_triples_match_the_8_byte_first_pass():
     """Option pair_w21 (K = 3 tables over a field of at most 21 bits, first pair pass as its own launch): Prover::new's grid
     pass also writes word i = A[i] | B[i] << 21 | C[i] << 42 and the pair pass reads those words instead of the caller's
-    8-byte tables (csrc/pairs.cuh).  Transcripts must not depend on it -- switched off, on, and on with pipelined loads --
+    8-byte tables (csrc/pairs.cuh).  Transcripts must not depend on it -- switched off, and on in its four variants (three /
+    two CTAs per SM, nested folds / the bilinear two-variable fold; the default is the last) --
     and the stats must show that the triple kernels really ran exactly where they apply (not for K != 3, not for a
     28-bit field).  Includes tables of p - 1 everywhere (all 21 bits of every field of a word set)."""
     code = (
@@ -154,7 +155,7 @@ def test_w21_triples_match_the_8_byte_first_pass():
         "    print(hashlib.sha256(b''.join(tr)).hexdigest())\n"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
     outs = []
-    for env_add in ({"SCB_PAIR_W21": "0"}, {"SCB_PAIR_W21": "1"}, {"SCB_PAIR_W21": "2"}):
+    for env_add in ({"SCB_PAIR_W21": "0"}, {"SCB_PAIR_W21": "1"}, {"SCB_PAIR_W21": "2"}, {"SCB_PAIR_W21": "4"}, {}):
         env = dict(os.environ, SCB_PAIR_FIRST_ALONE="12", **env_add)
         outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600))
     for o in outs:

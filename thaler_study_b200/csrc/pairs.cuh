@@ -585,15 +585,43 @@ __global__ void __launch_bounds__(kThreads, 2)
     grid_canon<K>(ar, c32, acc);
     grid_reduce_finish<PolSP, NG>(ar, acc, partials, ticket, out, GridConsts<K>::msg_k, &peer);
 }
+// Two variables folded at once: the nested folds lo = t0 + ra (t1 - t0), hi = t2 + ra (t3 - t2), c = lo + rb (hi - lo) are the
+// bilinear form c = w00 t0 + w10 t1 + w01 t2 + w11 t3 with w00 = (1 - ra)(1 - rb), w10 = ra (1 - rb), w01 = (1 - ra) rb,
+// w11 = ra rb -- the same field element, so the same canonical value.  With the weights as per-pass constants W = w 2^32
+// (fold_const's form) the four products go unreduced into one 64-bit sum (< 4 p^2 < 2^58) and ONE Montgomery step brings it
+// back: 4 wide multiply-adds + mul.lo + mad.wide + one conditional subtraction (sum / 2^32 + p < 1.25 p for p < 2^28)
+// instead of 3 x (wide multiply + mul.lo + mad.wide + two adds + two conditional subtractions).
+struct Fold2C {
+    uint32_t w00, w10, w01, w11;
+};
+__device__ __forceinline__ Fold2C fold2_const(const PolSP& ar, const FieldDesc& f, uint32_t ra_m, uint32_t rb_m) {  // Montgomery challenges
+    const uint32_t one_m = (uint32_t)f.one[0];
+    const uint32_t na = ar.sub(one_m, ra_m), nb = ar.sub(one_m, rb_m);
+    Fold2C c;
+    c.w00 = ar.fold_const(ar.mul(na, nb));
+    c.w10 = ar.fold_const(ar.mul(ra_m, nb));
+    c.w01 = ar.fold_const(ar.mul(na, rb_m));
+    c.w11 = ar.fold_const(ar.mul(ra_m, rb_m));
+    return c;
+}
+__device__ __forceinline__ uint32_t fold2(const PolSP& ar, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, const Fold2C& c) {
+    uint64_t s = (uint64_t)t0 * c.w00;
+    s = mad_wide(t1, c.w10, s);
+    s = mad_wide(t2, c.w01, s);
+    s = mad_wide(t3, c.w11, s);
+    return ar.reduce_once(ar.redc32(s));
+}
 // the pair pass over the triple words: 16 words in, 3 x 4 packed uint32 out per thread-iteration.
 // PF: the next thread-iteration's 128 bytes are in flight while this one is folded (two CTAs per SM instead of three).
-template <bool PF>
+// F2: the two folds as one bilinear form (fold2) instead of three nested folds.
+template <bool PF, bool F2>
 __global__ void __launch_bounds__(kThreads, (PF ? 2 : 3))
     k_pair_pass_sp_w21(FieldDesc f, const uint64_t* __restrict__ w21, TabsOut<3> outp, ElemArg ra_arg, ElemArg rb_arg, uint64_t n_groups,
                        uint64_t* partials, unsigned int* ticket, uint64_t* out, PeerArg peer) {
     constexpr int K = 3, NG = (K + 1) * (K + 1);
     const PolSP ar(f);
     const PolSP::FoldC ra = ar.fold_const(ar.from_words(ra_arg.w)), rb = ar.fold_const(ar.from_words(rb_arg.w));
+    const Fold2C w2 = fold2_const(ar, f, ar.from_words(ra_arg.w), ar.from_words(rb_arg.w));
     uint64_t acc[NG];
 #pragma unroll
     for (int i = 0; i < NG; ++i) acc[i] = 0;
@@ -619,8 +647,12 @@ __global__ void __launch_bounds__(kThreads, (PF ? 2 : 3))
             for (int q = 0; q < 16; ++q) t[q] = (uint32_t)(w[q] >> (21 * k)) & kW21Mask;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const uint32_t lo = ar.fold_c(t[4 * q], t[4 * q + 1], ra), hi = ar.fold_c(t[4 * q + 2], t[4 * q + 3], ra);
-                c[k][q] = ar.fold_c(lo, hi, rb);
+                if constexpr (F2) {
+                    c[k][q] = fold2(ar, t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3], w2);
+                } else {
+                    const uint32_t lo = ar.fold_c(t[4 * q], t[4 * q + 1], ra), hi = ar.fold_c(t[4 * q + 2], t[4 * q + 3], ra);
+                    c[k][q] = ar.fold_c(lo, hi, rb);
+                }
             }
             uint64_t o[2] = {(uint64_t)c[k][0] | ((uint64_t)c[k][1] << 32), (uint64_t)c[k][2] | ((uint64_t)c[k][3] << 32)};
             st_words<2>(outp.p[k] + g * 2, o);
