@@ -1,6 +1,6 @@
 #!/bin/bash
-# round 2, third session: the round-end sequence with the final library (21-bit triples, prefetching pack threads), then the
-# ncu launch list of the bench command and --set full captures of the two new kernels
+# round 2, third session: the round-end sequence with the final library (21-bit triples + bilinear fold, stand-alone first pair
+# pass from 2^24 entries, prefetching pack threads)
 set -u
 mkdir -p gpurun_out
 P=gpurun_out/r2i
@@ -15,7 +15,5 @@ import json
 d = json.load(open("gpurun_out/r2i_bench.json"))
 print({k: d.get(k) for k in ("value", "ms_per_step", "verified")}, "e2e", d["e2e"]["ms_per_step"], d["e2e"].get("upload"), "roof", d["roofline"]["kernel"][:40], d["roofline"]["frac"])
 PY
-for v in 25 24; do for fa in 26 $v; do SCB_PAIR_FIRST_ALONE=$fa timeout 120 python scripts/kbench_w21.py $v 0,3,0,3 >> ${P}_first_alone.jsonl 2>> ${P}_first_alone.err; done; done
-cat ${P}_first_alone.jsonl
 timeout 600 python scripts/bench_gkr.py > ${P}_gkr.json 2> ${P}_gkr.err
 timeout 900 python scripts/bench_configs.py > ${P}_configs.jsonl 2> ${P}_configs.err

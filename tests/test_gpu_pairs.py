@@ -153,6 +153,13 @@ def test_w21_triples_match_the_8_byte_first_pass():
         "    tr = T.generate_transcript(T.Prover(g))\n"
         "    assert T.verify_transcript(tr, T.Verifier(18, g))\n"
         "    print(hashlib.sha256(b''.join(tr)).hexdigest())\n"
+        # default threshold (2^26) again: with the triples the first pass is a launch of its own from 2^24 entries (pair_w21_alone)
+        "T.set_option('pair_first_alone', 26); T.lib.scb_resident_stats_reset()\n"
+        "g = T.ProductMLE.new([T.DenseMultilinearExtension.synthetic(F, 24, 60 + k) for k in range(3)])\n"
+        "tr = T.generate_transcript(T.Prover(g))\n"
+        "assert T.verify_transcript(tr, T.Verifier(24, g))\n"
+        "assert w21() == ((1, 1) if T.get_option('pair_w21') != 0 else (0, 0)), w21()\n"
+        "print(hashlib.sha256(b''.join(tr)).hexdigest())\n"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
     outs = []
     for env_add in ({"SCB_PAIR_W21": "0"}, {"SCB_PAIR_W21": "1"}, {"SCB_PAIR_W21": "2"}, {"SCB_PAIR_W21": "4"}, {}):
@@ -160,7 +167,7 @@ def test_w21_triples_match_the_8_byte_first_pass():
         outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600))
     for o in outs:
         assert o.returncode == 0, o.stderr[-2000:]
-    assert len(outs[0].stdout.split()) == 12
+    assert len(outs[0].stdout.split()) == 13
     assert len(set(o.stdout for o in outs)) == 1
 
 

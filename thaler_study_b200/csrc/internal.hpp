@@ -30,6 +30,8 @@ bool resident_rounds_ok(const struct ::scb_poly* p, bool need_grid);
 bool pair_passes_ok(const struct ::scb_poly* p);
 // engine.cu: scb_poly_grid_evals; make_w21: also leave the 21-bit triples for a first pair pass that runs alone (pairs.cuh)
 int poly_grid_evals_ex(const struct ::scb_poly* p, uint64_t* out_elems, bool make_w21);
+// engine.cu: did the grid pass leave 21-bit triples of this polynomial's tables (pairs.cuh)?
+bool poly_has_w21(const struct ::scb_poly* p);
 // engine.cu: are this polynomial's tables stored as packed uint32 (packed.cuh)?
 bool poly_is_packed(const struct ::scb_poly* p);
 

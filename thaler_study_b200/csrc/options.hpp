@@ -16,6 +16,7 @@ namespace scb {
     X(pair_resident, 1)        /* pair passes inside one resident kernel; 0: one ordinary launch per pass (ncu) */          \
     X(pair_first_alone, 26)    /* tables of >= 2^n entries: the pass over 8-byte tables is its own launch; 0: never */     \
     X(pair_w21, 3)             /* K = 3, p < 2^21, first pair pass alone: the grid pass writes 21-bit triples for it; that pass: 1 = 3 CTAs/SM, 2 = prefetching (2 CTAs/SM), 3 / 4 = the same with the bilinear two-variable fold (3: measured best); 0: off */ \
+    X(pair_w21_alone, 24)      /* ... with the triples the first pair pass is its own launch from 2^n entries already (2^25: 0.62 -> 0.54 ms per proof) */ \
     X(pair_stage, 0)           /* cp.async staging in the pair kernels (measured slower) */                                 \
     X(pair_pipe, 1)            /* resident pair kernel: loads pipelined across tables */                                    \
     X(pair_bps, 0)             /* resident pair kernel: cap on CTAs per SM; 0: occupancy calculator */                      \

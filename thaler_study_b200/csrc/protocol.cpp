@@ -220,7 +220,10 @@ static int prover_new_impl(const scb_poly* g, scb_peers* peers, uint32_t world, 
             // may leave it a narrower copy of the tables (21-bit triples, pairs.cuh)
             uint32_t live = 0;
             RC_TRY(scb_poly_num_vars(p->g, &live));
-            const uint32_t first_alone = (uint32_t)opt(OPT_pair_first_alone);
+            uint32_t first_alone = (uint32_t)opt(OPT_pair_first_alone);
+            // with the triples the stand-alone pass pays off on smaller tables (option pair_w21_alone); whether they apply to this
+            // polynomial is the grid pass's decision, and scb_fs_generate_transcript follows it (poly_has_w21)
+            if (first_alone != 0 && opt(OPT_pair_w21) != 0 && (uint32_t)opt(OPT_pair_w21_alone) < first_alone) first_alone = (uint32_t)opt(OPT_pair_w21_alone);
             const bool resident = opt(OPT_pair_resident) != 0;  // 0: every pass is an ordinary launch (a sharded proof consolidates first)
             const bool alone_next = !poly_is_packed(p->g) && live >= 4 &&
                                     (resident ? first_alone != 0 && live >= first_alone && (!p->sharded || live > p->consolidate_at) : !p->sharded);
@@ -592,7 +595,7 @@ extern "C" int scb_fs_generate_transcript(scb_prover* p, uint8_t* out, size_t ca
             // extra launch + wait costs less than the two gains (option pair_first_alone = 0: everything in the
             // resident kernel; n: threshold 2^n).
             const uint32_t first_alone = (uint32_t)opt(OPT_pair_first_alone);
-            const bool alone_now = resident && first_alone != 0 && live >= first_alone && !poly_is_packed(p->g) &&
+            const bool alone_now = resident && ((first_alone != 0 && live >= first_alone) || poly_has_w21(p->g)) && !poly_is_packed(p->g) && live >= 4 &&
                                    (!p->sharded || (live > p->consolidate_at && live >= 4));  // sharded: two local variables stay
             if (!resident || alone_now) {
                 if (live < 4) {  // too small for a grid pass: the per-round path below finishes the proof
