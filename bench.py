@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="which curve is the headline at N>1")
     ap.add_argument("--cpu-vars", type=int, default=24, help="log2 table size of the bounded sample in the cpu_baseline leg")
     ap.add_argument("--ref-vars", type=int, default=0, help="--impl reference: log2 table size per step (0 = the workload's own size if it fits)")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)  # mean over 10 steps (every step time is printed): one host hiccup in 5 moved the mean by 7 %
     ap.add_argument("--e2e-warmup", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
