@@ -488,7 +488,7 @@ def run_ours(args):
                     times.append(a.elapsed_time(b))
             gms = sum(times) / len(times)
             g_timing = "CUDA events around the call, timed alone after the timed region (call includes one sync + 128 B D2H)"
-        proof_bytes = grid_bytes + sum(pbytes)  # per GPU and entry-column: 8 (grid) + 8+1 (first pair pass) + 1.25*(1+1/4+..) = 18.7 B; w21: 16 B per index less
+        proof_bytes = grid_bytes + sum(pbytes)  # per GPU and entry-column: 8 (grid) + 8+1 (first pair pass) + 1.25*(1+1/4+..) = 18.7 B; w21: 8 B per index (2.7 B per entry-column) less
         # what any schedule must move: the caller's 8-byte tables once before r_1 exists; after r_1 either the same bytes again or a
         # narrower copy written and read back -- K entries of a b-bit field need ceil(K b / 8) bytes per index each way
         bits = int(p).bit_length()
