@@ -293,12 +293,20 @@ struct scb_poly {
     // pairs.cuh, 21-bit triples: word i = t[0][i] | t[1][i] << 21 | t[2][i] << 42, written by the grid pass of a prover that will
     // run the first pair pass as its own launch.  Valid only for the buffers it was built from (w21_ok): copies of this struct
     // with other tables simply ignore it.
-    mutable BufRef w21;
-    mutable const uint64_t* w21_src[3] = {nullptr, nullptr, nullptr};
+    // The slot is never copied: a clone or a folded descendant starts without it, so the 2^v x 8 bytes die with the handle they
+    // were built on (the prover's private copy) instead of being kept alive by every copy of the struct.
+    struct W21Slot {
+        BufRef buf;
+        const uint64_t* src[3] = {nullptr, nullptr, nullptr};
+        W21Slot() = default;
+        W21Slot(const W21Slot&) {}
+        W21Slot& operator=(const W21Slot&) { return *this; }
+    };
+    mutable W21Slot w21s;
     bool w21_ok() const {
-        if (!w21 || t.size() != 3) return false;
+        if (!w21s.buf || t.size() != 3) return false;
         for (int k = 0; k < 3; ++k)
-            if (t[k].p32 || !t[k].buf || t[k].buf->ptr != w21_src[k] || t[k].nv != t[0].nv) return false;
+            if (t[k].p32 || !t[k].buf || t[k].buf->ptr != w21s.src[k] || t[k].nv != t[0].nv) return false;
         return true;
     }
     bool any_packed() const {
